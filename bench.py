@@ -1,0 +1,322 @@
+#!/usr/bin/env python3
+"""
+bench.py -- env-steps/s of the batched copter step on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            (N > 1: launched by torchrun)
+  python bench.py --impl reference ...                           (CPU arm, rank 0 only)
+
+Workload (BASELINE.json configs[2], per GPU): Lander3D, fp32, 2^24 envs per GPU (weak
+scaling; the config's 16M-env batch fits one GPU), same-step auto-reset, action stream
+`lander.py --random` (1.625e-2 * N(0,1) per motor, /root/reference lander.py:42) cycled from
+a pool of pre-generated action tensors resident in HBM.  A "step" is one launch of the step
+kernel over the GPU's whole shard = k_substeps env-steps per env.
+
+One JSON line on stdout (rank 0):
+  value     env-steps/s over all ranks, inputs resident in HBM (CUDA events, max over ranks)
+  e2e       the same through the host-array API (numpy/pinned host buffers in and out,
+            H2D + kernel + D2H inside the timed region)
+  roofline  the step kernel against the measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the per-object Python port (oracle/scalar_port.py, the reference's own
+            execution style) on the box's host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'env-steps/sec (whole box) for Lander3D'
+UNIT = 'env-steps/s'
+STREAMS = ('randn', 'const', 'unif')
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--envs-per-gpu', type=int, default=1 << 24)
+    ap.add_argument('--k-substeps', type=int, default=1)
+    ap.add_argument('--variant', default='Lander3D')
+    ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'])
+    ap.add_argument('--stream', default='randn', choices=STREAMS)
+    ap.add_argument('--pool', type=int, default=4, help='distinct pre-generated action tensors')
+    ap.add_argument('--e2e-steps', type=int, default=5)
+    ap.add_argument('--cpu-seconds', type=float, default=6.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the fused-substep side measurements')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arms
+# ---------------------------------------------------------------------------------------
+def cpu_port_rate(stream, seconds, procs):
+    from oracle.scalar_port import run_parallel, run_stream
+    if procs <= 1:
+        n, el = run_stream(stream, seconds)
+        return n / el
+    return run_parallel(stream, seconds, procs)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    """The reference's CPU implementation of the path: its per-object Python execution style
+    (oracle/scalar_port.py; the reference tree itself cannot travel to the GPU box and has no
+    native code to compile), one env loop per host core."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = host_cores()
+    per_step = max(0.5, min(3.0, 60.0 / max(1, args.steps + args.warmup)))
+    rates = []
+    t0 = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        r = cpu_port_rate(args.stream, per_step, cores)
+        if i >= args.warmup:
+            rates.append(r)
+    value = sum(rates) / len(rates)
+    sample = ('%d processes x one ScalarLander env loop each, %s action stream, %.1f s per step, '
+              'reset on done' % (cores, args.stream, per_step))
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': 'Lander3D single-env Python objects on host cores', 'stream': args.stream},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'wall_s': time.perf_counter() - t0}))
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+def make_actions(torch, stream, n, a, pool, dtype, device, seed):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = []
+    for _ in range(pool):
+        if stream == 'const':
+            t = torch.full((n, a), 1.625e-2, dtype=dtype, device=device)
+        elif stream == 'randn':
+            t = 1.625e-2 * torch.randn((n, a), dtype=dtype, device=device, generator=g)
+        else:
+            t = 2 * torch.rand((n, a), dtype=dtype, device=device, generator=g) - 1
+        out.append(t.contiguous())
+    return out
+
+
+def bytes_per_launch_per_env(w, a, o):
+    """state r+w, packed meta r+w, action read, obs write, reward, done."""
+    return 2 * 12 * w + 2 * 4 + a * w + o * 4 + w + 1
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import gym_copter_b200 as g
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (the product has no CPU path)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dtype = torch.float32 if args.dtype == 'f32' else torch.float64
+    n, k = args.envs_per_gpu, args.k_substeps
+    env = g.CopterVecEnv(args.variant, n, dtype=dtype, seed=2026, env_offset=rank * n,
+                         k_substeps=k, auto_reset=True, track_stats=True)
+    A, O, w = env.action_size, env.obs_size, (4 if dtype == torch.float32 else 8)
+    actions = make_actions(torch, args.stream, n, A, args.pool, dtype, dev, 1234 + rank)
+    env.reset()
+
+    def run(e, steps):
+        for i in range(steps):
+            e.step(actions[i % len(actions)])
+
+    # ---- device-resident measurement ------------------------------------------------------
+    run(env, args.warmup)
+    env.clear_stats()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = env.launches
+    barrier()
+    with ClockSampler(local) as clk:
+        ev0.record()
+        run(env, args.steps)
+        ev1.record()
+        barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = env.launches - launches0
+    value = world * n * k * args.steps / (ms * 1e-3)
+    stats = env.stats(reduce_group=True if world > 1 else None)    # the one (optional) collective
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    b_launch = bytes_per_launch_per_env(w, A, O)
+    achieved = b_launch * n / (ms * 1e-3 / args.steps) / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': None, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650',
+                'kernel': 'copter_step_kernel<%s,%s,stats>' % (args.dtype, args.variant),
+                'bytes_per_env_per_launch': b_launch, 'env_steps_per_launch': n * k}
+
+    # ---- fused-substep side measurements (same shard, same stream) -----------------------
+    extras = {}
+    if not args.no_extras and k == 1:
+        for kk in (4, 16):
+            env.k_substeps = kk
+            run(env, 3)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps_kk = max(10, args.steps // 4)
+            before = env.stats()['env_steps']
+            e0.record()
+            run(env, steps_kk)
+            e1.record()
+            barrier()
+            ms_kk = max_over_ranks(e0.elapsed_time(e1))
+            done_steps = env.stats()['env_steps'] - before          # idle substeps are not counted
+            extras['k%d' % kk] = {'value': world * done_steps / (ms_kk * 1e-3), 'unit': UNIT,
+                                  'ms_per_launch': ms_kk / steps_kk,
+                                  'note': 'executed env-steps only (envs idle after done within a launch)'}
+        env.k_substeps = 1
+
+    # ---- end to end through the host-array API -------------------------------------------
+    h = env.host_buffers()
+    h['action'][:] = actions[0].cpu().numpy()
+    for _ in range(2):
+        env.step_host(None)
+    barrier()
+    t0 = time.perf_counter()
+    ret_sum = 0.0
+    for i in range(args.e2e_steps):
+        obs, rew, dn, _, _ = env.step_host(None)
+        ret_sum += float(rew[0])                                    # host read of the result
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {'value': world * n * k * args.e2e_steps / e2e_s, 'unit': UNIT,
+           'h2d_bytes_per_step': n * A * w, 'd2h_bytes_per_step': n * (O * 4 + w + 1),
+           'ms_per_step': e2e_s / args.e2e_steps * 1e3,
+           'api': 'CopterVecEnv.step_host (copter_step_host_%s: chunked H2D + kernel + D2H over 4 streams)' % args.dtype}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ----------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        rate = cpu_port_rate(args.stream, args.cpu_seconds, cores)
+        one = cpu_port_rate(args.stream, min(3.0, args.cpu_seconds), 1)
+        cpu = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'single_core': one,
+               'sample': '%d processes x one per-object Python Lander loop (oracle/scalar_port.py), %s stream, '
+                         '%.0f s, reset on done' % (cores, args.stream, args.cpu_seconds)}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+            'config': {'workload': '%s %s, %d envs/GPU, k_substeps=%d, same-step auto-reset, on-device Philox reset forces'
+                                   % (args.variant, args.dtype, n, k),
+                       'action_stream': args.stream, 'global_envs': world * n,
+                       'l2': 'working set %.2f GB per launch > 126 MB L2, no flush needed' % (b_launch * n / 1e9),
+                       'parallelism': 'env shards, one per GPU, no per-step communication'},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
+            'clocks': clk.summary(),
+            'episodes': {kk: stats[kk] for kk in ('episodes', 'mean_length', 'landed', 'crashed', 'oob', 'angle', 'timeout')},
+            'fused_substeps': extras,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

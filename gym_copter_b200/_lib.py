@@ -1,0 +1,97 @@
+"""
+ctypes binding of libcopter_b200.so (include/copter_b200.h).  There is NO fallback: if the
+library is missing or a launch fails, the caller gets an exception.
+"""
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, 'libcopter_b200.so')
+
+ABI_VERSION = 1
+STATS_LEN = 16
+F_AUTO_RESET = 1
+STATUS_CRASHED, STATUS_LANDED, STATUS_LEVELING, STATUS_AIRBORNE = 0, 1, 2, 3
+VARIANT_IDS = {'Lander3D': 0, 'Lander2D': 1, 'Lander1D': 2, 'Hover3D': 3, 'Hover2D': 4, 'Hover1D': 5}
+STAT_NAMES = ('episodes', 'return_sum', 'length_sum', 'landed', 'bonus', 'crashed', 'oob',
+              'angle', 'timeout', 'env_steps')
+
+
+class CopterParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        'B', 'D', 'M', 'L', 'Ix', 'Iy', 'Iz', 'Jr', 'maxrpm',
+        'landing_vel_x', 'landing_vel_y', 'landing_angle', 'G',
+        'fps', 'initial_random_force', 'out_of_bounds_penalty', 'max_angle_deg', 'bounds',
+        'initial_altitude',
+        'target_radius', 'yaw_penalty_factor', 'xyz_penalty_factor', 'dz_max', 'dz_penalty',
+        'inside_radius_bonus')] + [('max_steps', C.c_int32), ('reserved', C.c_int32)]
+
+
+class CopterBuffers(C.Structure):
+    _fields_ = [('state', C.c_void_p), ('meta', C.c_void_p), ('action', C.c_void_p),
+                ('obs', C.c_void_p), ('reward', C.c_void_p), ('done', C.c_void_p),
+                ('init_force', C.c_void_p), ('ep_return', C.c_void_p), ('stats', C.c_void_p),
+                ('final_obs', C.c_void_p), ('state_stride', C.c_int64)]
+
+
+class CopterError(RuntimeError):
+    pass
+
+
+_ARG_ERRORS = {-1: 'COPTER_E_ARG (null or missing buffer)', -2: 'COPTER_E_VARIANT',
+               -3: 'COPTER_E_ALIGN (buffer not 16-byte aligned)', -4: 'COPTER_E_RANGE'}
+
+_lib = None
+
+
+def load():
+    """Loads the library once. Raises CopterError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CopterError(
+            '%s is missing: build it with `python -m gym_copter_b200.build` (needs nvcc). '
+            'gym_copter_b200 has no CPU or PyTorch fallback.' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    P, B, i64, u64, vp, i32 = C.POINTER(CopterParams), C.POINTER(CopterBuffers), C.c_int64, C.c_uint64, C.c_void_p, C.c_int
+    lib.copter_abi_version.restype = i32
+    lib.copter_default_params.argtypes = [P]
+    lib.copter_default_params.restype = None
+    for f in (lib.copter_obs_size, lib.copter_action_size):
+        f.argtypes, f.restype = [i32], i32
+    for f in (lib.copter_reset_f32, lib.copter_reset_f64):
+        f.argtypes, f.restype = [P, B, i64, i32, vp], i32
+    for f in (lib.copter_step_f32, lib.copter_step_f64):
+        f.argtypes, f.restype = [P, B, i64, i64, u64, i32, i32, i32, vp], i32
+    for f in (lib.copter_dynamics_f32, lib.copter_dynamics_f64):
+        f.argtypes, f.restype = [P, vp, vp, vp, vp, vp, i64, vp], i32
+    for f in (lib.copter_reset_force_f32, lib.copter_reset_force_f64):
+        f.argtypes, f.restype = [P, vp, vp, i64, i64, u64, vp], i32
+    lib.copter_pipeline_create.argtypes, lib.copter_pipeline_create.restype = [i32, C.POINTER(vp)], i32
+    lib.copter_pipeline_destroy.argtypes, lib.copter_pipeline_destroy.restype = [vp], i32
+    for f in (lib.copter_step_host_f32, lib.copter_step_host_f64):
+        f.argtypes, f.restype = [vp, P, B, vp, vp, vp, vp, i64, i64, u64, i32, i32, i32, i64, vp], i32
+    if lib.copter_abi_version() != ABI_VERSION:
+        raise CopterError('libcopter_b200.so ABI %d != binding ABI %d: rebuild'
+                          % (lib.copter_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code == 0:
+        return
+    if code < 0:
+        raise CopterError('%s: %s' % (what, _ARG_ERRORS.get(code, 'error %d' % code)))
+    raise CopterError('%s: CUDA error %d' % (what, code))
+
+
+def default_params(**overrides):
+    p = CopterParams()
+    load().copter_default_params(C.byref(p))
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise TypeError('unknown copter parameter %r' % k)
+        setattr(p, k, v)
+    return p

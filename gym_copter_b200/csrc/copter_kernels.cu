@@ -1,0 +1,784 @@
+// copter_kernels.cu -- hand-written sm_100a kernels for the batched copter step, plus the
+// C ABI declared in include/copter_b200.h.
+//
+// One thread per env.  State lives in HBM as 12/V "vector planes" of 128-bit vectors
+// (float4 / double2) so that every state access of a warp is one fully coalesced 128-bit
+// load or store; the packed meta word, the action row and the reward are coalesced too, and
+// the row-major float32 observation is staged through a per-warp shared-memory tile so that
+// it leaves the SM as contiguous 256-byte warp stores instead of a 40-byte-strided scatter.
+// K reference steps are fused per launch with the whole env state held in registers.
+//
+// What each device function restates (paths relative to the reference root):
+//   motor_forces()      gym_copter/dynamics/__init__.py:120-132, 231-247   (Eq. 6)
+//   dynamics_update()   gym_copter/dynamics/__init__.py:139-197, 249-302   (Eq. 12, FSM, Euler)
+//   lander_shaping()    gym_copter/envs/lander.py:48-56
+//   env_substep()       gym_copter/envs/task.py:77-137 + gym_copter/envs/lander.py:58-72
+//   reset state         gym_copter/envs/task.py:145-197, gym_copter/dynamics/__init__.py:210-217
+//
+// Precision.  T = double reproduces the numpy reference to ~1e-13.  T = float stores and
+// integrates in fp32 but evaluates the motor -> thrust/torque stage in fp64: the squares of
+// fp32 motor commands are exact in fp64, which removes the systematic thrust/torque bias
+// that otherwise grows like t^2 (altitude) and t^4 (lateral position) and breaks the 1e-4
+// budget over 1000 steps (measured: 1.5e-3 all-fp32 vs 1.8e-5 mixed).
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/copter_b200.h"
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kWarpsPerBlock = kBlock / 32;
+
+enum { ST_CRASHED = 0, ST_LANDED = 1, ST_LEVELING = 2, ST_AIRBORNE = 3 };
+enum { CAUSE_LANDED = 1, CAUSE_BONUS = 2, CAUSE_OOB = 4, CAUSE_ANGLE = 8, CAUSE_CRASHED = 16, CAUSE_TIMEOUT = 32 };
+
+// ------------------------------------------------------------------------------------------
+// compile-time description of the env variants
+// ------------------------------------------------------------------------------------------
+template <int VARIANT> struct Variant;
+template <> struct Variant<COPTER_LANDER3D> { static constexpr int O = 10, A = 4, first = 0; static constexpr bool lander = true; };
+template <> struct Variant<COPTER_LANDER2D> { static constexpr int O = 6,  A = 2, first = 2; static constexpr bool lander = true; };
+template <> struct Variant<COPTER_LANDER1D> { static constexpr int O = 2,  A = 1, first = 4; static constexpr bool lander = true; };
+template <> struct Variant<COPTER_HOVER3D>  { static constexpr int O = 12, A = 4, first = 0; static constexpr bool lander = false; };
+template <> struct Variant<COPTER_HOVER2D>  { static constexpr int O = 6,  A = 2, first = 2; static constexpr bool lander = false; };
+template <> struct Variant<COPTER_HOVER1D>  { static constexpr int O = 2,  A = 1, first = 4; static constexpr bool lander = false; };
+
+// ------------------------------------------------------------------------------------------
+// kernel-side constants, derived once on the host from CopterParams
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct KParams {
+    double kT, kR, kP, kY;        // B w^2/M, L B w^2/Ix, L B w^2/Iy, D w^2/Iz  (w = maxrpm*pi/30)
+    double force_scale, force_off; // u32 -> U(-F,F): u * 2F/2^32 - F
+    T G, dt, gphi, gthe, gpsi;    // (Iy-Iz)/Ix, (Iz-Ix)/Iy, (Ix-Iy)/Iz
+    T lvx, lvy, lang, invM;
+    T oob_penalty, max_angle, bounds, z0, target_radius;
+    T yaw_pf, xyz_pf, dz_max, dz_penalty, bonus;
+    int max_steps;
+    int status0;                  // status right after reset (dynamics/__init__.py:215-217)
+};
+
+template <typename T>
+KParams<T> make_kparams(const CopterParams& p) {
+    KParams<T> k;
+    const double w = p.maxrpm * M_PI / 30.0;
+    k.kT = p.B * w * w / p.M;
+    k.kR = p.L * p.B * w * w / p.Ix;
+    k.kP = p.L * p.B * w * w / p.Iy;
+    k.kY = p.D * w * w / p.Iz;
+    k.force_scale = 2.0 * p.initial_random_force / 4294967296.0;
+    k.force_off = -p.initial_random_force;
+    k.G = (T)p.G;
+    k.dt = (T)((T)1 / (T)p.fps);
+    k.gphi = (T)((p.Iy - p.Iz) / p.Ix);
+    k.gthe = (T)((p.Iz - p.Ix) / p.Iy);
+    k.gpsi = (T)((p.Ix - p.Iy) / p.Iz);
+    k.lvx = (T)p.landing_vel_x; k.lvy = (T)p.landing_vel_y; k.lang = (T)p.landing_angle;
+    k.invM = (T)(1.0 / p.M);
+    k.oob_penalty = (T)p.out_of_bounds_penalty;
+    k.max_angle = (T)(p.max_angle_deg * M_PI / 180.0);
+    k.bounds = (T)p.bounds;
+    k.z0 = (T)(-p.initial_altitude);
+    k.target_radius = (T)p.target_radius;
+    k.yaw_pf = (T)p.yaw_penalty_factor; k.xyz_pf = (T)p.xyz_penalty_factor;
+    k.dz_max = (T)p.dz_max; k.dz_penalty = (T)p.dz_penalty; k.bonus = (T)p.inside_radius_bonus;
+    k.max_steps = p.max_steps;
+    k.status0 = (-p.initial_altitude < 0) ? ST_AIRBORNE : ST_LANDED;
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------
+// small typed helpers
+// ------------------------------------------------------------------------------------------
+template <typename T> struct Vec;
+template <> struct Vec<float>  { using type = float4;  static constexpr int V = 4; };
+template <> struct Vec<double> { using type = double2; static constexpr int V = 2; };
+
+__device__ __forceinline__ void sincos_t(float a, float* s, float* c)   { sincosf(a, s, c); }
+__device__ __forceinline__ void sincos_t(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __forceinline__ float  sqrt_t(float a)  { return sqrtf(a); }
+__device__ __forceinline__ double sqrt_t(double a) { return sqrt(a); }
+__device__ __forceinline__ float  abs_t(float a)  { return fabsf(a); }
+__device__ __forceinline__ double abs_t(double a) { return fabs(a); }
+
+template <typename T>
+__device__ __forceinline__ void load_state(const T* __restrict__ state, int64_t stride, int64_t i, T (&s)[12]) {
+    using V4 = typename Vec<T>::type;
+    constexpr int V = Vec<T>::V;
+    const V4* planes = reinterpret_cast<const V4*>(state);
+#pragma unroll
+    for (int pl = 0; pl < 12 / V; ++pl) {
+        V4 v = planes[(int64_t)pl * stride + i];
+        const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) s[pl * V + j] = e[j];
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void store_state(T* __restrict__ state, int64_t stride, int64_t i, const T (&s)[12]) {
+    using V4 = typename Vec<T>::type;
+    constexpr int V = Vec<T>::V;
+    V4* planes = reinterpret_cast<V4*>(state);
+#pragma unroll
+    for (int pl = 0; pl < 12 / V; ++pl) {
+        V4 v;
+        T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) e[j] = s[pl * V + j];
+        planes[(int64_t)pl * stride + i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. SC'11), counter-based: no per-env generator state in HBM
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+// Reset force for (global env id, episode): exact in fp64, ONE rounding to T.
+template <typename T>
+__device__ __forceinline__ void reset_force(const KParams<T>& kp, uint64_t seed, uint64_t env, uint32_t episode, T (&f)[3]) {
+    uint32_t c[4] = {(uint32_t)env, (uint32_t)(env >> 32), episode, 0u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+    for (int j = 0; j < 3; ++j) f[j] = (T)fma((double)c[j], kp.force_scale, kp.force_off);
+}
+
+// ------------------------------------------------------------------------------------------
+// dynamics
+// ------------------------------------------------------------------------------------------
+template <typename T> struct Forces { T bz, u2, u3, u4; };   // -U1/M, U2/Ix, U3/Iy, U4/Iz
+
+// dynamics/__init__.py:120-132.  Always evaluated in fp64 (see header comment).
+template <typename T>
+__device__ __forceinline__ Forces<T> motor_forces(const KParams<T>& kp, T m0, T m1, T m2, T m3) {
+    const double q0 = (double)m0 * (double)m0, q1 = (double)m1 * (double)m1;
+    const double q2 = (double)m2 * (double)m2, q3 = (double)m3 * (double)m3;
+    const double s01 = q0 + q1, s23 = q2 + q3;
+    Forces<T> f;
+    f.bz = (T)(-kp.kT * (s01 + s23));
+    f.u2 = (T)(kp.kR * ((q1 + q2) - (q0 + q3)));      // roll right  (:231-235)
+    f.u3 = (T)(kp.kP * ((q1 + q3) - (q0 + q2)));      // pitch forward (:237-241)
+    f.u4 = (T)(kp.kY * (s01 - s23));                  // yaw cw (:243-247)
+    return f;
+}
+
+// dynamics/__init__.py:139-197 for one env.  NP = number of perturbed rate components the
+// caller supplies (3 on the env path: x,y,z only, envs/task.py:179-184; 6 for the Dynamics
+// facade).  DIRECT enables the LANDED -> AIRBORNE take-off transition, unreachable through
+// _Task.step (task.py:86-94).  Returns true when the call ran to the end of setMotors
+// (perturbation cleared, ticks += 1), false on the ground-contact early return (:177).
+template <typename T, int NP, bool DIRECT>
+__device__ __forceinline__ bool dynamics_update(const KParams<T>& kp, T (&s)[12], int& st,
+                                                const Forces<T>& f, const T (&p)[NP]) {
+    T sph, cph, sth, cth, sps, cps;
+    sincos_t(s[6], &sph, &cph);
+    sincos_t(s[8], &sth, &cth);
+    sincos_t(s[10], &sps, &cps);
+    // third column of the body->inertial rotation times the body-Z thrust (:292-302)
+    const T ax = f.bz * (sph * sps + cph * cps * sth);
+    const T ay = f.bz * (cph * sps * sth - cps * sph);
+    const T netz = f.bz * (cph * cth) + kp.G;                     // :143
+
+    if (DIRECT && st == ST_LANDED && netz < (T)0) st = ST_AIRBORNE;   // :147-149
+
+    if (st == ST_LEVELING) {                                       // :152-156
+        s[6] = (T)0; s[8] = (T)0; st = ST_LANDED;
+        return true;
+    }
+    if (st == ST_AIRBORNE) {
+        if (s[4] > (T)0 && s[5] > (T)0) {                          // :162 (pre-step state)
+            // :165-171 -- "velx" is dy, "vely" is dz, only phi is angle-tested (sic)
+            st = (s[5] > kp.lvy || abs_t(s[3]) > kp.lvx || abs_t(s[6]) > kp.lang) ? ST_CRASHED : ST_LEVELING;
+            return false;                                          // :177
+        }
+        const T dphi = s[7], dthe = s[9], dpsi = s[11];
+        // Eq. 12 (:257-290) with Omega = 0 (:135); the perturbation is added twice (:263-287, :183)
+        T d1 = ax, d3 = ay, d5 = netz;
+        T d7 = dpsi * dthe * kp.gphi + f.u2;
+        T d9 = -(dpsi * dphi * kp.gthe + f.u3);
+        T d11 = dthe * dphi * kp.gpsi + f.u4;
+        d1 += (T)2 * p[0]; d3 += (T)2 * p[1]; d5 += (T)2 * p[2];
+        if constexpr (NP == 6) { d7 += (T)2 * p[3]; d9 += (T)2 * p[4]; d11 += (T)2 * p[5]; }
+        // forward Euler, every derivative from the old state (:187)
+        const T dt = kp.dt;
+        s[0] += dt * s[1];  s[1] += dt * d1;
+        s[2] += dt * s[3];  s[3] += dt * d3;
+        s[4] += dt * s[5];  s[5] += dt * d5;
+        s[6] += dt * dphi;  s[7] += dt * d7;
+        s[8] += dt * dthe;  s[9] += dt * d9;
+        s[10] += dt * dpsi; s[11] += dt * d11;
+    }
+    return true;
+}
+
+// envs/lander.py:48-56
+template <typename T>
+__device__ __forceinline__ T lander_shaping(const KParams<T>& kp, const T (&s)[12]) {
+    const T spos = ((((s[0] * s[0] + s[1] * s[1]) + s[2] * s[2]) + s[3] * s[3]) + s[4] * s[4]) + s[5] * s[5];
+    const T spsi = s[10] * s[10] + s[11] * s[11];
+    T sh = -(kp.xyz_pf * sqrt_t(spos) + kp.yaw_pf * sqrt_t(spsi));
+    if (abs_t(s[5]) > kp.dz_max) sh -= kp.dz_penalty;
+    return sh;
+}
+
+// One reference _Task.step (envs/task.py:77-137) for one env held in registers.
+// `steps`/`st` are the env's counters; `pre_sh` is shaping(pre-step state) == prev_shaping
+// (the priming step of _reset sets it to shaping(s0) and every later step stores the
+// post-step value, task.py:197, lander.py:62).  On return `pre_sh` holds shaping(post).
+template <typename T, int VARIANT>
+__device__ __forceinline__ void env_substep(const KParams<T>& kp, T (&s)[12], int& st, int& steps,
+                                            const T (&m)[4], const T (&pert)[3], T& pre_sh,
+                                            T& reward, bool& done, int& cause) {
+    const int st0 = st;                                            // :81 stale status
+    if (st0 != ST_LANDED) {                                        // :86-94
+        const Forces<T> f = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
+        dynamics_update<T, 3, false>(kp, s, st, f, pert);
+    }
+    cause = 0;
+    done = false;
+    if (Variant<VARIANT>::lander) {
+        const T sh = lander_shaping<T>(kp, s);                     // lander.py:48-56
+        reward = sh - pre_sh;                                      // :58-62
+        pre_sh = sh;
+        if (st0 == ST_LANDED) {                                    // :64-72
+            done = true; cause |= CAUSE_LANDED;
+            if (sqrt_t(s[0] * s[0] + s[2] * s[2]) < kp.target_radius) { reward += kp.bonus; cause |= CAUSE_BONUS; }
+        }
+    } else {
+        reward = (T)1;                                             // attic hover.py:18-21
+    }
+    if (abs_t(s[0]) >= kp.bounds || abs_t(s[2]) >= kp.bounds) {    // task.py:111
+        done = true; reward -= kp.oob_penalty; cause |= CAUSE_OOB;
+    } else if (abs_t(s[6]) >= kp.max_angle || abs_t(s[8]) >= kp.max_angle) {   // :116
+        done = true; reward = -kp.oob_penalty; cause |= CAUSE_ANGLE;
+    } else if (st0 == ST_CRASHED) {                                // :121
+        done = true;
+    }
+    if (st0 == ST_CRASHED) cause |= CAUSE_CRASHED;
+    if (steps == kp.max_steps) { done = true; cause |= CAUSE_TIMEOUT; }          // :128
+    steps = min(steps + 1, 2047);                                  // :130 (11-bit field)
+    if (!done) cause = 0;
+}
+
+template <typename T>
+__device__ __forceinline__ void reset_state(const KParams<T>& kp, T (&s)[12], int& st, int& steps) {
+    // envs/task.py:149,164-171,191,197 and dynamics/__init__.py:215-217
+#pragma unroll
+    for (int j = 0; j < 12; ++j) s[j] = (T)0;
+    s[4] = kp.z0;
+    st = kp.status0;
+    steps = 1;
+}
+
+// Row-major float32 observation of a warp's 32 envs, staged through shared memory so the
+// global stores are contiguous 8-byte-per-lane warp stores.  `tile` is this warp's
+// 32*O-float region; `row0` the first env of the warp; `rows` how many of its envs exist.
+template <int VARIANT, typename T>
+__device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, float* tile, int lane,
+                                               int64_t row0, int rows, const T (&s)[12]) {
+    constexpr int O = Variant<VARIANT>::O, first = Variant<VARIANT>::first, H = O / 2;
+    float2* t2 = reinterpret_cast<float2*>(tile);
+#pragma unroll
+    for (int j = 0; j < H; ++j)
+        t2[lane * H + j] = make_float2((float)s[first + 2 * j], (float)s[first + 2 * j + 1]);
+    __syncwarp();
+    float2* out = reinterpret_cast<float2*>(obs + row0 * O);
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        const int e = j * 32 + lane;
+        if (e < rows * H) out[e] = t2[e];
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct StepArgs {
+    T* state; uint32_t* meta; const T* action; float* obs; T* reward; uint8_t* done;
+    const T* init_force; T* ep_return; double* stats; float* final_obs;
+    int64_t n, stride, env_offset; uint64_t seed; int k; int auto_reset;
+};
+
+template <typename T, int VARIANT, bool STATS>
+__global__ void __launch_bounds__(kBlock)
+copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant__ StepArgs<T> a) {
+    constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A;
+    __shared__ __align__(16) float tiles[kWarpsPerBlock][32 * O];
+    __shared__ double block_stats[STATS ? 10 : 1];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = tiles[warp];
+
+    // per-thread statistics, reduced once at the end of the grid-stride loop
+    int n_ep = 0, n_landed = 0, n_bonus = 0, n_crashed = 0, n_oob = 0, n_angle = 0, n_timeout = 0, n_steps = 0;
+    double sum_ret = 0.0; int sum_len = 0;
+
+    if (STATS) {
+        if (threadIdx.x < 10) block_stats[threadIdx.x] = 0.0;
+        __syncthreads();
+    }
+
+    const int64_t n_tiles = (a.n + kBlock - 1) / kBlock;
+    for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+        const int64_t row0 = tile_id * kBlock + warp * 32;       // first env of this warp
+        const int64_t i = row0 + lane;
+        const bool valid = i < a.n;
+        const int rows = (int)max((int64_t)0, min((int64_t)32, a.n - row0));
+
+        T s[12];
+        T m[4] = {(T)0, (T)0, (T)0, (T)0};
+        int st = ST_LANDED, steps = 1; uint32_t episode = 0;
+        T total = (T)0; bool done_any = false;
+        T ret = (T)0;
+
+        if (valid) {
+            load_state<T>(a.state, a.stride, i, s);
+            const uint32_t mw = a.meta[i];
+            st = (int)(mw & 3u); steps = (int)((mw >> 2) & 2047u); episode = mw >> 13;
+            // action row, clipped to [0,1] (task.py:91) and fanned out (_get_motors)
+            T act[A];
+            if constexpr (A == 4 && sizeof(T) == 4) {
+                const float4 v = reinterpret_cast<const float4*>(a.action)[i];
+                act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
+            } else if constexpr (A == 4) {
+                const double2 v0 = reinterpret_cast<const double2*>(a.action)[2 * i];
+                const double2 v1 = reinterpret_cast<const double2*>(a.action)[2 * i + 1];
+                act[0] = v0.x; act[1] = v0.y; act[2] = v1.x; act[3] = v1.y;
+            } else if constexpr (A == 2 && sizeof(T) == 4) {
+                const float2 v = reinterpret_cast<const float2*>(a.action)[i];
+                act[0] = v.x; act[1] = v.y;
+            } else if constexpr (A == 2) {
+                const double2 v = reinterpret_cast<const double2*>(a.action)[i];
+                act[0] = v.x; act[1] = v.y;
+            } else {
+                act[0] = a.action[i];
+            }
+#pragma unroll
+            for (int j = 0; j < A; ++j) act[j] = fmin(fmax(act[j], (T)0), (T)1);
+            if constexpr (A == 4) { m[0] = act[0]; m[1] = act[1]; m[2] = act[2]; m[3] = act[3]; }
+            else if constexpr (A == 2) { m[0] = act[0]; m[1] = act[1]; m[2] = act[1]; m[3] = act[0]; }   // attic lander2d.py:49-51
+            else { m[0] = m[1] = m[2] = m[3] = act[0]; }                                                // attic lander1d.py:47-49
+            if (STATS && a.ep_return) ret = a.ep_return[i];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) s[j] = (T)0;
+        }
+
+        T final_s[12];
+        bool want_final = (a.final_obs != nullptr);
+        T pre_sh = Variant<VARIANT>::lander ? lander_shaping<T>(kp, s) : (T)0;
+
+        for (int k = 0; k < a.k; ++k) {
+            const bool live = valid && !done_any;
+            if (__all_sync(0xffffffffu, !live)) break;             // whole warp finished: idle
+            if (live) {
+                // the reset perturbation is consumed by the first step of an episode
+                T pert[3] = {(T)0, (T)0, (T)0};
+                if (steps == 1) {
+                    T f[3];
+                    if (a.init_force) { f[0] = a.init_force[3 * i]; f[1] = a.init_force[3 * i + 1]; f[2] = a.init_force[3 * i + 2]; }
+                    else reset_force<T>(kp, a.seed, (uint64_t)(a.env_offset + i), episode, f);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) pert[j] = f[j] * kp.invM;      // dynamics/__init__.py:229
+                }
+                T r; bool dn; int cause;
+                env_substep<T, VARIANT>(kp, s, st, steps, m, pert, pre_sh, r, dn, cause);
+                total += r;
+                if (STATS) { ++n_steps; ret += r; }
+                if (dn) {
+                    done_any = true;
+                    if (STATS) {
+                        ++n_ep; sum_ret += (double)ret; sum_len += steps - 1; ret = (T)0;   // `steps` is 1 right after reset (task.py:191,197)
+                        n_landed += (cause & CAUSE_LANDED) != 0; n_bonus += (cause & CAUSE_BONUS) != 0;
+                        n_crashed += (cause & CAUSE_CRASHED) != 0; n_oob += (cause & CAUSE_OOB) != 0;
+                        n_angle += (cause & CAUSE_ANGLE) != 0; n_timeout += (cause & CAUSE_TIMEOUT) != 0;
+                    }
+                    if (want_final) {
+#pragma unroll
+                        for (int j = 0; j < 12; ++j) final_s[j] = s[j];
+                    }
+                    if (a.auto_reset) {
+                        reset_state<T>(kp, s, st, steps);
+                        episode = (episode + 1) & 0x7FFFFu;
+                        if (Variant<VARIANT>::lander) pre_sh = lander_shaping<T>(kp, s);
+                    }
+                }
+            }
+        }
+
+        if (valid) {
+            store_state<T>(a.state, a.stride, i, s);
+            a.meta[i] = (uint32_t)st | ((uint32_t)steps << 2) | (episode << 13);
+            a.reward[i] = total;
+            a.done[i] = done_any ? 1 : 0;
+            if (STATS && a.ep_return) a.ep_return[i] = ret;
+        }
+        if (a.obs) write_obs_rows<VARIANT, T>(a.obs, tile, lane, row0, rows, s);
+        if (want_final && __any_sync(0xffffffffu, done_any)) {
+            // terminal observation of finished envs; rows of unfinished envs are left untouched
+            constexpr int first = Variant<VARIANT>::first;
+            if (valid && done_any) {
+#pragma unroll
+                for (int j = 0; j < O; ++j) a.final_obs[i * O + j] = (float)final_s[first + j];
+            }
+        }
+    }
+
+    if (STATS) {
+        // warp reduce (REDUX for the integer counters), then one shared atomic per warp and
+        // one global atomic per block and statistic
+        const unsigned full = 0xffffffffu;
+        int c[9] = {n_ep, sum_len, n_landed, n_bonus, n_crashed, n_oob, n_angle, n_timeout, n_steps};
+#pragma unroll
+        for (int j = 0; j < 9; ++j) c[j] = __reduce_add_sync(full, c[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum_ret += __shfl_xor_sync(full, sum_ret, o);
+        if (lane == 0) {
+            atomicAdd(&block_stats[0], (double)c[0]);
+            atomicAdd(&block_stats[1], sum_ret);
+#pragma unroll
+            for (int j = 1; j < 9; ++j) atomicAdd(&block_stats[j + 1], (double)c[j]);
+        }
+        __syncthreads();
+        if (threadIdx.x < 10 && block_stats[threadIdx.x] != 0.0) atomicAdd(&a.stats[threadIdx.x], block_stats[threadIdx.x]);
+    }
+}
+
+template <typename T, int VARIANT>
+__global__ void __launch_bounds__(kBlock)
+copter_reset_kernel(const __grid_constant__ KParams<T> kp, T* state, uint32_t* meta, float* obs, T* ep_return, int64_t n, int64_t stride) {
+    constexpr int O = Variant<VARIANT>::O;
+    __shared__ __align__(16) float tiles[kWarpsPerBlock][32 * O];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n_tiles = (n + kBlock - 1) / kBlock;
+    for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+        const int64_t row0 = tile_id * kBlock + warp * 32, i = row0 + lane;
+        const int rows = (int)max((int64_t)0, min((int64_t)32, n - row0));
+        T s[12]; int st, steps;
+        reset_state<T>(kp, s, st, steps);
+        if (i < n) {
+            store_state<T>(state, stride, i, s);
+            meta[i] = (uint32_t)st | ((uint32_t)steps << 2);
+            if (ep_return) ep_return[i] = (T)0;
+        }
+        if (obs) write_obs_rows<VARIANT, T>(obs, tiles[warp], lane, row0, rows, s);
+    }
+}
+
+// Batched Dynamics.setMotors (dynamics/__init__.py:114-197), all four statuses reachable.
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+copter_dynamics_kernel(const __grid_constant__ KParams<T> kp, T* state, uint8_t* status, int32_t* ticks,
+                       T* perturb, const T* motors, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        T s[12], p[6], m[4];
+        load_state<T>(state, n, i, s);
+        int st = status[i];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) p[j] = perturb[6 * i + j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = motors[4 * i + j];
+        const Forces<T> f = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
+        const bool finished = dynamics_update<T, 6, true>(kp, s, st, f, p);
+        store_state<T>(state, n, i, s);
+        status[i] = (uint8_t)st;
+        if (finished) {                                            // :194-197
+#pragma unroll
+            for (int j = 0; j < 6; ++j) perturb[6 * i + j] = (T)0;
+            ticks[i] += 1;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+copter_reset_force_kernel(const __grid_constant__ KParams<T> kp, T* out, const uint32_t* episode,
+                          int64_t n, int64_t env_offset, uint64_t seed) {
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+        T f[3];
+        reset_force<T>(kp, seed, (uint64_t)(env_offset + i), episode ? episode[i] : 0u, f);
+        out[3 * i] = f[0]; out[3 * i + 1] = f[1]; out[3 * i + 2] = f[2];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launch helpers
+// ------------------------------------------------------------------------------------------
+int sm_count() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+    }
+    return sms;
+}
+
+// Persistent-style grid: at most one resident wave (SMs x CTAs/SM of this kernel), each CTA
+// walking the 256-env tiles with a grid stride.
+template <typename K>
+int grid_for(K kernel, int64_t n) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
+    const int64_t tiles = (n + kBlock - 1) / kBlock;
+    const int64_t cap = (int64_t)sm_count() * per_sm;
+    return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_params(const CopterParams* p) {
+    if (!p) return COPTER_E_ARG;
+    if (p->max_steps < 1 || p->max_steps > COPTER_MAX_STEPS_LIMIT) return COPTER_E_RANGE;
+    if (!(p->M > 0) || !(p->Ix > 0) || !(p->Iy > 0) || !(p->Iz > 0) || !(p->fps > 0)) return COPTER_E_RANGE;
+    return 0;
+}
+
+template <typename T, int VARIANT>
+int launch_step_v(const KParams<T>& kp, const StepArgs<T>& a, cudaStream_t s) {
+    if (a.stats) copter_step_kernel<T, VARIANT, true><<<grid_for(copter_step_kernel<T, VARIANT, true>, a.n), kBlock, 0, s>>>(kp, a);
+    else         copter_step_kernel<T, VARIANT, false><<<grid_for(copter_step_kernel<T, VARIANT, false>, a.n), kBlock, 0, s>>>(kp, a);
+    return (int)cudaGetLastError();
+}
+
+template <typename T>
+int launch_step(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_t env_offset, uint64_t seed,
+                int k, int variant, int flags, void* stream) {
+    int e = check_params(p);
+    if (e) return e;
+    if (!b || !b->state || !b->meta || !b->action || !b->reward || !b->done) return COPTER_E_ARG;
+    if (n < 0 || env_offset < 0 || k < 1 || (b->state_stride > 0 && b->state_stride < n)) return COPTER_E_RANGE;
+    if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
+    if (!aligned16(b->state) || !aligned16(b->action) || (b->obs && !aligned16(b->obs))) return COPTER_E_ALIGN;
+    if (n == 0) return 0;
+    const KParams<T> kp = make_kparams<T>(*p);
+    StepArgs<T> a;
+    a.state = (T*)b->state; a.meta = b->meta; a.action = (const T*)b->action; a.obs = b->obs;
+    a.reward = (T*)b->reward; a.done = b->done; a.init_force = (const T*)b->init_force;
+    a.ep_return = (T*)b->ep_return; a.stats = b->stats; a.final_obs = b->final_obs;
+    a.n = n; a.stride = b->state_stride > 0 ? b->state_stride : n; a.env_offset = env_offset; a.seed = seed; a.k = k; a.auto_reset = (flags & COPTER_F_AUTO_RESET) ? 1 : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (variant) {
+        case COPTER_LANDER3D: return launch_step_v<T, COPTER_LANDER3D>(kp, a, s);
+        case COPTER_LANDER2D: return launch_step_v<T, COPTER_LANDER2D>(kp, a, s);
+        case COPTER_LANDER1D: return launch_step_v<T, COPTER_LANDER1D>(kp, a, s);
+        case COPTER_HOVER3D:  return launch_step_v<T, COPTER_HOVER3D>(kp, a, s);
+        case COPTER_HOVER2D:  return launch_step_v<T, COPTER_HOVER2D>(kp, a, s);
+        default:              return launch_step_v<T, COPTER_HOVER1D>(kp, a, s);
+    }
+}
+
+template <typename T, int VARIANT>
+int launch_reset_v(const KParams<T>& kp, const CopterBuffers* b, int64_t n, cudaStream_t s) {
+    copter_reset_kernel<T, VARIANT><<<grid_for(copter_reset_kernel<T, VARIANT>, n), kBlock, 0, s>>>(kp, (T*)b->state, b->meta, b->obs, (T*)b->ep_return, n, b->state_stride > 0 ? b->state_stride : n);
+    return (int)cudaGetLastError();
+}
+
+template <typename T>
+int launch_reset(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, void* stream) {
+    int e = check_params(p);
+    if (e) return e;
+    if (!b || !b->state || !b->meta) return COPTER_E_ARG;
+    if (n < 0 || (b->state_stride > 0 && b->state_stride < n)) return COPTER_E_RANGE;
+    if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
+    if (!aligned16(b->state) || (b->obs && !aligned16(b->obs))) return COPTER_E_ALIGN;
+    if (n == 0) return 0;
+    const KParams<T> kp = make_kparams<T>(*p);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (variant) {
+        case COPTER_LANDER3D: return launch_reset_v<T, COPTER_LANDER3D>(kp, b, n, s);
+        case COPTER_LANDER2D: return launch_reset_v<T, COPTER_LANDER2D>(kp, b, n, s);
+        case COPTER_LANDER1D: return launch_reset_v<T, COPTER_LANDER1D>(kp, b, n, s);
+        case COPTER_HOVER3D:  return launch_reset_v<T, COPTER_HOVER3D>(kp, b, n, s);
+        case COPTER_HOVER2D:  return launch_reset_v<T, COPTER_HOVER2D>(kp, b, n, s);
+        default:              return launch_reset_v<T, COPTER_HOVER1D>(kp, b, n, s);
+    }
+}
+
+template <typename T>
+int launch_dynamics(const CopterParams* p, void* state, uint8_t* status, int32_t* ticks, void* perturb,
+                    const void* motors, int64_t n, void* stream) {
+    int e = check_params(p);
+    if (e) return e;
+    if (!state || !status || !ticks || !perturb || !motors) return COPTER_E_ARG;
+    if (n < 0) return COPTER_E_RANGE;
+    if (!aligned16(state)) return COPTER_E_ALIGN;
+    if (n == 0) return 0;
+    const KParams<T> kp = make_kparams<T>(*p);
+    copter_dynamics_kernel<T><<<grid_for(copter_dynamics_kernel<T>, n), kBlock, 0, (cudaStream_t)stream>>>(kp, (T*)state, status, ticks, (T*)perturb, (const T*)motors, n);
+    return (int)cudaGetLastError();
+}
+
+template <typename T>
+int launch_reset_force(const CopterParams* p, T* out, const uint32_t* episode, int64_t n, int64_t env_offset,
+                       uint64_t seed, void* stream) {
+    int e = check_params(p);
+    if (e) return e;
+    if (!out) return COPTER_E_ARG;
+    if (n < 0 || env_offset < 0) return COPTER_E_RANGE;
+    if (n == 0) return 0;
+    const KParams<T> kp = make_kparams<T>(*p);
+    copter_reset_force_kernel<T><<<grid_for(copter_reset_force_kernel<T>, n), kBlock, 0, (cudaStream_t)stream>>>(kp, out, episode, n, env_offset, seed);
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer pipeline: the step for callers that hold numpy-style HOST arrays
+// ------------------------------------------------------------------------------------------
+struct Pipeline {
+    int n_streams;
+    cudaStream_t streams[8];
+    cudaEvent_t start, done[8];
+};
+
+template <typename T>
+int step_host(Pipeline* pl, const CopterParams* p, const CopterBuffers* dev, const void* h_action, float* h_obs,
+              void* h_reward, uint8_t* h_done, int64_t n, int64_t env_offset, uint64_t seed, int k, int variant,
+              int flags, int64_t chunk, void* caller_stream) {
+    if (!pl || !dev || !h_action || !h_reward || !h_done || !dev->action) return COPTER_E_ARG;
+    if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
+    if (n < 0 || chunk <= 0) return COPTER_E_RANGE;
+    const int O = copter_obs_size(variant), A = copter_action_size(variant);
+    constexpr int V = Vec<T>::V;
+    chunk = (chunk + 255) / 256 * 256;                    // keeps every sub-shard 16-byte aligned
+    const int64_t stride = dev->state_stride > 0 ? dev->state_stride : n;
+    cudaError_t ce;
+    if ((ce = cudaEventRecord(pl->start, (cudaStream_t)caller_stream)) != cudaSuccess) return (int)ce;
+    for (int s = 0; s < pl->n_streams; ++s)
+        if ((ce = cudaStreamWaitEvent(pl->streams[s], pl->start, 0)) != cudaSuccess) return (int)ce;
+    int c = 0;
+    for (int64_t lo = 0; lo < n; lo += chunk, ++c) {
+        const int64_t m = (n - lo < chunk) ? (n - lo) : chunk;
+        cudaStream_t st = pl->streams[c % pl->n_streams];
+        CopterBuffers b = *dev;
+        b.state = (T*)dev->state + lo * V;               // same planes, shifted by `lo` vectors
+        b.state_stride = stride;
+        b.meta = dev->meta + lo;
+        b.action = (const T*)dev->action + lo * A;
+        b.obs = dev->obs ? dev->obs + lo * O : nullptr;
+        b.reward = (T*)dev->reward + lo;
+        b.done = dev->done + lo;
+        b.init_force = dev->init_force ? (const T*)dev->init_force + lo * 3 : nullptr;
+        b.ep_return = dev->ep_return ? (T*)dev->ep_return + lo : nullptr;
+        b.final_obs = dev->final_obs ? dev->final_obs + lo * O : nullptr;
+        if ((ce = cudaMemcpyAsync((void*)b.action, (const T*)h_action + lo * A, sizeof(T) * m * A, cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)ce;
+        const int e = launch_step<T>(p, &b, m, env_offset + lo, seed, k, variant, flags, st);
+        if (e) return e;
+        if (h_obs && b.obs && (ce = cudaMemcpyAsync(h_obs + lo * O, b.obs, sizeof(float) * m * O, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)ce;
+        if ((ce = cudaMemcpyAsync((T*)h_reward + lo, b.reward, sizeof(T) * m, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)ce;
+        if ((ce = cudaMemcpyAsync(h_done + lo, b.done, m, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)ce;
+    }
+    for (int s = 0; s < pl->n_streams; ++s) {
+        if ((ce = cudaEventRecord(pl->done[s], pl->streams[s])) != cudaSuccess) return (int)ce;
+        if ((ce = cudaStreamWaitEvent((cudaStream_t)caller_stream, pl->done[s], 0)) != cudaSuccess) return (int)ce;
+    }
+    for (int s = 0; s < pl->n_streams; ++s)
+        if ((ce = cudaStreamSynchronize(pl->streams[s])) != cudaSuccess) return (int)ce;
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int copter_abi_version(void) { return COPTER_ABI_VERSION; }
+
+void copter_default_params(CopterParams* p) {
+    if (!p) return;
+    p->B = 5.E-03; p->D = 2.E-06; p->M = 1.380; p->L = 0.350;           // dji_phantom.py:12-17
+    p->Ix = 2; p->Iy = 2; p->Iz = 3; p->Jr = 38E-04; p->maxrpm = 15000;  // dji_phantom.py:20-25
+    p->landing_vel_x = 2.0; p->landing_vel_y = 1.0; p->landing_angle = M_PI / 4; p->G = 9.80665;   // dynamics:71-76
+    p->fps = 100; p->initial_random_force = 30; p->out_of_bounds_penalty = 100;                    // task.py:25,32-38
+    p->max_angle_deg = 45; p->bounds = 10; p->initial_altitude = 10; p->max_steps = 1000;
+    p->target_radius = 2; p->yaw_penalty_factor = 50; p->xyz_penalty_factor = 25;                  // lander.py:17-23
+    p->dz_max = 10; p->dz_penalty = 100; p->inside_radius_bonus = 100;
+    p->reserved = 0;
+}
+
+int copter_obs_size(int variant) {
+    static const int o[COPTER_NUM_VARIANTS] = {10, 6, 2, 12, 6, 2};
+    return (variant < 0 || variant >= COPTER_NUM_VARIANTS) ? COPTER_E_VARIANT : o[variant];
+}
+
+int copter_action_size(int variant) {
+    static const int a[COPTER_NUM_VARIANTS] = {4, 2, 1, 4, 2, 1};
+    return (variant < 0 || variant >= COPTER_NUM_VARIANTS) ? COPTER_E_VARIANT : a[variant];
+}
+
+int copter_reset_f32(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, void* stream) { return launch_reset<float>(p, b, n, variant, stream); }
+int copter_reset_f64(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, void* stream) { return launch_reset<double>(p, b, n, variant, stream); }
+
+int copter_step_f32(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_t env_offset, uint64_t seed, int k, int variant, int flags, void* stream) {
+    return launch_step<float>(p, b, n, env_offset, seed, k, variant, flags, stream);
+}
+int copter_step_f64(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_t env_offset, uint64_t seed, int k, int variant, int flags, void* stream) {
+    return launch_step<double>(p, b, n, env_offset, seed, k, variant, flags, stream);
+}
+
+int copter_dynamics_f32(const CopterParams* p, void* state, uint8_t* status, int32_t* ticks, void* perturb, const void* motors, int64_t n, void* stream) {
+    return launch_dynamics<float>(p, state, status, ticks, perturb, motors, n, stream);
+}
+int copter_dynamics_f64(const CopterParams* p, void* state, uint8_t* status, int32_t* ticks, void* perturb, const void* motors, int64_t n, void* stream) {
+    return launch_dynamics<double>(p, state, status, ticks, perturb, motors, n, stream);
+}
+
+int copter_reset_force_f32(const CopterParams* p, float* out, const uint32_t* ep, int64_t n, int64_t env_offset, uint64_t seed, void* stream) {
+    return launch_reset_force<float>(p, out, ep, n, env_offset, seed, stream);
+}
+int copter_reset_force_f64(const CopterParams* p, double* out, const uint32_t* ep, int64_t n, int64_t env_offset, uint64_t seed, void* stream) {
+    return launch_reset_force<double>(p, out, ep, n, env_offset, seed, stream);
+}
+
+int copter_pipeline_create(int n_streams, void** out) {
+    if (!out || n_streams < 1 || n_streams > 8) return COPTER_E_ARG;
+    Pipeline* pl = new Pipeline();
+    pl->n_streams = n_streams;
+    cudaError_t ce = cudaEventCreateWithFlags(&pl->start, cudaEventDisableTiming);
+    for (int s = 0; s < n_streams && ce == cudaSuccess; ++s) {
+        ce = cudaStreamCreateWithFlags(&pl->streams[s], cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&pl->done[s], cudaEventDisableTiming);
+    }
+    if (ce != cudaSuccess) { delete pl; return (int)ce; }
+    *out = pl;
+    return 0;
+}
+
+int copter_pipeline_destroy(void* pipeline) {
+    Pipeline* pl = (Pipeline*)pipeline;
+    if (!pl) return COPTER_E_ARG;
+    for (int s = 0; s < pl->n_streams; ++s) { cudaStreamDestroy(pl->streams[s]); cudaEventDestroy(pl->done[s]); }
+    cudaEventDestroy(pl->start);
+    delete pl;
+    return 0;
+}
+
+int copter_step_host_f32(void* pipeline, const CopterParams* p, const CopterBuffers* dev, const float* h_action, float* h_obs,
+                         float* h_reward, uint8_t* h_done, int64_t n, int64_t env_offset, uint64_t seed, int k, int variant,
+                         int flags, int64_t chunk_envs, void* stream) {
+    return step_host<float>((Pipeline*)pipeline, p, dev, h_action, h_obs, h_reward, h_done, n, env_offset, seed, k, variant, flags, chunk_envs, stream);
+}
+int copter_step_host_f64(void* pipeline, const CopterParams* p, const CopterBuffers* dev, const double* h_action, float* h_obs,
+                         double* h_reward, uint8_t* h_done, int64_t n, int64_t env_offset, uint64_t seed, int k, int variant,
+                         int flags, int64_t chunk_envs, void* stream) {
+    return step_host<double>((Pipeline*)pipeline, p, dev, h_action, h_obs, h_reward, h_done, n, env_offset, seed, k, variant, flags, chunk_envs, stream);
+}
+
+}  // extern "C"

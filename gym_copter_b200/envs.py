@@ -1,0 +1,470 @@
+"""
+Host-side mirror of the reference's env API for the batched CUDA step.
+
+`CopterVecEnv` keeps the reference's `reset(seed, options) -> (obs, info)` /
+`step(action) -> (obs, reward, terminated, truncated, info)` surface
+(/root/reference: gym_copter/envs/task.py:77-143, gym_copter/envs/lander.py:25-37) with a
+leading env dimension, in the style of gymnasium.vector.VectorEnv (`num_envs`,
+`single_observation_space`, `single_action_space`).  All arithmetic happens in
+libcopter_b200.so; PyTorch only owns the device memory and the stream.  There is no CPU
+path: constructing an env without a CUDA device or without the built library raises.
+
+`Lander` (and `Lander2D`, `Hover3D`, ...) are the single-env facades: one env, numpy in and
+out, python float reward / bool done -- the shapes the reference's callers (lander.py:29-64)
+consume.
+"""
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CopterBuffers, CopterError, VARIANT_IDS, STAT_NAMES
+
+_OBS_IDX = {'Lander3D': tuple(range(10)), 'Lander2D': (2, 3, 4, 5, 6, 7), 'Lander1D': (4, 5),
+            'Hover3D': tuple(range(12)), 'Hover2D': (2, 3, 4, 5, 6, 7), 'Hover1D': (4, 5)}
+_ACT_SIZE = {'Lander3D': 4, 'Lander2D': 2, 'Lander1D': 1, 'Hover3D': 4, 'Hover2D': 2, 'Hover1D': 1}
+_ALL_NAMES = ['X', 'dX', 'Y', 'dY', 'Z', 'dZ', 'Phi', 'dPhi', 'Theta', 'dTheta', 'Psi', 'dPsi']
+
+
+class Box:
+    """Duck-typed stand-in for gymnasium.spaces.Box (gymnasium is not installed in this
+    image); the real class is used instead when importable."""
+
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.low = np.full(shape, low, dtype)
+        self.high = np.full(shape, high, dtype)
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+
+    def sample(self):
+        lo = np.where(np.isfinite(self.low), self.low, -1.0)
+        hi = np.where(np.isfinite(self.high), self.high, 1.0)
+        return np.random.uniform(lo, hi).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+    def __repr__(self):
+        return 'Box(%s, %s, %s, %s)' % (self.low.min(), self.high.max(), self.shape, self.dtype)
+
+
+def _make_box(low, high, shape):
+    try:
+        from gymnasium import spaces          # pragma: no cover (absent in this image)
+        if not getattr(__import__('gymnasium'), '__shim__', False):
+            return spaces.Box(low, high, shape=shape, dtype=np.float32)
+    except Exception:
+        pass
+    return Box(low, high, shape)
+
+
+class CopterVecEnv:
+    """
+    N independent copter envs stepped in lockstep on one GPU.
+
+    variant      'Lander3D' (the reference's live `Lander`), 'Lander2D', 'Lander1D',
+                 'Hover3D', 'Hover2D', 'Hover1D' 
+    dtype        torch.float32 (throughput path) or torch.float64 (trajectory-exact path)
+    k_substeps   reference steps fused per `step()` under one action (frame-skip)
+    auto_reset   same-step auto-reset: a finished env reports done/terminal reward and is
+                 replaced by a fresh reset state whose observation is returned
+    env_offset   global id of env 0 of this shard (keys the per-env Philox reset stream, so
+                 results do not depend on how the batch is sharded over GPUs)
+    track_stats  accumulate episode statistics on the device (see `stats()`)
+    track_returns  also keep a running per-env episode return (one more T[N] array read and
+                 written per step) so that `stats()` reports return sums / means
+    keep_final_obs  also record the terminal observation of finished envs (`info['final_obs']`)
+    kwargs       any CopterParams field, e.g. initial_altitude=5, max_steps=500 (task.py:32-38)
+    """
+
+    metadata = {'render_modes': ['human', 'rgb_array'], 'render_fps': 100}
+    FRAMES_PER_SECOND = 100
+
+    def __init__(self, variant='Lander3D', num_envs=1, dtype=torch.float32, device=None, seed=0,
+                 env_offset=0, k_substeps=1, auto_reset=True, track_stats=False,
+                 track_returns=False, keep_final_obs=False, **params):
+        if variant not in VARIANT_IDS:
+            raise ValueError('unknown variant %r' % (variant,))
+        if dtype not in (torch.float32, torch.float64):
+            raise ValueError('dtype must be torch.float32 or torch.float64')
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise CopterError('gym_copter_b200 needs a CUDA device (there is no CPU fallback)')
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != 'cuda':
+            raise CopterError('device must be a CUDA device')
+        self.variant, self.num_envs, self.dtype = variant, int(num_envs), dtype
+        self.seed_value, self.env_offset = int(seed), int(env_offset)
+        self.k_substeps, self.auto_reset = int(k_substeps), bool(auto_reset)
+        self.params = _lib.default_params(**params)
+        self.FRAMES_PER_SECOND = self.params.fps
+        self.TARGET_RADIUS = self.params.target_radius
+        self.obs_size, self.action_size = len(_OBS_IDX[variant]), _ACT_SIZE[variant]
+        self.STATE_NAMES = [_ALL_NAMES[j] for j in _OBS_IDX[variant]]
+        self.single_observation_space = _make_box(-np.inf, np.inf, (self.obs_size,))
+        self.single_action_space = _make_box(-1, 1, (self.action_size,))
+        self.observation_space = _make_box(-np.inf, np.inf, (self.num_envs, self.obs_size))
+        self.action_space = _make_box(-1, 1, (self.num_envs, self.action_size))
+        self.viewer = None
+        self.launches = 0           # kernels launched by this env (bench.py's gpu_launches)
+
+        n, dev = self.num_envs, self.device
+        V = 4 if dtype == torch.float32 else 2
+        self._f32 = dtype == torch.float32
+        self.state_planes = torch.zeros((12 // V, n, V), dtype=dtype, device=dev)
+        self.meta = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.obs = torch.zeros((n, self.obs_size), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(n, dtype=dtype, device=dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._truncated = torch.zeros(n, dtype=torch.bool, device=dev)
+        self._action = torch.zeros((n, self.action_size), dtype=dtype, device=dev)
+        track_stats = track_stats or track_returns
+        self.ep_return = torch.zeros(n, dtype=dtype, device=dev) if track_returns else None
+        self._stats = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=dev) if track_stats else None
+        self.final_obs = torch.zeros((n, self.obs_size), dtype=torch.float32, device=dev) if keep_final_obs else None
+        self._force = None
+        self._is_reset = False
+        self._pipeline = None
+        self._host = None
+
+    # ---- plumbing -----------------------------------------------------------------------
+
+    def _buffers(self, action=None, force=None):
+        b = CopterBuffers()
+        b.state, b.meta = self.state_planes.data_ptr(), self.meta.data_ptr()
+        b.action = action.data_ptr() if action is not None else None
+        b.obs, b.reward, b.done = self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr()
+        b.init_force = force.data_ptr() if force is not None else None
+        b.ep_return = self.ep_return.data_ptr() if self.ep_return is not None else None
+        b.stats = self._stats.data_ptr() if self._stats is not None else None
+        b.final_obs = self.final_obs.data_ptr() if self.final_obs is not None else None
+        return b
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _as_action(self, action):
+        n, a = self.num_envs, self.action_size
+        if isinstance(action, torch.Tensor):
+            t = action
+            if t.device != self.device or t.dtype != self.dtype:
+                t = t.to(device=self.device, dtype=self.dtype)
+        else:
+            t = torch.as_tensor(np.asarray(action), dtype=self.dtype).to(self.device)
+        if t.numel() != n * a:
+            raise ValueError('action must have shape (%d, %d), got %s' % (n, a, tuple(t.shape)))
+        t = t.reshape(n, a)
+        if not t.is_contiguous() or t.data_ptr() % 16:
+            self._action.copy_(t)
+            t = self._action
+        return t
+
+    # ---- reference API ------------------------------------------------------------------
+
+    def reset(self, seed=None, options=None, force=None):
+        """
+        Resets every env (envs/task.py:145-197).  `seed` re-keys the Philox reset-force
+        stream (the reference's seed argument is dead code, task.py:147).  `force` ([N,3],
+        newtons) injects the reset perturbation instead of the Philox draw -- it is then used
+        for every episode of the env until `reset()` is called without it.
+        """
+        if seed is not None:
+            self.seed_value = int(seed)
+        self._force = None
+        if force is not None:
+            f = torch.as_tensor(np.asarray(force) if not isinstance(force, torch.Tensor) else force)
+            self._force = f.to(device=self.device, dtype=self.dtype).reshape(self.num_envs, 3).contiguous()
+        with torch.cuda.device(self.device):
+            fn = self._lib.copter_reset_f32 if self._f32 else self._lib.copter_reset_f64
+            b = self._buffers()
+            _lib.check(fn(C.byref(self.params), C.byref(b), self.num_envs, VARIANT_IDS[self.variant],
+                          self._stream()), 'copter_reset')
+        self.launches += 1
+        self._is_reset = True
+        return self.obs, {}
+
+    def step(self, action):
+        """
+        One batched `_Task.step` (envs/task.py:77-137), k_substeps times under one action.
+        Returns (obs f32 [N,O], reward [N], terminated bool [N], truncated bool [N], info).
+        The returned tensors are the env's own output buffers: they are overwritten by the
+        next step (clone them to keep them).
+        """
+        if not self._is_reset:
+            raise CopterError('step() called before reset()')    # gymnasium's OrderEnforcing
+        t = self._as_action(action)
+        with torch.cuda.device(self.device):
+            fn = self._lib.copter_step_f32 if self._f32 else self._lib.copter_step_f64
+            b = self._buffers(t, self._force)
+            _lib.check(fn(C.byref(self.params), C.byref(b), self.num_envs, self.env_offset,
+                          self.seed_value & 0xFFFFFFFFFFFFFFFF, self.k_substeps,
+                          VARIANT_IDS[self.variant], _lib.F_AUTO_RESET if self.auto_reset else 0,
+                          self._stream()), 'copter_step')
+        self.launches += 1
+        info = {}
+        if self.final_obs is not None:
+            info['final_obs'] = self.final_obs
+        return self.obs, self.reward, self.done.view(torch.bool), self._truncated, info
+
+    # ---- host-array API (numpy in / numpy out, as the reference's callers use it) ------
+
+    def host_buffers(self):
+        """Page-locked host arrays (numpy views) the host-array step reads and fills:
+        dict(action [N,A], obs [N,O] f32, reward [N], done [N] uint8)."""
+        if self._host is None:
+            n = self.num_envs
+            t = {'action': torch.zeros((n, self.action_size), dtype=self.dtype).pin_memory(),
+                 'obs': torch.zeros((n, self.obs_size), dtype=torch.float32).pin_memory(),
+                 'reward': torch.zeros(n, dtype=self.dtype).pin_memory(),
+                 'done': torch.zeros(n, dtype=torch.uint8).pin_memory()}
+            self._host_t = t
+            self._host = {k: v.numpy() for k, v in t.items()}
+        return self._host
+
+    def step_host(self, action=None, chunk_envs=1 << 20, n_streams=4):
+        """
+        `step()` for callers that live on the host: `action` is a numpy array [N,A] (or None
+        when the caller has filled `host_buffers()['action']` in place, which avoids one host
+        copy); returns numpy (obs, reward, terminated, truncated, info) -- views of the
+        page-locked buffers, valid until the next call.  The host->device copy of the actions,
+        the step kernel and the device->host copies of obs/reward/done are chunked and
+        pipelined over `n_streams` CUDA streams inside copter_step_host_*.
+        """
+        if not self._is_reset:
+            raise CopterError('step() called before reset()')
+        h = self.host_buffers()
+        if action is not None and action is not h['action']:
+            a = np.asarray(action)
+            if a.size != h['action'].size:
+                raise ValueError('action must have shape %s' % (h['action'].shape,))
+            np.copyto(h['action'], a.reshape(h['action'].shape), casting='same_kind')
+        with torch.cuda.device(self.device):
+            if self._pipeline is None:
+                out = C.c_void_p()
+                _lib.check(self._lib.copter_pipeline_create(int(n_streams), C.byref(out)), 'copter_pipeline_create')
+                self._pipeline = out
+            fn = self._lib.copter_step_host_f32 if self._f32 else self._lib.copter_step_host_f64
+            b = self._buffers(self._action, self._force)
+            t = self._host_t
+            _lib.check(fn(self._pipeline, C.byref(self.params), C.byref(b), t['action'].data_ptr(),
+                          t['obs'].data_ptr(), t['reward'].data_ptr(), t['done'].data_ptr(),
+                          self.num_envs, self.env_offset, self.seed_value & 0xFFFFFFFFFFFFFFFF,
+                          self.k_substeps, VARIANT_IDS[self.variant],
+                          _lib.F_AUTO_RESET if self.auto_reset else 0, int(chunk_envs), self._stream()),
+                       'copter_step_host')
+        chunk = (int(chunk_envs) + 255) // 256 * 256
+        self.launches += (self.num_envs + chunk - 1) // chunk
+        return h['obs'], h['reward'], h['done'].view(np.bool_), np.zeros(self.num_envs, np.bool_), {}
+
+    def close(self):
+        if self.viewer is not None:
+            self.viewer.close()
+            self.viewer = None
+        if self._pipeline is not None:
+            self._lib.copter_pipeline_destroy(self._pipeline)
+            self._pipeline = None
+
+    def __del__(self):
+        try:
+            if getattr(self, '_pipeline', None) is not None:
+                self._lib.copter_pipeline_destroy(self._pipeline)
+                self._pipeline = None
+        except Exception:
+            pass
+
+    def render(self, mode='human'):
+        return None if self.viewer is None else self.viewer.render(mode)    # lander.py:75-77
+
+    def set_altitude(self, altitude):
+        self.params.initial_altitude = float(altitude)                      # task.py:67-69
+
+    def seed(self, seed=None):
+        self.seed_value = 0 if seed is None else int(seed)
+        return [self.seed_value]
+
+    @property
+    def unwrapped(self):
+        return self
+
+    # ---- state access -------------------------------------------------------------------
+
+    @property
+    def state(self):
+        """[N,12] copy of the state in the reference's component order (dynamics:48-59)."""
+        return self.state_planes.permute(1, 0, 2).reshape(self.num_envs, 12)
+
+    def set_state(self, state, status=None, steps=None):
+        """
+        Overwrites the 12-component state of every env ([N,12]); status follows
+        Dynamics.setState (AIRBORNE iff z < 0, dynamics:215-217) unless given.  The reward
+        shaping baseline (prev_shaping) is that of the new state.
+        """
+        s = torch.as_tensor(np.asarray(state) if not isinstance(state, torch.Tensor) else state)
+        s = s.to(device=self.device, dtype=self.dtype).reshape(self.num_envs, 12)
+        V = self.state_planes.shape[2]
+        self.state_planes.copy_(s.reshape(self.num_envs, 12 // V, V).permute(1, 0, 2))
+        m = self.meta.to(torch.int64) & 0xFFFFFFFF
+        st = torch.where(s[:, 4] < 0, 3, 1).to(torch.int64) if status is None else \
+            torch.as_tensor(status, device=self.device).to(torch.int64).expand(self.num_envs)
+        stp = ((m >> 2) & 2047) if steps is None else \
+            torch.as_tensor(steps, device=self.device).to(torch.int64).expand(self.num_envs)
+        m = (m & ~0x1FFF) | st | (stp << 2)
+        self.meta.copy_(torch.where(m >= 2 ** 31, m - 2 ** 32, m).to(torch.int32))
+        self.obs.copy_(s[:, list(_OBS_IDX[self.variant])].to(torch.float32))
+
+    def _meta64(self):
+        return self.meta.to(torch.int64) & 0xFFFFFFFF
+
+    @property
+    def status(self):
+        return (self._meta64() & 3).to(torch.int32)
+
+    @property
+    def steps(self):
+        return ((self._meta64() >> 2) & 2047).to(torch.int32)
+
+    @property
+    def episodes(self):
+        return (self._meta64() >> 13).to(torch.int32)
+
+    def stats(self, reduce_group=None):
+        """
+        Episode statistics accumulated on the device since construction (or `clear_stats()`).
+        With `reduce_group` (a torch.distributed process group, or True for the default
+        group) the vector is all-reduced (SUM) over the ranks first -- the only collective
+        this package ever issues.
+        """
+        if self._stats is None:
+            raise CopterError('construct the env with track_stats=True')
+        v = self._stats.clone()
+        if reduce_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(v, op=dist.ReduceOp.SUM, group=None if reduce_group is True else reduce_group)
+        v = v.cpu().numpy()
+        out = {k: float(v[j]) for j, k in enumerate(STAT_NAMES)}
+        ep = max(out['episodes'], 1.0)
+        out['mean_return'], out['mean_length'] = out['return_sum'] / ep, out['length_sum'] / ep
+        return out
+
+    def clear_stats(self):
+        if self._stats is not None:
+            self._stats.zero_()
+
+    # ---- checkpoint ---------------------------------------------------------------------
+
+    def state_dict(self):
+        d = {'variant': self.variant, 'seed': self.seed_value, 'env_offset': self.env_offset,
+             'state_planes': self.state_planes.clone(), 'meta': self.meta.clone(), 'obs': self.obs.clone()}
+        if self._stats is not None:
+            d['stats'] = self._stats.clone()
+        if self.ep_return is not None:
+            d['ep_return'] = self.ep_return.clone()
+        return d
+
+    def load_state_dict(self, d):
+        if d['variant'] != self.variant or d['state_planes'].shape != self.state_planes.shape:
+            raise CopterError('checkpoint does not match this env')
+        self.seed_value, self.env_offset = d['seed'], d['env_offset']
+        self.state_planes.copy_(d['state_planes'])
+        self.meta.copy_(d['meta'])
+        self.obs.copy_(d['obs'])
+        if self._stats is not None and 'stats' in d:
+            self._stats.copy_(d['stats'])
+        if self.ep_return is not None and 'ep_return' in d:
+            self.ep_return.copy_(d['ep_return'])
+        self._is_reset = True
+
+
+def _variant_class(name):
+    def __init__(self, num_envs=1, **kw):
+        CopterVecEnv.__init__(self, name, num_envs, **kw)
+    return type(name + 'Vec', (CopterVecEnv,), {'__init__': __init__, '__doc__': 'CopterVecEnv(%r, ...)' % name})
+
+
+Lander3DVec = _variant_class('Lander3D')
+Lander2DVec = _variant_class('Lander2D')
+Lander1DVec = _variant_class('Lander1D')
+Hover3DVec = _variant_class('Hover3D')
+Hover2DVec = _variant_class('Hover2D')
+Hover1DVec = _variant_class('Hover1D')
+LanderVec = Lander3DVec
+
+
+class SingleEnv:
+    """
+    The reference's single-env call shapes over a one-env batch: numpy float32 obs, python
+    float reward, python bool done, `truncated` always False (envs/task.py:133-137).
+    No auto-reset and float64 arithmetic by default, like the reference.
+    """
+
+    def __init__(self, variant, dtype=torch.float64, **kw):
+        kw.setdefault('auto_reset', False)
+        self.vec = CopterVecEnv(variant, 1, dtype=dtype, **kw)
+        for k in ('observation_space', 'action_space'):
+            setattr(self, k, getattr(self.vec, 'single_' + k))
+        self.STATE_NAMES, self.TARGET_RADIUS = self.vec.STATE_NAMES, self.vec.TARGET_RADIUS
+        self.FRAMES_PER_SECOND, self.metadata = self.vec.FRAMES_PER_SECOND, self.vec.metadata
+        self.viewer, self.pose, self.done = None, None, False
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def reset(self, seed=None, options=None, force=None):
+        obs, info = self.vec.reset(seed, options, None if force is None else np.asarray(force).reshape(1, 3))
+        self.done = False
+        self._update_pose()
+        return obs[0].cpu().numpy(), info
+
+    def step(self, action):
+        a = np.asarray(action, dtype=np.float64).reshape(1, -1)
+        obs, r, term, trunc, info = self.vec.step(a)
+        self.done = bool(term[0].item())
+        self._update_pose()
+        return obs[0].cpu().numpy(), float(r[0].item()), self.done, False, {}
+
+    def _update_pose(self):
+        s = self.vec.state[0].cpu().numpy()
+        self.pose = (s[0], s[2], s[4], s[6], s[8], s[10])          # task.py:102
+
+    def set_altitude(self, altitude):
+        self.vec.set_altitude(altitude)
+
+    def render(self, mode='human'):
+        return None if self.viewer is None else self.viewer.render(mode)
+
+    def close(self):
+        self.vec.close()
+
+
+def _single_class(name):
+    def __init__(self, **kw):
+        SingleEnv.__init__(self, name, **kw)
+    return type(name, (SingleEnv,), {'__init__': __init__})
+
+
+Lander = _single_class('Lander3D')
+Lander3D = Lander
+Lander2D = _single_class('Lander2D')
+Lander1D = _single_class('Lander1D')
+Hover3D = _single_class('Hover3D')
+Hover2D = _single_class('Hover2D')
+Hover1D = _single_class('Hover1D')
+
+
+def make(env_id, **kw):
+    """`gym.make`-shaped constructor: 'Lander-v0' / 'gym_copter:Lander-v0' (gym_copter/__init__.py:9-13)
+    and the batched ids '<Variant>Vec-v0'."""
+    name = env_id.split(':')[-1]
+    name = name[:-3] if name.endswith('-v0') else name
+    table = {'Lander': Lander, 'Lander3D': Lander, 'Lander2D': Lander2D, 'Lander1D': Lander1D,
+             'Hover3D': Hover3D, 'Hover2D': Hover2D, 'Hover1D': Hover1D,
+             'LanderVec': Lander3DVec, 'Lander3DVec': Lander3DVec, 'Lander2DVec': Lander2DVec,
+             'Lander1DVec': Lander1DVec, 'Hover3DVec': Hover3DVec, 'Hover2DVec': Hover2DVec,
+             'Hover1DVec': Hover1DVec}
+    if name not in table:
+        raise ValueError('unknown env id %r' % env_id)
+    return table[name](**kw)

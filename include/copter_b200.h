@@ -1,0 +1,169 @@
+/*
+ * copter_b200.h -- C ABI of libcopter_b200.so: the batched, B200-native (sm_100a) replacement
+ * for the reference's per-env physics + env step.
+ *
+ * The reference (simondlevy/gym-copter) is pure Python and has no FFI of its own; the
+ * boundary this library sits behind is its Python class API.  Each entry point below names
+ * the reference interface it replaces (paths relative to the reference root):
+ *
+ *   copter_default_params      gym_copter/dynamics/vehicles/dji_phantom.py:9-26,
+ *                              gym_copter/dynamics/__init__.py:71-76,
+ *                              gym_copter/envs/task.py:25,32-38, gym_copter/envs/lander.py:17-23
+ *   copter_reset_{f32,f64}     _Task._reset / Lander.reset      envs/task.py:145-197, envs/lander.py:35-37
+ *   copter_step_{f32,f64}      _Task.step + Lander._get_reward/_get_state/_get_motors
+ *                              envs/task.py:77-137, envs/lander.py:39-74,95-97
+ *                              (which call Dynamics.setMotors, dynamics/__init__.py:114-197)
+ *   copter_dynamics_{f32,f64}  Dynamics.setMotors driven directly (take-off style use)
+ *                              dynamics/__init__.py:114-197,210-229
+ *   copter_step_host_{f32,f64} the same step for callers holding HOST buffers (numpy actions as in
+ *                              lander.py:42-44), host<->device copies pipelined inside the call
+ *
+ * Ownership: every device buffer is allocated and owned by the caller (PyTorch CUDA tensors
+ * in the shipped host code).  The library never allocates device memory for the caller,
+ * never frees, and never synchronises the stream it is given (copter_step_host_* is the one
+ * exception: it returns after its own internal streams have drained).
+ * Errors: every function returns 0 on success, a positive cudaError_t from the launch, or a
+ * negative COPTER_E_* argument error.  No exceptions cross the ABI.
+ * Threading: stateless and re-entrant; the caller selects the device (cudaSetDevice /
+ * torch.cuda.device) and passes the stream.  Launches are asynchronous.
+ *
+ * Memory layout (N envs, T = float or double, V = 16/sizeof(T) elements per 128-bit vector):
+ *   state   T[12/V][N][V]   "vector planes": component j of env i is state[j/V][i][j%V], so a
+ *                           thread reads its env with 12/V coalesced 128-bit loads.
+ *                           Component order = the reference's state vector
+ *                           (dynamics/__init__.py:48-59): x dx y dy z dz phi dphi theta dtheta psi dpsi.
+ *   meta    uint32[N]       bits 0-1 flight status (COPTER_STATUS_*), bits 2-12 the env's
+ *                           `steps` counter (envs/task.py:128-130; saturates at 2047), bits 13-31
+ *                           episode index (wraps at 2^19; keys the reset-force stream).
+ *   action  T[N][A]         row-major, A = action size of the variant.
+ *   obs     float[N][O]     row-major float32 (envs/task.py:133), O = observation size.
+ *   reward  T[N]; done uint8[N] (0/1).
+ */
+#ifndef COPTER_B200_H
+#define COPTER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COPTER_ABI_VERSION 1
+
+/* dynamics/__init__.py:65-68 */
+enum { COPTER_STATUS_CRASHED = 0, COPTER_STATUS_LANDED = 1, COPTER_STATUS_LEVELING = 2, COPTER_STATUS_AIRBORNE = 3 };
+
+/* env variants: the live Lander (= Lander3D) and the attic-defined projections */
+enum { COPTER_LANDER3D = 0, COPTER_LANDER2D = 1, COPTER_LANDER1D = 2,
+       COPTER_HOVER3D = 3, COPTER_HOVER2D = 4, COPTER_HOVER1D = 5, COPTER_NUM_VARIANTS = 6 };
+
+enum { COPTER_E_ARG = -1, COPTER_E_VARIANT = -2, COPTER_E_ALIGN = -3, COPTER_E_RANGE = -4 };
+
+/* flags for copter_step_* */
+enum { COPTER_F_AUTO_RESET = 1 };
+
+/* episode statistics vector (double[COPTER_STATS_LEN]); accumulated with atomics, never cleared by the library */
+enum { COPTER_STAT_EPISODES = 0, COPTER_STAT_RETURN_SUM = 1, COPTER_STAT_LENGTH_SUM = 2,
+       COPTER_STAT_LANDED = 3, COPTER_STAT_BONUS = 4, COPTER_STAT_CRASHED = 5, COPTER_STAT_OOB = 6,
+       COPTER_STAT_ANGLE = 7, COPTER_STAT_TIMEOUT = 8, COPTER_STAT_ENV_STEPS = 9, COPTER_STATS_LEN = 16 };
+
+#define COPTER_META_STATUS(m)  ((m) & 3u)
+#define COPTER_META_STEPS(m)   (((m) >> 2) & 2047u)
+#define COPTER_META_EPISODE(m) ((m) >> 13)
+#define COPTER_MAX_STEPS_LIMIT 2046
+
+typedef struct CopterParams {
+    /* vehicle (dji_phantom.py:9-26) */
+    double B, D, M, L, Ix, Iy, Iz, Jr, maxrpm;
+    /* dynamics/__init__.py:71-76 */
+    double landing_vel_x, landing_vel_y, landing_angle, G;
+    /* envs/task.py:25,32-38 */
+    double fps, initial_random_force, out_of_bounds_penalty, max_angle_deg, bounds, initial_altitude;
+    /* envs/lander.py:17-23 */
+    double target_radius, yaw_penalty_factor, xyz_penalty_factor, dz_max, dz_penalty, inside_radius_bonus;
+    int32_t max_steps;
+    int32_t reserved;
+} CopterParams;
+
+int copter_abi_version(void);
+void copter_default_params(CopterParams* p);
+int copter_obs_size(int variant);      /* O, or COPTER_E_VARIANT */
+int copter_action_size(int variant);   /* A, or COPTER_E_VARIANT */
+
+/* Buffers of one shard of envs; all device pointers. Nullable members are marked. */
+typedef struct CopterBuffers {
+    void*       state;       /* T[12/V][n][V] */
+    uint32_t*   meta;        /* [n] */
+    const void* action;      /* T[n][A]            (unused by reset) */
+    float*      obs;         /* [n][O]             nullable: skip the observation write */
+    void*       reward;      /* T[n]               (unused by reset) */
+    uint8_t*    done;        /* [n]                (unused by reset) */
+    const void* init_force;  /* T[n][3] nullable: injected reset force (N) used instead of the Philox draw */
+    void*       ep_return;   /* T[n]   nullable: running episode return, feeds COPTER_STAT_RETURN_SUM */
+    double*     stats;       /* [COPTER_STATS_LEN] nullable */
+    float*      final_obs;   /* [n][O] nullable: observation of the terminal state of envs that finished */
+    int64_t     state_stride;/* vectors per state plane in the allocation; 0 means n. Lets a call step a
+                                sub-range [lo, lo+n) of a larger shard: pass state + lo vectors, stride = shard size */
+} CopterBuffers;
+
+/*
+ * Reset every env of the shard: default pose, status, steps = 1, episode = 0, obs of the
+ * initial state.  The reset force is not stored: it is (re)generated on the first step of
+ * an episode from Philox4x32-10 with counter (env_lo, env_hi, episode, 0), key = seed,
+ * env = env_offset + i, unless init_force is given to copter_step_*.
+ */
+int copter_reset_f32(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, void* stream);
+int copter_reset_f64(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, void* stream);
+
+/*
+ * One launch = k_substeps reference steps for each of the n envs under one action (rewards
+ * summed; an env that finishes idles for the rest of the launch).  With COPTER_F_AUTO_RESET
+ * a finished env is replaced in the same launch by a fresh reset state and `obs` holds that
+ * state's observation; without it the env keeps stepping past `done` like the reference.
+ */
+int copter_step_f32(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_t env_offset,
+                    uint64_t seed, int k_substeps, int variant, int flags, void* stream);
+int copter_step_f64(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_t env_offset,
+                    uint64_t seed, int k_substeps, int variant, int flags, void* stream);
+
+/*
+ * Batched Dynamics.setMotors: state T[12/V][n][V], status uint8[n], ticks int32[n],
+ * perturb T[n][6] (ACCELERATIONS, i.e. force/M as stored by Dynamics.perturb; consumed and
+ * zeroed exactly when the reference does), motors T[n][4].
+ */
+int copter_dynamics_f32(const CopterParams* p, void* state, uint8_t* status, int32_t* ticks,
+                        void* perturb, const void* motors, int64_t n, void* stream);
+int copter_dynamics_f64(const CopterParams* p, void* state, uint8_t* status, int32_t* ticks,
+                        void* perturb, const void* motors, int64_t n, void* stream);
+
+/* Reset-force stream exposed for tests and host-side mirrors: out T[n][3]. */
+int copter_reset_force_f32(const CopterParams* p, float* out, const uint32_t* episode_or_null,
+                           int64_t n, int64_t env_offset, uint64_t seed, void* stream);
+int copter_reset_force_f64(const CopterParams* p, double* out, const uint32_t* episode_or_null,
+                           int64_t n, int64_t env_offset, uint64_t seed, void* stream);
+
+/*
+ * The same step for callers that hold HOST arrays (the reference's callers pass numpy
+ * arrays, lander.py:42-44).  The shard is cut into chunks of `chunk_envs`; for each chunk
+ * the action rows are copied host->device, the step kernel runs on that sub-range, and
+ * obs/reward/done are copied device->host, round-robin over the pipeline's streams so the
+ * two PCIe directions and the kernel overlap.  `dev` are the device buffers of the whole
+ * shard (dev->action is the device staging area for the actions).  Host arrays should be
+ * page-locked for the copies to be asynchronous.  Work is ordered after `stream`; the call
+ * returns when all chunks have landed in the host arrays.
+ */
+int copter_pipeline_create(int n_streams, void** out_pipeline);      /* 1..8 streams */
+int copter_pipeline_destroy(void* pipeline);
+int copter_step_host_f32(void* pipeline, const CopterParams* p, const CopterBuffers* dev,
+                         const float* h_action, float* h_obs_or_null, float* h_reward, uint8_t* h_done,
+                         int64_t n, int64_t env_offset, uint64_t seed, int k_substeps, int variant,
+                         int flags, int64_t chunk_envs, void* stream);
+int copter_step_host_f64(void* pipeline, const CopterParams* p, const CopterBuffers* dev,
+                         const double* h_action, float* h_obs_or_null, double* h_reward, uint8_t* h_done,
+                         int64_t n, int64_t env_offset, uint64_t seed, int k_substeps, int variant,
+                         int flags, int64_t chunk_envs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

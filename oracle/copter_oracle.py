@@ -244,13 +244,16 @@ class DynamicsBatch:
 class EnvBatch:
 
     def __init__(self, variant, n, params=None, dtype=np.float64, seed=0, env_offset=0,
-                 auto_reset=True):
+                 auto_reset=True, env_ids=None):
         self.kind, self.obs_idx, self.act_size, self.fanout = VARIANTS[variant]
         self.obs_idx, self.fanout = list(self.obs_idx), list(self.fanout)
         self.variant, self.n = variant, n
         self.p = params or OracleParams()
         self.dtype = np.dtype(dtype)
         self.seed, self.env_offset, self.auto_reset = seed, env_offset, auto_reset
+        # global env ids (key the Philox stream); default: a contiguous shard
+        self.env_ids = (np.arange(n, dtype=np.uint64) + np.uint64(env_offset) if env_ids is None
+                        else np.asarray(env_ids, dtype=np.uint64))
         self.dyn = DynamicsBatch(n, self.p, dtype)
         self.steps = np.zeros(n, np.int64)
         self.episode = np.zeros(n, np.int64)
@@ -272,8 +275,7 @@ class EnvBatch:
         return self.dyn.x[:, self.obs_idx].astype(np.float32)
 
     def forces_for(self, env_mask):
-        ids = np.arange(self.n, dtype=np.uint64) + np.uint64(self.env_offset)
-        return reset_force(self.seed, ids, self.episode, self.p.initial_random_force, self.dtype)
+        return reset_force(self.seed, self.env_ids, self.episode, self.p.initial_random_force, self.dtype)
 
     def reset_where(self, w, force=None):
         """
