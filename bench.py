@@ -38,8 +38,8 @@ STREAMS = ('randn', 'const', 'unif')
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
-    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=1000)
+    ap.add_argument('--warmup', type=int, default=50)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--envs-per-gpu', type=int, default=1 << 24)
     ap.add_argument('--k-substeps', type=int, default=1)
@@ -58,52 +58,52 @@ def parse():
 # clocks
 # ---------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, every 5 ms)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mx, self.reasons, self.stop = index, [], None, set(), False
+        self.thread = None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            try:
+                vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+                idx = int(vis.split(',')[self.index]) if vis else self.index
+            except Exception:
+                idx = self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {'hw_slowdown': nv.nvmlClocksThrottleReasonHwSlowdown,
+                    'hw_thermal_slowdown': nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    'sw_thermal_slowdown': nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    'sw_power_cap': nv.nvmlClocksThrottleReasonSwPowerCap}
+
+            def loop():
+                while not self.stop:
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.reasons.update(k for k, b in bits.items() if r & b)
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+            self.thread = threading.Thread(target=loop, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
-
     def __exit__(self, *a):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self.stop = True
+        if self.thread is not None:
+            self.thread.join(timeout=1)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
-        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(names, r[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        sm.sort()
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        sm = sorted(self.sm)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.mx,
+                'reasons': sorted(self.reasons), 'samples': len(sm)}
 
 
 # ---------------------------------------------------------------------------------------
@@ -297,6 +297,13 @@ def main():
         cpu = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'single_core': one,
                'sample': '%d processes x one per-object Python Lander loop (oracle/scalar_port.py), %s stream, '
                          '%.0f s, reset on done' % (cores, args.stream, args.cpu_seconds)}
+        try:        # context: the oracle's compiled C restatement, OpenMP over all host threads
+            from oracle.c_oracle import throughput
+            cpu['c_port'] = {'value': throughput(args.stream, 4.0, cores), 'unit': UNIT, 'cores': cores,
+                             'single_core': throughput(args.stream, 2.0, 1),
+                             'sample': 'oracle/copter_oracle.c, 65536 envs, fp64, %s stream, 4 s' % args.stream}
+        except Exception as e:
+            cpu['c_port'] = {'unavailable': repr(e)[:200]}
 
     if rank == 0:
         line = {

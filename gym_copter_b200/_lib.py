@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, 'libcopter_b200.so')
+# COPTER_B200_LIB: developer knob used by tools/sweep.py to time alternative builds
+LIB_PATH = os.environ.get('COPTER_B200_LIB') or os.path.join(PKG, 'libcopter_b200.so')
 
 ABI_VERSION = 1
 STATS_LEN = 16

@@ -29,7 +29,18 @@
 
 namespace {
 
-constexpr int kBlock = 256;
+#ifndef COPTER_F32_CTAS_PER_SM
+#define COPTER_F32_CTAS_PER_SM 4
+#endif
+
+#ifndef COPTER_BLOCK
+#define COPTER_BLOCK 256
+#endif
+#ifndef COPTER_STREAMING
+#define COPTER_STREAMING 0      // 1: evict-first (ld/st .cs) hints on the state planes
+#endif
+
+constexpr int kBlock = COPTER_BLOCK;
 constexpr int kWarpsPerBlock = kBlock / 32;
 
 enum { ST_CRASHED = 0, ST_LANDED = 1, ST_LEVELING = 2, ST_AIRBORNE = 3 };
@@ -111,7 +122,7 @@ __device__ __forceinline__ void load_state(const T* __restrict__ state, int64_t 
     const V4* planes = reinterpret_cast<const V4*>(state);
 #pragma unroll
     for (int pl = 0; pl < 12 / V; ++pl) {
-        V4 v = planes[(int64_t)pl * stride + i];
+        V4 v = COPTER_STREAMING ? __ldcs(&planes[(int64_t)pl * stride + i]) : planes[(int64_t)pl * stride + i];
         const T* e = reinterpret_cast<const T*>(&v);
 #pragma unroll
         for (int j = 0; j < V; ++j) s[pl * V + j] = e[j];
@@ -129,7 +140,7 @@ __device__ __forceinline__ void store_state(T* __restrict__ state, int64_t strid
         T* e = reinterpret_cast<T*>(&v);
 #pragma unroll
         for (int j = 0; j < V; ++j) e[j] = s[pl * V + j];
-        planes[(int64_t)pl * stride + i] = v;
+        if (COPTER_STREAMING) __stcs(&planes[(int64_t)pl * stride + i], v); else planes[(int64_t)pl * stride + i] = v;
     }
 }
 
@@ -224,25 +235,50 @@ __device__ __forceinline__ bool dynamics_update(const KParams<T>& kp, T (&s)[12]
     return true;
 }
 
-// envs/lander.py:48-56
+// envs/lander.py:48-56, kept as its three ingredients: shaping = -(xyz_pf*ra + yaw_pf*rc) - pen
+template <typename T> struct Shaping { T ra, rc, pen; };
+
 template <typename T>
-__device__ __forceinline__ T lander_shaping(const KParams<T>& kp, const T (&s)[12]) {
+__device__ __forceinline__ Shaping<T> lander_shaping(const KParams<T>& kp, const T (&s)[12]) {
     const T spos = ((((s[0] * s[0] + s[1] * s[1]) + s[2] * s[2]) + s[3] * s[3]) + s[4] * s[4]) + s[5] * s[5];
     const T spsi = s[10] * s[10] + s[11] * s[11];
-    T sh = -(kp.xyz_pf * sqrt_t(spos) + kp.yaw_pf * sqrt_t(spsi));
-    if (abs_t(s[5]) > kp.dz_max) sh -= kp.dz_penalty;
+    Shaping<T> sh;
+    sh.ra = sqrt_t(spos);
+    sh.rc = sqrt_t(spsi);
+    sh.pen = abs_t(s[5]) > kp.dz_max ? kp.dz_penalty : (T)0;
     return sh;
+}
+
+// reward = shaping(post) - shaping(pre) (envs/lander.py:58-62), evaluated without the
+// cancellation of two O(250..1e4) numbers:  sqrt(a1) - sqrt(a0) = (a1 - a0) / (sqrt(a1) + sqrt(a0))
+// and a1 - a0 = sum_j (post_j - pre_j)(post_j + pre_j).  In fp32 this keeps the error
+// proportional to |reward| instead of |shaping| (which reaches 1e-3 absolute on fast
+// trajectories); in fp64 it agrees with the reference's literal subtraction to ~1e-13.
+// `pre8` = (x,dx,y,dy,z,dz,psi,dpsi) before the step.
+template <typename T>
+__device__ __forceinline__ T shaping_delta(const KParams<T>& kp, const T (&pre8)[8], const Shaping<T>& pre,
+                                           const T (&s)[12], const Shaping<T>& post) {
+    T na = (T)0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) na += (s[j] - pre8[j]) * (s[j] + pre8[j]);
+    const T nc = (s[10] - pre8[6]) * (s[10] + pre8[6]) + (s[11] - pre8[7]) * (s[11] + pre8[7]);
+    const T da = post.ra + pre.ra, dc = post.rc + pre.rc;
+    const T ga = da > (T)0 ? na / da : (T)0;
+    const T gc = dc > (T)0 ? nc / dc : (T)0;
+    return -(kp.xyz_pf * ga + kp.yaw_pf * gc) - (post.pen - pre.pen);
 }
 
 // One reference _Task.step (envs/task.py:77-137) for one env held in registers.
 // `steps`/`st` are the env's counters; `pre_sh` is shaping(pre-step state) == prev_shaping
 // (the priming step of _reset sets it to shaping(s0) and every later step stores the
-// post-step value, task.py:197, lander.py:62).  On return `pre_sh` holds shaping(post).
+// post-step value, task.py:197, lander.py:62), so it never has to live in HBM.  On return
+// `pre_sh` holds shaping(post).
 template <typename T, int VARIANT>
 __device__ __forceinline__ void env_substep(const KParams<T>& kp, T (&s)[12], int& st, int& steps,
-                                            const T (&m)[4], const T (&pert)[3], T& pre_sh,
+                                            const T (&m)[4], const T (&pert)[3], Shaping<T>& pre_sh,
                                             T& reward, bool& done, int& cause) {
     const int st0 = st;                                            // :81 stale status
+    const T pre8[8] = {s[0], s[1], s[2], s[3], s[4], s[5], s[10], s[11]};
     if (st0 != ST_LANDED) {                                        // :86-94
         const Forces<T> f = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
         dynamics_update<T, 3, false>(kp, s, st, f, pert);
@@ -250,8 +286,8 @@ __device__ __forceinline__ void env_substep(const KParams<T>& kp, T (&s)[12], in
     cause = 0;
     done = false;
     if (Variant<VARIANT>::lander) {
-        const T sh = lander_shaping<T>(kp, s);                     // lander.py:48-56
-        reward = sh - pre_sh;                                      // :58-62
+        const Shaping<T> sh = lander_shaping<T>(kp, s);            // lander.py:48-56
+        reward = shaping_delta<T>(kp, pre8, pre_sh, s, sh);        // :58-62
         pre_sh = sh;
         if (st0 == ST_LANDED) {                                    // :64-72
             done = true; cause |= CAUSE_LANDED;
@@ -315,7 +351,7 @@ struct StepArgs {
 };
 
 template <typename T, int VARIANT, bool STATS>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? COPTER_F32_CTAS_PER_SM : 2)
 copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant__ StepArgs<T> a) {
     constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A;
     __shared__ __align__(16) float tiles[kWarpsPerBlock][32 * O];
@@ -379,9 +415,7 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
             for (int j = 0; j < 12; ++j) s[j] = (T)0;
         }
 
-        T final_s[12];
-        bool want_final = (a.final_obs != nullptr);
-        T pre_sh = Variant<VARIANT>::lander ? lander_shaping<T>(kp, s) : (T)0;
+        Shaping<T> pre_sh = lander_shaping<T>(kp, s);
 
         for (int k = 0; k < a.k; ++k) {
             const bool live = valid && !done_any;
@@ -408,9 +442,9 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
                         n_crashed += (cause & CAUSE_CRASHED) != 0; n_oob += (cause & CAUSE_OOB) != 0;
                         n_angle += (cause & CAUSE_ANGLE) != 0; n_timeout += (cause & CAUSE_TIMEOUT) != 0;
                     }
-                    if (want_final) {
+                    if (a.final_obs) {   // terminal observation; rows of unfinished envs stay untouched
 #pragma unroll
-                        for (int j = 0; j < 12; ++j) final_s[j] = s[j];
+                        for (int j = 0; j < O; ++j) a.final_obs[i * O + j] = (float)s[Variant<VARIANT>::first + j];
                     }
                     if (a.auto_reset) {
                         reset_state<T>(kp, s, st, steps);
@@ -429,14 +463,6 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
             if (STATS && a.ep_return) a.ep_return[i] = ret;
         }
         if (a.obs) write_obs_rows<VARIANT, T>(a.obs, tile, lane, row0, rows, s);
-        if (want_final && __any_sync(0xffffffffu, done_any)) {
-            // terminal observation of finished envs; rows of unfinished envs are left untouched
-            constexpr int first = Variant<VARIANT>::first;
-            if (valid && done_any) {
-#pragma unroll
-                for (int j = 0; j < O; ++j) a.final_obs[i * O + j] = (float)final_s[first + j];
-            }
-        }
     }
 
     if (STATS) {

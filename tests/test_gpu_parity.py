@@ -57,7 +57,13 @@ def action_streams(rng, n, t, a):
 
 
 class Tracker:
-    """Differential comparison with the divergence rule described in the module docstring."""
+    """Differential comparison with the divergence rule described in the module docstring.
+    The discrete outputs (done flag, flight status, step counter, episode index) must agree
+    bit for bit; on the fp32 path an env whose discrete outputs differ (a threshold comparison
+    flipped by rounding) is counted as a flip and leaves the comparison, because from then on
+    its episode timeline is shifted against the oracle's."""
+
+    F32_EPS = 1.2e-7          # float32 observations can differ in the last bit on any path
 
     def __init__(self, n, dtype):
         self.sync = np.ones(n, bool)
@@ -65,20 +71,28 @@ class Tracker:
         self.flips, self.episodes = 0, 0
         self.max_state = self.max_reward = self.max_obs = 0.0
 
-    def compare(self, done, reward, state, obs, steps, o_done, o_reward, o_state, o_obs, o_steps):
-        bad = self.sync & (done != o_done)
+    def compare(self, done, reward, state, obs, discrete, o_done, o_reward, o_state, o_obs, o_discrete):
+        bad = done != o_done
+        for a, b in zip(discrete, o_discrete):
+            bad |= np.asarray(a) != np.asarray(b)
+        r_err = np.abs(reward - o_reward) / np.maximum(np.abs(o_reward), 1.0)
+        if not self.exact:
+            # inside a K-fused launch an episode may end one substep early/late with both sides
+            # reporting done: the summed reward then differs by one step's reward
+            bad |= o_done & (r_err > self.tol)
+        bad &= self.sync
         self.flips += int(bad.sum())
         self.sync &= ~bad
         s = self.sync
         self.episodes += int((o_done & s).sum())
-        self.max_reward = max(self.max_reward, merr(reward[s], o_reward[s]))
-        self.max_state = max(self.max_state, merr(state[s], o_state[s]))
-        self.max_obs = max(self.max_obs, merr(obs[s], o_obs[s]))
-        assert np.array_equal(steps[s], o_steps[s])
+        if s.any():
+            self.max_reward = max(self.max_reward, float(r_err[s].max()))
+            self.max_state = max(self.max_state, merr(state[s], o_state[s]))
+            self.max_obs = max(self.max_obs, merr(obs[s], o_obs[s]))
 
     def finish(self, min_episodes=1):
         assert self.max_state <= self.tol, self.max_state
-        assert self.max_obs <= self.tol, self.max_obs
+        assert self.max_obs <= max(self.tol, self.F32_EPS), self.max_obs
         assert self.max_reward <= self.tol, self.max_reward
         assert self.episodes >= min_episodes
         if self.exact:
@@ -115,7 +129,7 @@ def test_golden_trajectories(pkg, golden_dir, variant, dtype):
             st = ref_st = np.zeros((N, 12))
         o = obs.cpu().numpy() if t % 10 == 9 else np.zeros((N, len(obs_idx)), np.float32)
         ref_o = ref_st[:, obs_idx].astype(np.float32) if t % 10 == 9 else o
-        tr.compare(done, r.cpu().numpy(), st, o, steps, g['done'][t], g['reward'][t], ref_st, ref_o, g_steps)
+        tr.compare(done, r.cpu().numpy(), st, o, [steps], g['done'][t], g['reward'][t], ref_st, ref_o, [g_steps])
         assert not trunc.any()
     tr.finish(min_episodes=10)
     if dtype == torch.float64:
@@ -142,10 +156,8 @@ def test_batch_vs_oracle_philox_autoreset(pkg, variant, k, dtype):
         obs, r, term, _, _ = env.step(torch.as_tensor(act[t]))
         o_obs, o_r, o_done, info = orc.step(act[t].astype(np.float64), k_substeps=k)
         tr.compare(term.cpu().numpy(), r.cpu().numpy(), env.state.cpu().numpy(), obs.cpu().numpy(),
-                   env.steps.cpu().numpy(), o_done, o_r, orc.dyn.x, o_obs, orc.steps)
-        s = tr.sync
-        assert np.array_equal(env.status.cpu().numpy()[s], orc.dyn.status[s])
-        assert np.array_equal(env.episodes.cpu().numpy()[s], orc.episode[s])
+                   [env.steps.cpu().numpy(), env.status.cpu().numpy(), env.episodes.cpu().numpy()],
+                   o_done, o_r, orc.dyn.x, o_obs, [orc.steps, orc.dyn.status, orc.episode])
     tr.finish(min_episodes=N)
 
 
@@ -153,7 +165,7 @@ def test_fp32_1000_step_episodes_within_budget(pkg):
     """Long-lived episodes (near-hover constant and jittered commands): the fp32 path must hold
     1e-4 against the fp64 oracle over the full 1000 steps (the case that breaks an all-fp32
     thrust computation)."""
-    N, T = 4096, 1000
+    N, T = 4096, 999           # the 1000th step ends every episode (task.py:128)
     rng = np.random.default_rng(5)
     base = (HOVER * (1 + 0.0005 * rng.uniform(-1, 1, (N, 4)))).astype(np.float32)
     env = pkg.CopterVecEnv('Lander3D', N, dtype=torch.float32, seed=3, auto_reset=False)
@@ -239,7 +251,7 @@ def test_soft_landing_fsm(pkg, kat):
         env.reset(force=np.zeros((5, 3)))
         env.set_state(np.tile(np.array(g['s0']), (5, 1)))
         for tr in g['trace']:
-            obs, r, term, _, _ = env.step(np.full((5, 4), g['action'], np.float32))
+            obs, r, term, _, _ = env.step(np.full((5, 4), g['action'], NP_T[dtype]))
             assert env.status.tolist() == [tr['status']] * 5
             assert term.tolist() == [tr['done']] * 5
             assert merr(r.cpu().numpy(), [tr['reward']] * 5) <= TOL[dtype]

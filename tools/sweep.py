@@ -1,0 +1,89 @@
+#!/usr/bin/env python3
+"""
+Developer tool: build-time parameter sweep of the step kernel (CTAs/SM target, block size,
+cache hints).  `build` cross-compiles the variants here (no GPU needed) into tools/variants/;
+`run` times each on the GPU box (one subprocess per variant) and prints achieved GB/s.
+
+    python tools/sweep.py build
+    gpurun -- python tools/sweep.py run [--envs N] [--k K]
+"""
+import itertools
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VDIR = os.path.join(ROOT, 'tools', 'variants')
+SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
+
+VARIANTS = {}
+for ctas, block, cs in itertools.product((3, 4, 5, 6), (128, 256, 512), (0, 1)):
+    if (ctas, block) in ((3, 128), (6, 512), (5, 512)):
+        continue
+    per_sm = ctas * 256 // block          # keep threads/SM = ctas*256
+    VARIANTS['t%d_b%d_cs%d' % (ctas * 256, block, cs)] = ['-DCOPTER_F32_CTAS_PER_SM=%d' % per_sm,
+                                                          '-DCOPTER_BLOCK=%d' % block, '-DCOPTER_STREAMING=%d' % cs]
+
+
+def build():
+    os.makedirs(VDIR, exist_ok=True)
+    procs = []
+    for name, flags in VARIANTS.items():
+        out = os.path.join(VDIR, 'lib_%s.so' % name)
+        cmd = ['nvcc', '-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
+               '-Xcompiler', '-fPIC', '-shared'] + flags + ['-o', out, SRC]
+        procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        if len(procs) >= 8:
+            for n, p in procs:
+                o, _ = p.communicate()
+                print(n, 'rc', p.returncode, o[-200:] if p.returncode else '')
+            procs = []
+    for n, p in procs:
+        o, _ = p.communicate()
+        print(n, 'rc', p.returncode, o[-200:] if p.returncode else '')
+
+
+def time_one(envs, k, steps, stats):
+    import torch
+    sys.path.insert(0, ROOT)
+    import gym_copter_b200 as g
+    env = g.LanderVec(envs, seed=1, k_substeps=k, track_stats=bool(stats))
+    env.reset()
+    acts = [1.625e-2 * torch.randn((envs, 4), device='cuda') for _ in range(4)]
+    for i in range(20):
+        env.step(acts[i % 4])
+    best = 1e9
+    for rep in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(steps):
+            env.step(acts[i % 4])
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / steps)
+    print(json.dumps({'ms': best, 'gbs': 165 * envs / best / 1e6, 'steps_per_s': envs * k / best * 1e3}))
+
+
+def run(envs, k, stats):
+    for name in VARIANTS:
+        lib = os.path.join(VDIR, 'lib_%s.so' % name)
+        if not os.path.exists(lib):
+            continue
+        env = dict(os.environ, COPTER_B200_LIB=lib)
+        r = subprocess.run([sys.executable, __file__, 'one', str(envs), str(k), str(stats)], env=env, capture_output=True, text=True)
+        print('%-16s %s' % (name, r.stdout.strip() or r.stderr[-300:]), flush=True)
+
+
+if __name__ == '__main__':
+    a = sys.argv[1:]
+    if a[0] == 'build':
+        build()
+    elif a[0] == 'one':
+        time_one(int(a[1]), int(a[2]), 200 if int(a[2]) == 1 else 40, int(a[3]))
+    else:
+        envs = int(a[a.index('--envs') + 1]) if '--envs' in a else 1 << 24
+        k = int(a[a.index('--k') + 1]) if '--k' in a else 1
+        stats = int(a[a.index('--stats') + 1]) if '--stats' in a else 0
+        run(envs, k, stats)
