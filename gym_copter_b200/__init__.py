@@ -11,5 +11,6 @@ from .envs import (CopterVecEnv, LanderVec, Lander3DVec, Lander2DVec, Lander1DVe
                    Hover3DVec, Hover2DVec, Hover1DVec, Lander, Lander3D, Lander2D,
                    Lander1D, Hover3D, Hover2D, Hover1D, SingleEnv, make)
 from .dynamics import Dynamics                                                         # noqa: F401
+from .sharding import shard_range, make_sharded_env, all_reduce_stats                  # noqa: F401
 
 __version__ = '0.1.0'

@@ -36,6 +36,9 @@ namespace {
 #ifndef COPTER_BLOCK
 #define COPTER_BLOCK 256
 #endif
+#ifndef COPTER_LIBM_ONLY
+#define COPTER_LIBM_ONLY 0      // 1 (A/B knob): library sincosf, IEEE sqrt and division everywhere
+#endif
 #ifndef COPTER_STREAMING
 #define COPTER_STREAMING 0      // 1: evict-first (ld/st .cs) hints on the state planes
 #endif
@@ -108,10 +111,35 @@ template <typename T> struct Vec;
 template <> struct Vec<float>  { using type = float4;  static constexpr int V = 4; };
 template <> struct Vec<double> { using type = double2; static constexpr int V = 2; };
 
-__device__ __forceinline__ void sincos_t(float a, float* s, float* c)   { sincosf(a, s, c); }
+// fp32 sin/cos.  |a| <= pi/4 needs no range reduction: evaluate the same degree-7 / degree-8
+// minimax polynomials the accurate sincosf uses on its reduced interval (max rel. error
+// 7e-8 / 9e-8 over the interval) and skip its quadrant logic; anything larger takes the
+// library's accurate path (roll/pitch beyond pi/4 end the episode, task.py:116, so in
+// practice only a large yaw angle ever does).  Never the SFU approximations (__sinf/__cosf).
+__device__ __forceinline__ void sincos_t(float a, float* s, float* c) {
+    if (!COPTER_LIBM_ONLY && fabsf(a) <= 0.78539816f) {
+        const float z = a * a;
+        float ps = fmaf(z, -1.95152959e-4f, 8.33216087e-3f);
+        ps = fmaf(ps, z, -1.66666546e-1f);
+        *s = fmaf(a * z, ps, a);
+        float pc = fmaf(z, 2.44331571e-5f, -1.38873163e-3f);
+        pc = fmaf(pc, z, 4.16666456e-2f);
+        pc = fmaf(pc, z, -0.5f);
+        *c = fmaf(pc, z, 1.0f);
+    } else {
+        sincosf(a, s, c);
+    }
+}
 __device__ __forceinline__ void sincos_t(double a, double* s, double* c) { sincos(a, s, c); }
 __device__ __forceinline__ float  sqrt_t(float a)  { return sqrtf(a); }
 __device__ __forceinline__ double sqrt_t(double a) { return sqrt(a); }
+// Reward-only helpers (never used for the state): on the fp32 path sqrt and the quotient of
+// shaping_delta go through MUFU.RSQ / MUFU.RCP (<= 2 ulp), a few 1e-7 of the reward against a
+// 1e-4 budget; the fp64 path keeps IEEE sqrt and division.
+__device__ __forceinline__ float  reward_sqrt(float a)  { return COPTER_LIBM_ONLY ? sqrtf(a) : (a > 0.0f ? a * rsqrtf(a) : 0.0f); }
+__device__ __forceinline__ double reward_sqrt(double a) { return sqrt(a); }
+__device__ __forceinline__ float  reward_div(float n, float d)   { return COPTER_LIBM_ONLY ? n / d : __fdividef(n, d); }
+__device__ __forceinline__ double reward_div(double n, double d) { return n / d; }
 __device__ __forceinline__ float  abs_t(float a)  { return fabsf(a); }
 __device__ __forceinline__ double abs_t(double a) { return fabs(a); }
 
@@ -191,9 +219,13 @@ __device__ __forceinline__ Forces<T> motor_forces(const KParams<T>& kp, T m0, T 
 // facade).  DIRECT enables the LANDED -> AIRBORNE take-off transition, unreachable through
 // _Task.step (task.py:86-94).  Returns true when the call ran to the end of setMotors
 // (perturbation cleared, ticks += 1), false on the ground-contact early return (:177).
+// `inc` receives the UNROUNDED Euler increments dt*ds of (x,dx,y,dy,z,dz,psi,dpsi) -- zero when
+// the state was not integrated -- for the reward (see shaping_delta).
 template <typename T, int NP, bool DIRECT>
 __device__ __forceinline__ bool dynamics_update(const KParams<T>& kp, T (&s)[12], int& st,
-                                                const Forces<T>& f, const T (&p)[NP]) {
+                                                const Forces<T>& f, const T (&p)[NP], T (&inc)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) inc[j] = (T)0;
     T sph, cph, sth, cth, sps, cps;
     sincos_t(s[6], &sph, &cph);
     sincos_t(s[8], &sth, &cth);
@@ -225,6 +257,8 @@ __device__ __forceinline__ bool dynamics_update(const KParams<T>& kp, T (&s)[12]
         if constexpr (NP == 6) { d7 += (T)2 * p[3]; d9 += (T)2 * p[4]; d11 += (T)2 * p[5]; }
         // forward Euler, every derivative from the old state (:187)
         const T dt = kp.dt;
+        inc[0] = dt * s[1]; inc[1] = dt * d1; inc[2] = dt * s[3]; inc[3] = dt * d3;
+        inc[4] = dt * s[5]; inc[5] = dt * d5; inc[6] = dt * dpsi; inc[7] = dt * d11;
         s[0] += dt * s[1];  s[1] += dt * d1;
         s[2] += dt * s[3];  s[3] += dt * d3;
         s[4] += dt * s[5];  s[5] += dt * d5;
@@ -243,28 +277,30 @@ __device__ __forceinline__ Shaping<T> lander_shaping(const KParams<T>& kp, const
     const T spos = ((((s[0] * s[0] + s[1] * s[1]) + s[2] * s[2]) + s[3] * s[3]) + s[4] * s[4]) + s[5] * s[5];
     const T spsi = s[10] * s[10] + s[11] * s[11];
     Shaping<T> sh;
-    sh.ra = sqrt_t(spos);
-    sh.rc = sqrt_t(spsi);
+    sh.ra = reward_sqrt(spos);
+    sh.rc = reward_sqrt(spsi);
     sh.pen = abs_t(s[5]) > kp.dz_max ? kp.dz_penalty : (T)0;
     return sh;
 }
 
 // reward = shaping(post) - shaping(pre) (envs/lander.py:58-62), evaluated without the
 // cancellation of two O(250..1e4) numbers:  sqrt(a1) - sqrt(a0) = (a1 - a0) / (sqrt(a1) + sqrt(a0))
-// and a1 - a0 = sum_j (post_j - pre_j)(post_j + pre_j).  In fp32 this keeps the error
-// proportional to |reward| instead of |shaping| (which reaches 1e-3 absolute on fast
-// trajectories); in fp64 it agrees with the reference's literal subtraction to ~1e-13.
-// `pre8` = (x,dx,y,dy,z,dz,psi,dpsi) before the step.
+// with a1 - a0 = sum_j inc_j (2 pre_j + inc_j), where inc_j = dt*ds_j is the Euler increment
+// BEFORE it is rounded into the stored state.  In fp32 this keeps the reward error
+// proportional to |reward| (1e-5 measured) instead of |shaping| * 2^-24 (literal subtraction,
+// up to 1e-3) or ulp(state)/increment (differences of stored states, 3e-4 at |v| ~ 270 m/s);
+// in fp64 it agrees with the reference's literal subtraction to ~1e-13.
+// `pre8` = (x,dx,y,dy,z,dz,psi,dpsi) before the step, `inc` from dynamics_update.
 template <typename T>
 __device__ __forceinline__ T shaping_delta(const KParams<T>& kp, const T (&pre8)[8], const Shaping<T>& pre,
-                                           const T (&s)[12], const Shaping<T>& post) {
+                                           const T (&inc)[8], const Shaping<T>& post) {
     T na = (T)0;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) na += (s[j] - pre8[j]) * (s[j] + pre8[j]);
-    const T nc = (s[10] - pre8[6]) * (s[10] + pre8[6]) + (s[11] - pre8[7]) * (s[11] + pre8[7]);
+    for (int j = 0; j < 6; ++j) na += inc[j] * ((T)2 * pre8[j] + inc[j]);
+    const T nc = inc[6] * ((T)2 * pre8[6] + inc[6]) + inc[7] * ((T)2 * pre8[7] + inc[7]);
     const T da = post.ra + pre.ra, dc = post.rc + pre.rc;
-    const T ga = da > (T)0 ? na / da : (T)0;
-    const T gc = dc > (T)0 ? nc / dc : (T)0;
+    const T ga = da > (T)0 ? reward_div(na, da) : (T)0;
+    const T gc = dc > (T)0 ? reward_div(nc, dc) : (T)0;
     return -(kp.xyz_pf * ga + kp.yaw_pf * gc) - (post.pen - pre.pen);
 }
 
@@ -275,19 +311,18 @@ __device__ __forceinline__ T shaping_delta(const KParams<T>& kp, const T (&pre8)
 // `pre_sh` holds shaping(post).
 template <typename T, int VARIANT>
 __device__ __forceinline__ void env_substep(const KParams<T>& kp, T (&s)[12], int& st, int& steps,
-                                            const T (&m)[4], const T (&pert)[3], Shaping<T>& pre_sh,
+                                            const Forces<T>& f, const T (&pert)[3], Shaping<T>& pre_sh,
                                             T& reward, bool& done, int& cause) {
     const int st0 = st;                                            // :81 stale status
     const T pre8[8] = {s[0], s[1], s[2], s[3], s[4], s[5], s[10], s[11]};
-    if (st0 != ST_LANDED) {                                        // :86-94
-        const Forces<T> f = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
-        dynamics_update<T, 3, false>(kp, s, st, f, pert);
-    }
+    T inc[8] = {(T)0, (T)0, (T)0, (T)0, (T)0, (T)0, (T)0, (T)0};
+    if (st0 != ST_LANDED)                                          // :86-94
+        dynamics_update<T, 3, false>(kp, s, st, f, pert, inc);
     cause = 0;
     done = false;
     if (Variant<VARIANT>::lander) {
         const Shaping<T> sh = lander_shaping<T>(kp, s);            // lander.py:48-56
-        reward = shaping_delta<T>(kp, pre8, pre_sh, s, sh);        // :58-62
+        reward = shaping_delta<T>(kp, pre8, pre_sh, inc, sh);      // :58-62
         pre_sh = sh;
         if (st0 == ST_LANDED) {                                    // :64-72
             done = true; cause |= CAUSE_LANDED;
@@ -360,9 +395,11 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* tile = tiles[warp];
 
-    // per-thread statistics, reduced once at the end of the grid-stride loop
-    int n_ep = 0, n_landed = 0, n_bonus = 0, n_crashed = 0, n_oob = 0, n_angle = 0, n_timeout = 0, n_steps = 0;
-    double sum_ret = 0.0; int sum_len = 0;
+    // Statistics: only the executed-step count lives in a register across tiles; episode events
+    // are folded into the CTA's shared counters at the end of the tile in which they happen
+    // (ballot/popc per cause, REDUX for the length sum), and each CTA issues one global atomic
+    // per statistic when it retires.
+    int n_steps = 0;
 
     if (STATS) {
         if (threadIdx.x < 10) block_stats[threadIdx.x] = 0.0;
@@ -380,7 +417,7 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
         T m[4] = {(T)0, (T)0, (T)0, (T)0};
         int st = ST_LANDED, steps = 1; uint32_t episode = 0;
         T total = (T)0; bool done_any = false;
-        T ret = (T)0;
+        T ret = (T)0, ep_ret = (T)0; int ep_cause = 0, ep_len = 0;     // STATS only
 
         if (valid) {
             load_state<T>(a.state, a.stride, i, s);
@@ -416,6 +453,8 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
         }
 
         Shaping<T> pre_sh = lander_shaping<T>(kp, s);
+        // the action is fixed for the K substeps of a launch, so Eq. 6 (the fp64 stage) runs once
+        const Forces<T> forces = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
 
         for (int k = 0; k < a.k; ++k) {
             const bool live = valid && !done_any;
@@ -431,17 +470,12 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
                     for (int j = 0; j < 3; ++j) pert[j] = f[j] * kp.invM;      // dynamics/__init__.py:229
                 }
                 T r; bool dn; int cause;
-                env_substep<T, VARIANT>(kp, s, st, steps, m, pert, pre_sh, r, dn, cause);
+                env_substep<T, VARIANT>(kp, s, st, steps, forces, pert, pre_sh, r, dn, cause);
                 total += r;
                 if (STATS) { ++n_steps; ret += r; }
                 if (dn) {
                     done_any = true;
-                    if (STATS) {
-                        ++n_ep; sum_ret += (double)ret; sum_len += steps - 1; ret = (T)0;   // `steps` is 1 right after reset (task.py:191,197)
-                        n_landed += (cause & CAUSE_LANDED) != 0; n_bonus += (cause & CAUSE_BONUS) != 0;
-                        n_crashed += (cause & CAUSE_CRASHED) != 0; n_oob += (cause & CAUSE_OOB) != 0;
-                        n_angle += (cause & CAUSE_ANGLE) != 0; n_timeout += (cause & CAUSE_TIMEOUT) != 0;
-                    }
+                    if (STATS) { ep_cause = cause; ep_len = steps - 1; ep_ret = ret; ret = (T)0; }   // `steps` is 1 right after reset (task.py:191,197)
                     if (a.final_obs) {   // terminal observation; rows of unfinished envs stay untouched
 #pragma unroll
                         for (int j = 0; j < O; ++j) a.final_obs[i * O + j] = (float)s[Variant<VARIANT>::first + j];
@@ -463,23 +497,35 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
             if (STATS && a.ep_return) a.ep_return[i] = ret;
         }
         if (a.obs) write_obs_rows<VARIANT, T>(a.obs, tile, lane, row0, rows, s);
+        if (STATS) {
+            const unsigned full = 0xffffffffu;
+            const unsigned ended = __ballot_sync(full, done_any);
+            if (ended) {
+                const int len_sum = __reduce_add_sync(full, done_any ? ep_len : 0);
+                double ret_sum = done_any ? (double)ep_ret : 0.0;
+                if (a.ep_return) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) ret_sum += __shfl_xor_sync(full, ret_sum, o);
+                }
+                unsigned by_cause[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) by_cause[c] = __ballot_sync(full, done_any && ((ep_cause >> c) & 1));
+                if (lane == 0) {
+                    atomicAdd(&block_stats[COPTER_STAT_EPISODES], (double)__popc(ended));
+                    atomicAdd(&block_stats[COPTER_STAT_LENGTH_SUM], (double)len_sum);
+                    if (a.ep_return) atomicAdd(&block_stats[COPTER_STAT_RETURN_SUM], ret_sum);
+                    // cause bits: LANDED, BONUS, OOB, ANGLE, CRASHED, TIMEOUT
+                    const int slot[6] = {COPTER_STAT_LANDED, COPTER_STAT_BONUS, COPTER_STAT_OOB, COPTER_STAT_ANGLE, COPTER_STAT_CRASHED, COPTER_STAT_TIMEOUT};
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) if (by_cause[c]) atomicAdd(&block_stats[slot[c]], (double)__popc(by_cause[c]));
+                }
+            }
+        }
     }
 
     if (STATS) {
-        // warp reduce (REDUX for the integer counters), then one shared atomic per warp and
-        // one global atomic per block and statistic
-        const unsigned full = 0xffffffffu;
-        int c[9] = {n_ep, sum_len, n_landed, n_bonus, n_crashed, n_oob, n_angle, n_timeout, n_steps};
-#pragma unroll
-        for (int j = 0; j < 9; ++j) c[j] = __reduce_add_sync(full, c[j]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum_ret += __shfl_xor_sync(full, sum_ret, o);
-        if (lane == 0) {
-            atomicAdd(&block_stats[0], (double)c[0]);
-            atomicAdd(&block_stats[1], sum_ret);
-#pragma unroll
-            for (int j = 1; j < 9; ++j) atomicAdd(&block_stats[j + 1], (double)c[j]);
-        }
+        n_steps = __reduce_add_sync(0xffffffffu, n_steps);
+        if (lane == 0 && n_steps) atomicAdd(&block_stats[COPTER_STAT_ENV_STEPS], (double)n_steps);
         __syncthreads();
         if (threadIdx.x < 10 && block_stats[threadIdx.x] != 0.0) atomicAdd(&a.stats[threadIdx.x], block_stats[threadIdx.x]);
     }
@@ -520,7 +566,8 @@ copter_dynamics_kernel(const __grid_constant__ KParams<T> kp, T* state, uint8_t*
 #pragma unroll
         for (int j = 0; j < 4; ++j) m[j] = motors[4 * i + j];
         const Forces<T> f = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
-        const bool finished = dynamics_update<T, 6, true>(kp, s, st, f, p);
+        T inc[8];
+        const bool finished = dynamics_update<T, 6, true>(kp, s, st, f, p, inc);
         store_state<T>(state, n, i, s);
         status[i] = (uint8_t)st;
         if (finished) {                                            // :194-197

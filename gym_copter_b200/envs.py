@@ -341,8 +341,8 @@ class CopterVecEnv:
             raise CopterError('construct the env with track_stats=True')
         v = self._stats.clone()
         if reduce_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(v, op=dist.ReduceOp.SUM, group=None if reduce_group is True else reduce_group)
+            from .sharding import all_reduce_stats
+            all_reduce_stats(v, None if reduce_group is True else reduce_group)
         v = v.cpu().numpy()
         out = {k: float(v[j]) for j, k in enumerate(STAT_NAMES)}
         ep = max(out['episodes'], 1.0)

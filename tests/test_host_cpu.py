@@ -1,0 +1,159 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/copter_b200.h
+declares (no compute without a GPU), the host shell's non-GPU logic, and the N > 1 sharding
+logic over a world_size-2 gloo group."""
+import ctypes as C
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from gym_copter_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, 'include', 'copter_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    names = set(re.findall(r'\b(copter_[a-z0-9_]+)\s*\(', hdr))
+    assert len(names) >= 16
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+    assert lib.copter_abi_version() == 1
+
+
+def test_params_struct_matches_header_and_reference_constants(lib):
+    from gym_copter_b200 import default_params, CopterParams
+    p = default_params()
+    # /root/reference gym_copter/dynamics/vehicles/dji_phantom.py:9-26, dynamics/__init__.py:71-76,
+    # envs/task.py:25,32-38, envs/lander.py:17-23
+    assert (p.B, p.D, p.M, p.L, p.Ix, p.Iy, p.Iz, p.Jr, p.maxrpm) == (5e-3, 2e-6, 1.38, 0.35, 2, 2, 3, 38e-4, 15000)
+    assert (p.landing_vel_x, p.landing_vel_y, p.landing_angle, p.G) == (2.0, 1.0, np.pi / 4, 9.80665)
+    assert (p.fps, p.initial_random_force, p.out_of_bounds_penalty, p.max_angle_deg, p.bounds,
+            p.initial_altitude, p.max_steps) == (100, 30, 100, 45, 10, 10, 1000)
+    assert (p.target_radius, p.yaw_penalty_factor, p.xyz_penalty_factor, p.dz_max, p.dz_penalty,
+            p.inside_radius_bonus) == (2, 50, 25, 10, 100, 100)
+    assert C.sizeof(CopterParams) == 25 * 8 + 8
+    assert [lib.copter_obs_size(v) for v in range(6)] == [10, 6, 2, 12, 6, 2]
+    assert [lib.copter_action_size(v) for v in range(6)] == [4, 2, 1, 4, 2, 1]
+    assert lib.copter_obs_size(6) == -2 and lib.copter_action_size(-1) == -2
+    with pytest.raises(TypeError):
+        default_params(not_a_field=1)
+
+
+def test_argument_validation_without_a_gpu(lib):
+    from gym_copter_b200 import default_params
+    from gym_copter_b200._lib import CopterBuffers
+    p, b = default_params(), CopterBuffers()
+    assert lib.copter_step_f32(C.byref(p), C.byref(b), 16, 0, 0, 1, 0, 1, None) == -1      # null buffers
+    assert lib.copter_reset_f64(C.byref(p), C.byref(b), 16, 0, None) == -1
+    assert lib.copter_step_f32(None, C.byref(b), 16, 0, 0, 1, 0, 1, None) == -1
+    bad = default_params(max_steps=4000)
+    assert lib.copter_reset_f32(C.byref(bad), C.byref(b), 16, 0, None) == -4
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_product_fails_loudly_without_gpu():
+    import gym_copter_b200 as g
+    with pytest.raises(g.CopterError):
+        g.LanderVec(8)
+    with pytest.raises(g.CopterError):
+        g.Dynamics()
+    with pytest.raises(g.CopterError):
+        g.make('gym_copter:Lander-v0')
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'gym_copter_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
+                assert 'copter_oracle' not in src, f
+
+
+def test_spaces_and_ids():
+    from gym_copter_b200.envs import Box, make
+    b = Box(-1, 1, (4,))
+    assert b.contains(b.sample()) and not b.contains(np.full(4, 2.0, np.float32))
+    with pytest.raises(ValueError):
+        make('NoSuchEnv-v0')
+
+
+def test_shard_range_partitions():
+    from gym_copter_b200 import shard_range
+    for n in (0, 1, 7, 255, 256, 1000, 1 << 20, (1 << 24) + 3):
+        for world in (1, 2, 3, 4, 8):
+            r = [shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            if n >= 256 * world:
+                assert all(lo % 256 == 0 for lo, _ in r)
+                sizes = [hi - lo for lo, hi in r]
+                assert max(sizes) - min(sizes) <= 256
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from gym_copter_b200.sharding import shard_range, all_reduce_stats
+    from oracle.copter_oracle import EnvBatch
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    n_global, steps = 1537, 60
+    lo, hi = shard_range(n_global, rank, world)
+    # every rank draws the same global action stream and steps only its shard of the oracle
+    rng = np.random.default_rng(0)
+    env = EnvBatch('Lander3D', hi - lo, seed=11, env_offset=lo)
+    env.reset()
+    stats = torch.zeros(4, dtype=torch.float64)
+    for t in range(steps):
+        a = rng.uniform(-1, 1, (n_global, 4))
+        obs, r, done, info = env.step(a[lo:hi])
+        stats += torch.tensor([done.sum(), r.sum(), info['steps_taken'].sum(), 1.0 if rank == 0 else 0.0], dtype=torch.float64)
+    all_reduce_stats(stats)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (lo, hi, env.dyn.x.copy(), env.episode.copy()))
+    if rank == 0:
+        q.put((stats.tolist(), gathered))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_over_gloo():
+    """world_size 2 on CPU: shards step independently (zero per-step communication), the
+    union equals the unsharded batch bit for bit, and the stats all-reduce sums the ranks."""
+    import torch.multiprocessing as mp
+    from oracle.copter_oracle import EnvBatch
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    stats, gathered = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n_global, steps = 1537, 60
+    rng = np.random.default_rng(0)
+    whole = EnvBatch('Lander3D', n_global, seed=11)
+    whole.reset()
+    tot = np.zeros(3)
+    for t in range(steps):
+        obs, r, done, info = whole.step(rng.uniform(-1, 1, (n_global, 4)))
+        tot += [done.sum(), r.sum(), info['steps_taken'].sum()]
+    assert stats[0] == tot[0] and stats[2] == tot[2] and abs(stats[1] - tot[1]) <= 1e-6 * abs(tot[1])
+    assert stats[3] == steps          # only rank 0 contributed to this slot
+    for lo, hi, x, ep in gathered:
+        assert np.array_equal(x, whole.dyn.x[lo:hi]) and np.array_equal(ep, whole.episode[lo:hi])
+    assert sorted((lo, hi) for lo, hi, _, _ in gathered) == [(0, 768), (768, 1537)]

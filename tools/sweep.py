@@ -18,12 +18,10 @@ VDIR = os.path.join(ROOT, 'tools', 'variants')
 SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
 
 VARIANTS = {}
-for ctas, block, cs in itertools.product((3, 4, 5, 6), (128, 256, 512), (0, 1)):
-    if (ctas, block) in ((3, 128), (6, 512), (5, 512)):
-        continue
-    per_sm = ctas * 256 // block          # keep threads/SM = ctas*256
-    VARIANTS['t%d_b%d_cs%d' % (ctas * 256, block, cs)] = ['-DCOPTER_F32_CTAS_PER_SM=%d' % per_sm,
-                                                          '-DCOPTER_BLOCK=%d' % block, '-DCOPTER_STREAMING=%d' % cs]
+for ctas, block, libm in itertools.product((3, 4), (256, 512), (0, 1)):
+    per_sm = max(1, ctas * 256 // block)          # keep threads/SM ~ ctas*256
+    VARIANTS['t%d_b%d_libm%d' % (per_sm * block, block, libm)] = [
+        '-DCOPTER_F32_CTAS_PER_SM=%d' % per_sm, '-DCOPTER_BLOCK=%d' % block, '-DCOPTER_LIBM_ONLY=%d' % libm]
 
 
 def build():
