@@ -249,6 +249,33 @@ def main():
                 'kernel': 'copter_step_kernel<%s,%s,stats>' % (args.dtype, args.variant),
                 'bytes_per_env_per_launch': b_launch, 'env_steps_per_launch': n * k}
 
+    # ---- this box's own copy bandwidth, measured like MEASURED_PEAKS.json's hbm_gbs --------
+    if not args.no_extras:
+        try:
+            ca = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
+            cb = torch.empty_like(ca)
+            ca.fill_(1.0)
+            for _ in range(3):
+                cb.copy_(ca)
+            best = 1e9
+            for _ in range(10):
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize(); c0.record(); cb.copy_(ca); c1.record(); torch.cuda.synchronize()
+                best = min(best, c0.elapsed_time(c1))
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = max(50, int(ms / 0.7))          # about as long as the timed region above
+            c0.record()
+            for _ in range(reps):
+                cb.copy_(ca)
+            c1.record(); torch.cuda.synchronize()
+            gb = 4 * ca.numel() / 1e9
+            roofline['copy_here'] = {'burst_gbs': gb / best * 1e3, 'sustained_gbs': gb * reps / c0.elapsed_time(c1) * 1e3,
+                                     'how': 'torch b.copy_(a), 1 Gi bf16, read+write bytes; best of 10 / %d back to back' % reps}
+            roofline['frac_of_copy_here_sustained'] = achieved / roofline['copy_here']['sustained_gbs']
+            del ca, cb
+        except Exception as e:
+            roofline['copy_here'] = {'unavailable': repr(e)[:200]}
+
     # ---- fused-substep side measurements (same shard, same stream) -----------------------
     extras = {}
     if not args.no_extras and k == 1:

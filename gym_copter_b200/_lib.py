@@ -35,6 +35,13 @@ class CopterBuffers(C.Structure):
                 ('final_obs', C.c_void_p), ('state_stride', C.c_int64)]
 
 
+class CopterActionSource(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('reserved', C.c_int32), ('scale', C.c_double), ('offset', C.c_double)]
+
+
+SOURCE_KINDS = {'const': 0, 'randn': 1, 'uniform': 2}
+
+
 class CopterError(RuntimeError):
     pass
 
@@ -69,6 +76,8 @@ def load():
         f.argtypes, f.restype = [P, vp, vp, vp, vp, vp, i64, vp], i32
     for f in (lib.copter_reset_force_f32, lib.copter_reset_force_f64):
         f.argtypes, f.restype = [P, vp, vp, i64, i64, u64, vp], i32
+    for f in (lib.copter_rollout_f32, lib.copter_rollout_f64):
+        f.argtypes, f.restype = [P, B, C.POINTER(CopterActionSource), i64, i64, u64, i64, i32, i32, i32, vp, vp, vp, vp], i32
     lib.copter_pipeline_create.argtypes, lib.copter_pipeline_create.restype = [i32, C.POINTER(vp)], i32
     lib.copter_pipeline_destroy.argtypes, lib.copter_pipeline_destroy.restype = [vp], i32
     for f in (lib.copter_step_host_f32, lib.copter_step_host_f64):

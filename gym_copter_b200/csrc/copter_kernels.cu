@@ -375,6 +375,35 @@ __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, float* t
     __syncwarp();
 }
 
+// Folds the episodes that ended in this warp (flag `ended` per lane) into the CTA's shared
+// statistics: ballot/popc per cause bit, REDUX for the length sum, shuffle tree for the fp64
+// return sum; lane 0 then issues the shared-memory atomics.  Warp-uniform call.
+template <typename T>
+__device__ __forceinline__ void flush_episode_stats(double* block_stats, int lane, bool ended_lane, int ep_cause,
+                                                    int ep_len, T ep_ret, bool has_returns) {
+    const unsigned full = 0xffffffffu;
+    const unsigned ended = __ballot_sync(full, ended_lane);
+    if (!ended) return;
+    const int len_sum = __reduce_add_sync(full, ended_lane ? ep_len : 0);
+    double ret_sum = ended_lane ? (double)ep_ret : 0.0;
+    if (has_returns) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ret_sum += __shfl_xor_sync(full, ret_sum, o);
+    }
+    unsigned by_cause[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) by_cause[c] = __ballot_sync(full, ended_lane && ((ep_cause >> c) & 1));
+    if (lane == 0) {
+        atomicAdd(&block_stats[COPTER_STAT_EPISODES], (double)__popc(ended));
+        atomicAdd(&block_stats[COPTER_STAT_LENGTH_SUM], (double)len_sum);
+        if (has_returns) atomicAdd(&block_stats[COPTER_STAT_RETURN_SUM], ret_sum);
+        // cause bits: LANDED, BONUS, OOB, ANGLE, CRASHED, TIMEOUT
+        const int slot[6] = {COPTER_STAT_LANDED, COPTER_STAT_BONUS, COPTER_STAT_OOB, COPTER_STAT_ANGLE, COPTER_STAT_CRASHED, COPTER_STAT_TIMEOUT};
+#pragma unroll
+        for (int c = 0; c < 6; ++c) if (by_cause[c]) atomicAdd(&block_stats[slot[c]], (double)__popc(by_cause[c]));
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
@@ -497,32 +526,143 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
             if (STATS && a.ep_return) a.ep_return[i] = ret;
         }
         if (a.obs) write_obs_rows<VARIANT, T>(a.obs, tile, lane, row0, rows, s);
-        if (STATS) {
-            const unsigned full = 0xffffffffu;
-            const unsigned ended = __ballot_sync(full, done_any);
-            if (ended) {
-                const int len_sum = __reduce_add_sync(full, done_any ? ep_len : 0);
-                double ret_sum = done_any ? (double)ep_ret : 0.0;
-                if (a.ep_return) {
+        if (STATS) flush_episode_stats<T>(block_stats, lane, done_any, ep_cause, ep_len, ep_ret, a.ep_return != nullptr);
+    }
+
+    if (STATS) {
+        n_steps = __reduce_add_sync(0xffffffffu, n_steps);
+        if (lane == 0 && n_steps) atomicAdd(&block_stats[COPTER_STAT_ENV_STEPS], (double)n_steps);
+        __syncthreads();
+        if (threadIdx.x < 10 && block_stats[threadIdx.x] != 0.0) atomicAdd(&a.stats[threadIdx.x], block_stats[threadIdx.x]);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Multi-step rollout with on-device action sources: n_steps reference steps per launch, the
+// env state in registers throughout, the motor commands drawn on the device (no action tensor
+// in HBM).  Equivalent, step for step, to n_steps launches of copter_step_kernel with k = 1
+// fed the same commands (a finished env resets and keeps going -- no idling here).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct RolloutArgs {
+    T* state; uint32_t* meta; float* obs; T* reward_sum; uint8_t* done_any;
+    const T* init_force; T* ep_return; double* stats;
+    T* reward_tn; uint8_t* done_tn; T* action_tn;
+    int64_t n, stride, env_offset, first_step; uint64_t seed;
+    int n_steps, auto_reset, src_kind; T src_scale, src_offset;
+};
+
+__device__ __forceinline__ float  log_t(float a)  { return logf(a); }
+__device__ __forceinline__ double log_t(double a) { return log(a); }
+
+// Command vector of (env, step): offset + scale * xi, xi_j = 1 | N(0,1) | U(-1,1), from
+// Philox4x32-10 with counter (env_lo, env_hi, step, 1) -- stream tag 1, the reset forces use 0.
+template <typename T, int A>
+__device__ __forceinline__ void draw_action(const RolloutArgs<T>& a, uint64_t env, uint64_t step, T (&act)[A]) {
+    T xi[4] = {(T)1, (T)1, (T)1, (T)1};
+    if (a.src_kind != COPTER_SRC_CONST) {
+        uint32_t c[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)step, 1u};
+        philox4x32_10(c, (uint32_t)a.seed ^ (uint32_t)(step >> 32), (uint32_t)(a.seed >> 32));
+        if (a.src_kind == COPTER_SRC_UNIFORM) {
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) ret_sum += __shfl_xor_sync(full, ret_sum, o);
-                }
-                unsigned by_cause[6];
+            for (int j = 0; j < 4; ++j) xi[j] = (T)fma((double)c[j], 0x1p-31, -1.0);     // exact, one rounding
+        } else {                                                                         // Box-Muller, two pairs
 #pragma unroll
-                for (int c = 0; c < 6; ++c) by_cause[c] = __ballot_sync(full, done_any && ((ep_cause >> c) & 1));
-                if (lane == 0) {
-                    atomicAdd(&block_stats[COPTER_STAT_EPISODES], (double)__popc(ended));
-                    atomicAdd(&block_stats[COPTER_STAT_LENGTH_SUM], (double)len_sum);
-                    if (a.ep_return) atomicAdd(&block_stats[COPTER_STAT_RETURN_SUM], ret_sum);
-                    // cause bits: LANDED, BONUS, OOB, ANGLE, CRASHED, TIMEOUT
-                    const int slot[6] = {COPTER_STAT_LANDED, COPTER_STAT_BONUS, COPTER_STAT_OOB, COPTER_STAT_ANGLE, COPTER_STAT_CRASHED, COPTER_STAT_TIMEOUT};
-#pragma unroll
-                    for (int c = 0; c < 6; ++c) if (by_cause[c]) atomicAdd(&block_stats[slot[c]], (double)__popc(by_cause[c]));
-                }
+            for (int h = 0; h < 2; ++h) {
+                const T u1 = (T)(((double)c[2 * h] + 1.0) * 0x1p-32);                   // (0, 1]
+                const T u2 = (T)((double)c[2 * h + 1] * 0x1p-32);
+                const T r = sqrt_t((T)-2 * log_t(u1));
+                T sn, cs;
+                sincos_t((T)6.283185307179586 * u2, &sn, &cs);
+                xi[2 * h] = r * cs; xi[2 * h + 1] = r * sn;
             }
         }
     }
+#pragma unroll
+    for (int j = 0; j < A; ++j) act[j] = a.src_offset + a.src_scale * xi[j];
+}
 
+template <typename T, int VARIANT, bool STATS>
+__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? COPTER_F32_CTAS_PER_SM : 2)
+copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant__ RolloutArgs<T> a) {
+    constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A;
+    __shared__ __align__(16) float tiles[kWarpsPerBlock][32 * O];
+    __shared__ double block_stats[STATS ? 10 : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int n_steps = 0;
+    if (STATS) {
+        if (threadIdx.x < 10) block_stats[threadIdx.x] = 0.0;
+        __syncthreads();
+    }
+    const int64_t n_tiles = (a.n + kBlock - 1) / kBlock;
+    for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+        const int64_t row0 = tile_id * kBlock + warp * 32, i = row0 + lane;
+        const bool valid = i < a.n;
+        const int rows = (int)max((int64_t)0, min((int64_t)32, a.n - row0));
+        T s[12];
+        int st = ST_LANDED, steps = 1; uint32_t episode = 0;
+        T total = (T)0, ret = (T)0; bool done_any = false;
+        if (valid) {
+            load_state<T>(a.state, a.stride, i, s);
+            const uint32_t mw = a.meta[i];
+            st = (int)(mw & 3u); steps = (int)((mw >> 2) & 2047u); episode = mw >> 13;
+            if (STATS && a.ep_return) ret = a.ep_return[i];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) s[j] = (T)0;
+        }
+        Shaping<T> pre_sh = lander_shaping<T>(kp, s);
+        for (int t = 0; t < a.n_steps; ++t) {
+            bool dn = false; int cause = 0, ep_len = 0; T ep_ret = (T)0;
+            if (valid) {
+                T act[A], m[4];
+                draw_action<T, A>(a, (uint64_t)(a.env_offset + i), (uint64_t)(a.first_step + t), act);
+                if (a.action_tn) {
+#pragma unroll
+                    for (int j = 0; j < A; ++j) a.action_tn[((int64_t)t * a.n + i) * A + j] = act[j];
+                }
+#pragma unroll
+                for (int j = 0; j < A; ++j) act[j] = fmin(fmax(act[j], (T)0), (T)1);         // task.py:91
+                if constexpr (A == 4) { m[0] = act[0]; m[1] = act[1]; m[2] = act[2]; m[3] = act[3]; }
+                else if constexpr (A == 2) { m[0] = act[0]; m[1] = act[1]; m[2] = act[1]; m[3] = act[0]; }
+                else { m[0] = m[1] = m[2] = m[3] = act[0]; }
+                const Forces<T> forces = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
+                T pert[3] = {(T)0, (T)0, (T)0};
+                if (steps == 1) {
+                    T f[3];
+                    if (a.init_force) { f[0] = a.init_force[3 * i]; f[1] = a.init_force[3 * i + 1]; f[2] = a.init_force[3 * i + 2]; }
+                    else reset_force<T>(kp, a.seed, (uint64_t)(a.env_offset + i), episode, f);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) pert[j] = f[j] * kp.invM;
+                }
+                T r;
+                env_substep<T, VARIANT>(kp, s, st, steps, forces, pert, pre_sh, r, dn, cause);
+                total += r;
+                if (STATS) { ++n_steps; ret += r; }
+                if (a.reward_tn) a.reward_tn[(int64_t)t * a.n + i] = r;
+                if (a.done_tn) a.done_tn[(int64_t)t * a.n + i] = dn ? 1 : 0;
+                if (dn) {
+                    done_any = true;
+                    if (STATS) { ep_len = steps - 1; ep_ret = ret; ret = (T)0; }
+                    if (a.auto_reset) {
+                        reset_state<T>(kp, s, st, steps);
+                        episode = (episode + 1) & 0x7FFFFu;
+                        pre_sh = lander_shaping<T>(kp, s);
+                    }
+                }
+            }
+            if (STATS) flush_episode_stats<T>(block_stats, lane, dn, cause, ep_len, ep_ret, a.ep_return != nullptr);
+        }
+        if (valid) {
+            store_state<T>(a.state, a.stride, i, s);
+            a.meta[i] = (uint32_t)st | ((uint32_t)steps << 2) | (episode << 13);
+            if (a.reward_sum) a.reward_sum[i] = total;
+            if (a.done_any) a.done_any[i] = done_any ? 1 : 0;
+            if (STATS && a.ep_return) a.ep_return[i] = ret;
+        }
+        if (a.obs) write_obs_rows<VARIANT, T>(a.obs, tiles[warp], lane, row0, rows, s);
+    }
     if (STATS) {
         n_steps = __reduce_add_sync(0xffffffffu, n_steps);
         if (lane == 0 && n_steps) atomicAdd(&block_stats[COPTER_STAT_ENV_STEPS], (double)n_steps);
@@ -603,11 +743,16 @@ int sm_count() {
 }
 
 // Persistent-style grid: at most one resident wave (SMs x CTAs/SM of this kernel), each CTA
-// walking the 256-env tiles with a grid stride.
-template <typename K>
-int grid_for(K kernel, int64_t n) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
+// walking the 256-env tiles with a grid stride.  The occupancy query runs once per kernel
+// instantiation (and never inside a CUDA-graph capture after the first, uncaptured call).
+template <auto Kernel>
+int grid_for(int64_t n) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int q = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, Kernel, kBlock, 0) != cudaSuccess || q <= 0) q = 4;
+        per_sm = q;
+    }
     const int64_t tiles = (n + kBlock - 1) / kBlock;
     const int64_t cap = (int64_t)sm_count() * per_sm;
     return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
@@ -624,8 +769,8 @@ int check_params(const CopterParams* p) {
 
 template <typename T, int VARIANT>
 int launch_step_v(const KParams<T>& kp, const StepArgs<T>& a, cudaStream_t s) {
-    if (a.stats) copter_step_kernel<T, VARIANT, true><<<grid_for(copter_step_kernel<T, VARIANT, true>, a.n), kBlock, 0, s>>>(kp, a);
-    else         copter_step_kernel<T, VARIANT, false><<<grid_for(copter_step_kernel<T, VARIANT, false>, a.n), kBlock, 0, s>>>(kp, a);
+    if (a.stats) copter_step_kernel<T, VARIANT, true><<<grid_for<copter_step_kernel<T, VARIANT, true>>(a.n), kBlock, 0, s>>>(kp, a);
+    else         copter_step_kernel<T, VARIANT, false><<<grid_for<copter_step_kernel<T, VARIANT, false>>(a.n), kBlock, 0, s>>>(kp, a);
     return (int)cudaGetLastError();
 }
 
@@ -657,8 +802,46 @@ int launch_step(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_
 }
 
 template <typename T, int VARIANT>
+int launch_rollout_v(const KParams<T>& kp, const RolloutArgs<T>& a, cudaStream_t s) {
+    if (a.stats) copter_rollout_kernel<T, VARIANT, true><<<grid_for<copter_rollout_kernel<T, VARIANT, true>>(a.n), kBlock, 0, s>>>(kp, a);
+    else         copter_rollout_kernel<T, VARIANT, false><<<grid_for<copter_rollout_kernel<T, VARIANT, false>>(a.n), kBlock, 0, s>>>(kp, a);
+    return (int)cudaGetLastError();
+}
+
+template <typename T>
+int launch_rollout(const CopterParams* p, const CopterBuffers* b, const CopterActionSource* src, int64_t n,
+                   int64_t env_offset, uint64_t seed, int64_t first_step, int n_steps, int variant, int flags,
+                   void* reward_tn, uint8_t* done_tn, void* action_tn, void* stream) {
+    int e = check_params(p);
+    if (e) return e;
+    if (!b || !b->state || !b->meta || !src) return COPTER_E_ARG;
+    if (n < 0 || env_offset < 0 || n_steps < 1 || first_step < 0 || (b->state_stride > 0 && b->state_stride < n)) return COPTER_E_RANGE;
+    if (src->kind < COPTER_SRC_CONST || src->kind > COPTER_SRC_UNIFORM) return COPTER_E_RANGE;
+    if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
+    if (!aligned16(b->state) || (b->obs && !aligned16(b->obs))) return COPTER_E_ALIGN;
+    if (n == 0) return 0;
+    const KParams<T> kp = make_kparams<T>(*p);
+    RolloutArgs<T> a;
+    a.state = (T*)b->state; a.meta = b->meta; a.obs = b->obs; a.reward_sum = (T*)b->reward; a.done_any = b->done;
+    a.init_force = (const T*)b->init_force; a.ep_return = (T*)b->ep_return; a.stats = b->stats;
+    a.reward_tn = (T*)reward_tn; a.done_tn = done_tn; a.action_tn = (T*)action_tn;
+    a.n = n; a.stride = b->state_stride > 0 ? b->state_stride : n; a.env_offset = env_offset; a.first_step = first_step;
+    a.seed = seed; a.n_steps = n_steps; a.auto_reset = (flags & COPTER_F_AUTO_RESET) ? 1 : 0;
+    a.src_kind = src->kind; a.src_scale = (T)src->scale; a.src_offset = (T)src->offset;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (variant) {
+        case COPTER_LANDER3D: return launch_rollout_v<T, COPTER_LANDER3D>(kp, a, s);
+        case COPTER_LANDER2D: return launch_rollout_v<T, COPTER_LANDER2D>(kp, a, s);
+        case COPTER_LANDER1D: return launch_rollout_v<T, COPTER_LANDER1D>(kp, a, s);
+        case COPTER_HOVER3D:  return launch_rollout_v<T, COPTER_HOVER3D>(kp, a, s);
+        case COPTER_HOVER2D:  return launch_rollout_v<T, COPTER_HOVER2D>(kp, a, s);
+        default:              return launch_rollout_v<T, COPTER_HOVER1D>(kp, a, s);
+    }
+}
+
+template <typename T, int VARIANT>
 int launch_reset_v(const KParams<T>& kp, const CopterBuffers* b, int64_t n, cudaStream_t s) {
-    copter_reset_kernel<T, VARIANT><<<grid_for(copter_reset_kernel<T, VARIANT>, n), kBlock, 0, s>>>(kp, (T*)b->state, b->meta, b->obs, (T*)b->ep_return, n, b->state_stride > 0 ? b->state_stride : n);
+    copter_reset_kernel<T, VARIANT><<<grid_for<copter_reset_kernel<T, VARIANT>>(n), kBlock, 0, s>>>(kp, (T*)b->state, b->meta, b->obs, (T*)b->ep_return, n, b->state_stride > 0 ? b->state_stride : n);
     return (int)cudaGetLastError();
 }
 
@@ -693,7 +876,7 @@ int launch_dynamics(const CopterParams* p, void* state, uint8_t* status, int32_t
     if (!aligned16(state)) return COPTER_E_ALIGN;
     if (n == 0) return 0;
     const KParams<T> kp = make_kparams<T>(*p);
-    copter_dynamics_kernel<T><<<grid_for(copter_dynamics_kernel<T>, n), kBlock, 0, (cudaStream_t)stream>>>(kp, (T*)state, status, ticks, (T*)perturb, (const T*)motors, n);
+    copter_dynamics_kernel<T><<<grid_for<copter_dynamics_kernel<T>>(n), kBlock, 0, (cudaStream_t)stream>>>(kp, (T*)state, status, ticks, (T*)perturb, (const T*)motors, n);
     return (int)cudaGetLastError();
 }
 
@@ -706,7 +889,7 @@ int launch_reset_force(const CopterParams* p, T* out, const uint32_t* episode, i
     if (n < 0 || env_offset < 0) return COPTER_E_RANGE;
     if (n == 0) return 0;
     const KParams<T> kp = make_kparams<T>(*p);
-    copter_reset_force_kernel<T><<<grid_for(copter_reset_force_kernel<T>, n), kBlock, 0, (cudaStream_t)stream>>>(kp, out, episode, n, env_offset, seed);
+    copter_reset_force_kernel<T><<<grid_for<copter_reset_force_kernel<T>>(n), kBlock, 0, (cudaStream_t)stream>>>(kp, out, episode, n, env_offset, seed);
     return (int)cudaGetLastError();
 }
 
@@ -804,6 +987,15 @@ int copter_step_f32(const CopterParams* p, const CopterBuffers* b, int64_t n, in
 }
 int copter_step_f64(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_t env_offset, uint64_t seed, int k, int variant, int flags, void* stream) {
     return launch_step<double>(p, b, n, env_offset, seed, k, variant, flags, stream);
+}
+
+int copter_rollout_f32(const CopterParams* p, const CopterBuffers* b, const CopterActionSource* src, int64_t n, int64_t env_offset, uint64_t seed,
+                       int64_t first_step, int n_steps, int variant, int flags, float* reward_tn, uint8_t* done_tn, float* action_tn, void* stream) {
+    return launch_rollout<float>(p, b, src, n, env_offset, seed, first_step, n_steps, variant, flags, reward_tn, done_tn, action_tn, stream);
+}
+int copter_rollout_f64(const CopterParams* p, const CopterBuffers* b, const CopterActionSource* src, int64_t n, int64_t env_offset, uint64_t seed,
+                       int64_t first_step, int n_steps, int variant, int flags, double* reward_tn, uint8_t* done_tn, double* action_tn, void* stream) {
+    return launch_rollout<double>(p, b, src, n, env_offset, seed, first_step, n_steps, variant, flags, reward_tn, done_tn, action_tn, stream);
 }
 
 int copter_dynamics_f32(const CopterParams* p, void* state, uint8_t* status, int32_t* ticks, void* perturb, const void* motors, int64_t n, void* stream) {

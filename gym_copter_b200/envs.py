@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import CopterBuffers, CopterError, VARIANT_IDS, STAT_NAMES
+from ._lib import CopterActionSource, CopterBuffers, CopterError, SOURCE_KINDS, VARIANT_IDS, STAT_NAMES
 
 _OBS_IDX = {'Lander3D': tuple(range(10)), 'Lander2D': (2, 3, 4, 5, 6, 7), 'Lander1D': (4, 5),
             'Hover3D': tuple(range(12)), 'Hover2D': (2, 3, 4, 5, 6, 7), 'Hover1D': (4, 5)}
@@ -129,14 +129,17 @@ class CopterVecEnv:
         self._is_reset = False
         self._pipeline = None
         self._host = None
+        self.rollout_step = 0       # global step index of the on-device action streams
 
     # ---- plumbing -----------------------------------------------------------------------
 
-    def _buffers(self, action=None, force=None):
+    def _buffers(self, action=None, force=None, reward=None, done=None):
         b = CopterBuffers()
         b.state, b.meta = self.state_planes.data_ptr(), self.meta.data_ptr()
         b.action = action.data_ptr() if action is not None else None
-        b.obs, b.reward, b.done = self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr()
+        b.obs = self.obs.data_ptr()
+        b.reward = (self.reward if reward is None else reward).data_ptr()
+        b.done = (self.done if done is None else done).data_ptr()
         b.init_force = force.data_ptr() if force is not None else None
         b.ep_return = self.ep_return.data_ptr() if self.ep_return is not None else None
         b.stats = self._stats.data_ptr() if self._stats is not None else None
@@ -186,19 +189,25 @@ class CopterVecEnv:
         self._is_reset = True
         return self.obs, {}
 
-    def step(self, action):
+    def step(self, action, reward_out=None, done_out=None):
         """
         One batched `_Task.step` (envs/task.py:77-137), k_substeps times under one action.
         Returns (obs f32 [N,O], reward [N], terminated bool [N], truncated bool [N], info).
         The returned tensors are the env's own output buffers: they are overwritten by the
-        next step (clone them to keep them).
+        next step (clone them to keep them) -- or pass `reward_out` ([N], env dtype) and
+        `done_out` ([N] uint8) to have the kernel write this step's reward / done flags
+        straight into a slice of a rollout buffer.
         """
         if not self._is_reset:
             raise CopterError('step() called before reset()')    # gymnasium's OrderEnforcing
         t = self._as_action(action)
+        for o, dt in ((reward_out, self.dtype), (done_out, torch.uint8)):
+            if o is not None and (o.dtype != dt or o.numel() != self.num_envs or not o.is_contiguous()
+                                  or o.device != self.device):
+                raise ValueError('reward_out/done_out must be contiguous [N] tensors of the env dtype / uint8 on the env device')
         with torch.cuda.device(self.device):
             fn = self._lib.copter_step_f32 if self._f32 else self._lib.copter_step_f64
-            b = self._buffers(t, self._force)
+            b = self._buffers(t, self._force, reward_out, done_out)
             _lib.check(fn(C.byref(self.params), C.byref(b), self.num_envs, self.env_offset,
                           self.seed_value & 0xFFFFFFFFFFFFFFFF, self.k_substeps,
                           VARIANT_IDS[self.variant], _lib.F_AUTO_RESET if self.auto_reset else 0,
@@ -207,7 +216,55 @@ class CopterVecEnv:
         info = {}
         if self.final_obs is not None:
             info['final_obs'] = self.final_obs
-        return self.obs, self.reward, self.done.view(torch.bool), self._truncated, info
+        return (self.obs, self.reward if reward_out is None else reward_out,
+                (self.done if done_out is None else done_out).view(torch.bool), self._truncated, info)
+
+    # ---- fused multi-step rollout with on-device action sources -----------------------
+
+    def rollout(self, n_steps, source='const', scale=None, offset=None, record_rewards=False,
+                record_dones=False, record_actions=False):
+        """
+        `n_steps` env steps in ONE kernel launch, the commands generated on the device:
+          source='const'    action = offset                 (default offset 1.625e-2: the
+                                                             reference heuristic, lander.py:21,42)
+          source='randn'    action = offset + scale*N(0,1)  (default scale 1.625e-2, offset 0:
+                                                             `lander.py --random`)
+          source='uniform'  action = offset + scale*U(-1,1) (default scale 1: the action space)
+        Step for step identical to `n_steps` calls of step() with k_substeps=1 on the same
+        commands.  Returns a dict: 'obs' (after the last step), 'reward_sum' [N], 'done_any'
+        [N] bool, plus 'rewards' [T,N], 'dones' [T,N] bool, 'actions' [T,N,A] when recorded.
+        """
+        if not self._is_reset:
+            raise CopterError('rollout() called before reset()')
+        if source not in SOURCE_KINDS:
+            raise ValueError('source must be one of %s' % sorted(SOURCE_KINDS))
+        d_scale, d_off = {'const': (0.0, 1.625e-2), 'randn': (1.625e-2, 0.0), 'uniform': (1.0, 0.0)}[source]
+        src = CopterActionSource(SOURCE_KINDS[source], 0, d_scale if scale is None else float(scale),
+                                 d_off if offset is None else float(offset))
+        n, T = self.num_envs, int(n_steps)
+        out = {}
+        rew = torch.empty((T, n), dtype=self.dtype, device=self.device) if record_rewards else None
+        dn = torch.empty((T, n), dtype=torch.uint8, device=self.device) if record_dones else None
+        act = torch.empty((T, n, self.action_size), dtype=self.dtype, device=self.device) if record_actions else None
+        with torch.cuda.device(self.device):
+            fn = self._lib.copter_rollout_f32 if self._f32 else self._lib.copter_rollout_f64
+            b = self._buffers(None, self._force)
+            _lib.check(fn(C.byref(self.params), C.byref(b), C.byref(src), n, self.env_offset,
+                          self.seed_value & 0xFFFFFFFFFFFFFFFF, self.rollout_step, T,
+                          VARIANT_IDS[self.variant], _lib.F_AUTO_RESET if self.auto_reset else 0,
+                          rew.data_ptr() if rew is not None else None,
+                          dn.data_ptr() if dn is not None else None,
+                          act.data_ptr() if act is not None else None, self._stream()), 'copter_rollout')
+        self.launches += 1
+        self.rollout_step += T
+        out.update(obs=self.obs, reward_sum=self.reward, done_any=self.done.view(torch.bool))
+        if rew is not None:
+            out['rewards'] = rew
+        if dn is not None:
+            out['dones'] = dn.view(torch.bool)
+        if act is not None:
+            out['actions'] = act
+        return out
 
     # ---- host-array API (numpy in / numpy out, as the reference's callers use it) ------
 

@@ -1,0 +1,84 @@
+"""
+Policy-in-the-loop rollouts (BASELINE.json configs[4]).
+
+The per-step loop the reference's consumers run on the host -- obs -> network -> clip ->
+env.step (/root/reference attic/drl/3dtest.py:36-61) -- stays on the device end to end: the
+policy reads the env's observation tensor in place, the step kernel reads the policy's action
+tensor in place and writes reward / done straight into row t of the [T, N] rollout buffers
+(GAE-ready layout), and the whole T-step horizon is captured once in a CUDA graph and replayed,
+so a rollout costs one graph launch instead of T x (policy kernels + 1) launches.
+"""
+
+import torch
+
+from ._lib import CopterError
+
+
+class PolicyRollout:
+    """
+    env      a CopterVecEnv (already constructed on the target device)
+    policy   callable obs[N,O] f32 -> action[N,A] (torch module or function; runs under no_grad)
+    horizon  T env.step() calls per rollout
+    store_obs  also keep obs_t (the observation the policy saw) in a [T, N, O] buffer
+    """
+
+    def __init__(self, env, policy, horizon, store_obs=False, use_cuda_graph=True):
+        self.env, self.policy, self.horizon = env, policy, int(horizon)
+        n, dev = env.num_envs, env.device
+        self.rewards = torch.zeros((self.horizon, n), dtype=env.dtype, device=dev)
+        self.dones = torch.zeros((self.horizon, n), dtype=torch.uint8, device=dev)
+        self.obs = torch.zeros((self.horizon, n, env.obs_size), dtype=torch.float32, device=dev) if store_obs else None
+        self.last_obs = env.obs                       # observation after the last step (bootstrap value input)
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self.launches_per_rollout = self.horizon      # of OUR kernels; the policy's are torch's
+
+    def _body(self):
+        env = self.env
+        for t in range(self.horizon):
+            if self.obs is not None:
+                self.obs[t].copy_(env.obs)
+            action = self.policy(env.obs)
+            if action.dtype != env.dtype:
+                action = action.to(env.dtype)
+            env.step(action, reward_out=self.rewards[t], done_out=self.dones[t])
+
+    @torch.no_grad()
+    def run(self):
+        """One horizon. Returns (rewards [T,N], dones [T,N] bool view, last_obs [N,O])."""
+        if not self.env._is_reset:
+            raise CopterError('reset() the env before rolling out')
+        if not self.use_cuda_graph:
+            self._body()
+        else:
+            if self._graph is None:
+                # warm up on a side stream (allocator + lazy module init), then capture
+                s = torch.cuda.Stream(device=self.env.device)
+                s.wait_stream(torch.cuda.current_stream(self.env.device))
+                with torch.cuda.stream(s):
+                    self._body()
+                torch.cuda.current_stream(self.env.device).wait_stream(s)
+                torch.cuda.synchronize(self.env.device)
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._body()
+            self._graph.replay()
+            self.env.launches += self.horizon
+        return self.rewards, self.dones.view(torch.bool), self.last_obs
+
+
+def mlp_policy(obs_size, action_size, hidden=64, dtype=torch.bfloat16, device='cuda', seed=0):
+    """The small tanh MLP of SURVEY.md 8d config 5 (O -> 64 -> 64 -> A), random init."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    net = torch.nn.Sequential(
+        torch.nn.Linear(obs_size, hidden), torch.nn.Tanh(),
+        torch.nn.Linear(hidden, hidden), torch.nn.Tanh(),
+        torch.nn.Linear(hidden, action_size), torch.nn.Tanh())
+    for p in net.parameters():
+        p.data = (torch.randn(p.shape, generator=g) * (0.5 / max(1, p.shape[-1]) ** 0.5))
+    net = net.to(device=device, dtype=dtype).eval()
+
+    def policy(obs):
+        return net(obs.to(dtype)).float()
+    policy.net = net
+    return policy

@@ -13,6 +13,8 @@
  *   copter_step_{f32,f64}      _Task.step + Lander._get_reward/_get_state/_get_motors
  *                              envs/task.py:77-137, envs/lander.py:39-74,95-97
  *                              (which call Dynamics.setMotors, dynamics/__init__.py:114-197)
+ *   copter_rollout_{f32,f64}   the caller's loop `for t: env.step(heuristic action)` (lander.py:40-64)
+ *                              with the constant / --random command streams generated on the device
  *   copter_dynamics_{f32,f64}  Dynamics.setMotors driven directly (take-off style use)
  *                              dynamics/__init__.py:114-197,210-229
  *   copter_step_host_{f32,f64} the same step for callers holding HOST buffers (numpy actions as in
@@ -125,6 +127,31 @@ int copter_step_f32(const CopterParams* p, const CopterBuffers* b, int64_t n, in
                     uint64_t seed, int k_substeps, int variant, int flags, void* stream);
 int copter_step_f64(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_t env_offset,
                     uint64_t seed, int k_substeps, int variant, int flags, void* stream);
+
+/*
+ * Multi-step rollout with an on-device action source: n_steps reference steps per env in ONE
+ * launch with the state in registers, the motor commands generated on the device instead of
+ * read from HBM.  Step t of the launch uses the command vector
+ *     action_j = offset + scale * xi_j,   xi = 1 (CONST) | N(0,1) (RANDN) | U(-1,1) (UNIFORM),
+ * xi drawn from Philox4x32-10 with counter (env_lo, env_hi, first_step + t, 1), key = seed,
+ * so a rollout is reproducible and independent of how it is cut into launches.  CONST with
+ * offset 1.625e-2 is the reference's heuristic, RANDN with scale 1.625e-2 its `--random`
+ * stream (lander.py:21,42).  Equivalent step for step to n_steps calls of copter_step_* with
+ * k_substeps = 1 on the same commands (finished envs reset and continue; nothing idles).
+ * b->action is unused; b->reward / b->done (nullable here) receive the per-env reward SUM and
+ * "any episode finished" flag of the launch, b->obs the observation after the last step.
+ * Optional per-step outputs: reward_tn T[n_steps][n], done_tn uint8[n_steps][n] (GAE-ready
+ * layout), action_tn T[n_steps][n][A] (the commands used, before clipping).
+ */
+enum { COPTER_SRC_CONST = 0, COPTER_SRC_RANDN = 1, COPTER_SRC_UNIFORM = 2 };
+typedef struct CopterActionSource { int32_t kind; int32_t reserved; double scale; double offset; } CopterActionSource;
+
+int copter_rollout_f32(const CopterParams* p, const CopterBuffers* b, const CopterActionSource* src,
+                       int64_t n, int64_t env_offset, uint64_t seed, int64_t first_step, int n_steps,
+                       int variant, int flags, float* reward_tn, uint8_t* done_tn, float* action_tn, void* stream);
+int copter_rollout_f64(const CopterParams* p, const CopterBuffers* b, const CopterActionSource* src,
+                       int64_t n, int64_t env_offset, uint64_t seed, int64_t first_step, int n_steps,
+                       int variant, int flags, double* reward_tn, uint8_t* done_tn, double* action_tn, void* stream);
 
 /*
  * Batched Dynamics.setMotors: state T[12/V][n][V], status uint8[n], ticks int32[n],

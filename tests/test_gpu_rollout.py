@@ -1,0 +1,152 @@
+"""GPU tests of the rows next to the step: fused multi-step rollouts with
+on-device action sources, policy-in-the-loop rollouts under a CUDA graph, the host-array
+pipeline, and the lander.py-compatible CSV export."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle.copter_oracle import EnvBatch, VARIANTS, source_actions      # noqa: E402
+
+
+def merr(a, ref):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    return float(np.max(np.abs(a - ref) / np.maximum(np.abs(ref), 1.0)))
+
+
+@pytest.fixture(scope='module')
+def pkg():
+    import gym_copter_b200
+    gym_copter_b200.load_library()
+    return gym_copter_b200
+
+
+@pytest.mark.parametrize('dtype,nd', [(torch.float64, np.float64), (torch.float32, np.float32)])
+@pytest.mark.parametrize('source', ['const', 'randn', 'uniform'])
+def test_action_sources_match_their_definition(pkg, source, dtype, nd):
+    n, T, off, seed = 3001, 5, 10 ** 11, 0xFEEDFACE1234
+    env = pkg.CopterVecEnv('Lander3D', n, dtype=dtype, seed=seed, env_offset=off)
+    env.reset()
+    env.rollout_step = 2 ** 33 + 5          # exercises the high word of the step counter
+    out = env.rollout(T, source=source, record_actions=True)
+    acts = out['actions'].cpu().numpy()
+    ids = np.arange(n, dtype=np.uint64) + np.uint64(off)
+    for t in range(T):
+        kw = dict(const=(0.0, 1.625e-2), randn=(1.625e-2, 0.0), uniform=(1.0, 0.0))[source]
+        ref = source_actions(seed, ids, 2 ** 33 + 5 + t, source, kw[0], kw[1], 4, nd)
+        if source == 'randn':
+            assert np.max(np.abs(acts[t] - ref)) <= (1e-13 if nd == np.float64 else 2e-7)
+        else:
+            assert np.array_equal(acts[t], ref)
+    if source == 'randn':
+        z = acts / 1.625e-2
+        assert abs(z.mean()) < 0.02 and abs(z.std() - 1) < 0.02
+        assert abs(np.corrcoef(z.reshape(-1, 4).T)[0, 1]) < 0.02
+
+
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+@pytest.mark.parametrize('variant,source', [('Lander3D', 'randn'), ('Lander3D', 'uniform'), ('Lander2D', 'randn'),
+                                            ('Hover3D', 'const'), ('Lander1D', 'uniform')])
+def test_rollout_equals_single_steps_and_oracle(pkg, variant, source, dtype):
+    """One fused launch of T steps == T launches of step() on the recorded commands, bit for
+    bit (same device arithmetic), and == the oracle within the path's tolerance."""
+    n, T, seed = 1500, 120, 77
+    fused = pkg.CopterVecEnv(variant, n, dtype=dtype, seed=seed, track_returns=True)
+    single = pkg.CopterVecEnv(variant, n, dtype=dtype, seed=seed, track_returns=True)
+    orc = EnvBatch(variant, n, seed=seed)
+    fused.reset(); single.reset(); orc.reset()
+    out = fused.rollout(T, source=source, record_rewards=True, record_dones=True, record_actions=True)
+    acts = out['actions']
+    tol = 1e-9 if dtype == torch.float64 else 1e-4
+    sync = np.ones(n, bool)
+    rsum = torch.zeros(n, dtype=dtype, device='cuda')
+    dany = torch.zeros(n, dtype=torch.bool, device='cuda')
+    for t in range(T):
+        obs, r, term, _, _ = single.step(acts[t])
+        assert torch.equal(r, out['rewards'][t]) and torch.equal(term, out['dones'][t])
+        rsum += r
+        dany |= term
+        o_obs, o_r, o_done, _ = orc.step(acts[t].cpu().numpy().astype(np.float64))
+        d = term.cpu().numpy()
+        sync &= (d == o_done) & (single.status.cpu().numpy() == orc.dyn.status)
+        assert merr(r.cpu().numpy()[sync], o_r[sync]) <= tol
+    assert torch.equal(fused.state, single.state) and torch.equal(fused.meta, single.meta)
+    assert torch.equal(out['obs'], single.obs) and torch.equal(out['done_any'], dany)
+    assert merr(out['reward_sum'].cpu().numpy(), rsum.cpu().numpy()) <= (1e-12 if dtype == torch.float64 else 1e-5)
+    fs, ss = fused.stats(), single.stats()
+    for k in ('episodes', 'length_sum', 'landed', 'bonus', 'crashed', 'oob', 'angle', 'timeout', 'env_steps'):
+        assert fs[k] == ss[k], k
+    assert abs(fs['return_sum'] - ss['return_sum']) <= 1e-6 * max(1.0, abs(ss['return_sum']))
+    assert fs['env_steps'] == n * T
+    assert sync.sum() >= (n if dtype == torch.float64 else 0.99 * n)
+    if source != 'uniform' or dtype == torch.float64:
+        assert merr(fused.state.cpu().numpy()[sync], orc.dyn.x[sync]) <= tol
+
+
+def test_rollout_is_independent_of_launch_partition(pkg):
+    n, seed = 777, 3
+    a = pkg.CopterVecEnv('Lander3D', n, seed=seed)
+    b = pkg.CopterVecEnv('Lander3D', n, seed=seed)
+    a.reset(); b.reset()
+    a.rollout(60, source='randn')
+    for chunk in (1, 7, 20, 32):
+        b.rollout(chunk, source='randn')
+    assert torch.equal(a.state, b.state) and torch.equal(a.meta, b.meta) and a.rollout_step == b.rollout_step == 60
+
+
+def test_policy_rollout_graph_equals_eager(pkg):
+    n, T = 4096, 6
+    envs = [pkg.CopterVecEnv('Lander3D', n, seed=5) for _ in range(2)]
+    pol = pkg.mlp_policy(10, 4, dtype=torch.float32, seed=1)
+    scaled = lambda obs: 0.0166 * (1 + 0.2 * pol(obs))         # noqa: E731  (keeps the copters flying)
+    for e in envs:
+        e.reset()
+    graph = pkg.PolicyRollout(envs[0], scaled, T, store_obs=True, use_cuda_graph=True)
+    eager = pkg.PolicyRollout(envs[1], scaled, T, store_obs=True, use_cuda_graph=False)
+    for it in range(3):
+        r1, d1, o1 = graph.run()
+        r2, d2, o2 = eager.run()
+        assert torch.equal(r1, r2) and torch.equal(d1, d2) and torch.equal(o1, o2)
+        assert torch.equal(graph.obs, eager.obs)
+    assert torch.equal(envs[0].state, envs[1].state)
+    assert r1.shape == (T, n) and d1.dtype == torch.bool
+
+
+def test_step_host_matches_device_step(pkg):
+    n = 70000
+    rng = np.random.default_rng(0)
+    e1 = pkg.CopterVecEnv('Lander3D', n, seed=4, track_stats=True)
+    e2 = pkg.CopterVecEnv('Lander3D', n, seed=4, track_stats=True)
+    e1.reset(); e2.reset()
+    for t in range(12):
+        a = (1.625e-2 * rng.standard_normal((n, 4))).astype(np.float32)
+        if t % 2:
+            a[::3] = rng.uniform(-1, 1, (len(a[::3]), 4)).astype(np.float32)
+        obs, r, term, trunc, _ = e1.step_host(a, chunk_envs=8192, n_streams=3)
+        o2, r2, t2, _, _ = e2.step(torch.as_tensor(a))
+        assert isinstance(obs, np.ndarray) and obs.dtype == np.float32 and term.dtype == np.bool_
+        assert np.array_equal(obs, o2.cpu().numpy()) and np.array_equal(r, r2.cpu().numpy())
+        assert np.array_equal(term, t2.cpu().numpy()) and not trunc.any()
+    assert torch.equal(e1.state, e2.state) and e1.stats() == e2.stats()
+    e1.close()
+
+
+def test_csv_export_matches_lander_py_format(pkg, tmp_path):
+    env = pkg.make('gym_copter:Lander-v0')
+    obs, _ = env.reset(force=[1.0, 2.0, 3.0])
+    path = os.path.join(tmp_path, 'traj.csv')
+    with pkg.CsvTrajectoryWriter(path, env) as w:
+        for k in range(5):
+            a = 1.625e-2 * np.ones(4)
+            obs, r, done, _, _ = env.step(a)
+            w.write(a, obs)
+    lines = open(path).read().strip().split('\n')
+    # lander.py:33-38 header, :48-54 rows
+    assert lines[0] == 't,m1,m2,m3,m4,X,dX,Y,dY,Z,dZ,Phi,dPhi,Theta,dTheta'
+    assert len(lines) == 6 and all(len(l.split(',')) == 15 for l in lines[1:])
+    first = lines[1].split(',')
+    assert first[0] == '0.000000' and first[1] == '0.016250' and lines[2].split(',')[0] == '0.010000'
+    assert abs(float(first[9]) - (-10.0)) < 1e-6

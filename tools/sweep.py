@@ -64,8 +64,35 @@ def time_one(envs, k, steps, stats):
     print(json.dumps({'ms': best, 'gbs': 165 * envs / best / 1e6, 'steps_per_s': envs * k / best * 1e3}))
 
 
+def copy_peak():
+    """This box's own copy bandwidth, measured the way MEASURED_PEAKS.json's hbm_gbs was
+    (torch b.copy_(a) over 1 Gi bf16 elements, read + write bytes): burst best-of-10, then a
+    0.5 s back-to-back loop."""
+    import torch
+    a = torch.empty(1 << 30, dtype=torch.bfloat16, device='cuda')
+    b = torch.empty_like(a)
+    a.fill_(1.0)
+    for _ in range(3):
+        b.copy_(a)
+    best = 1e9
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record(); b.copy_(a); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(800):
+        b.copy_(a)
+    e1.record(); torch.cuda.synchronize()
+    gb = 2 * a.numel() * 2 / 1e9
+    print(json.dumps({'copy_burst_gbs': gb / best * 1e3, 'copy_sustained_gbs': gb * 800 / e0.elapsed_time(e1) * 1e3}), flush=True)
+
+
 def run(envs, k, stats):
-    for name in VARIANTS:
+    if k == 1:
+        copy_peak()
+    extra = sorted(f[4:-3] for f in os.listdir(VDIR) if f.startswith('lib_v') and f.endswith('.so'))
+    for name in list(VARIANTS) + extra:
         lib = os.path.join(VDIR, 'lib_%s.so' % name)
         if not os.path.exists(lib):
             continue
