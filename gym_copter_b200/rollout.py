@@ -52,13 +52,16 @@ class PolicyRollout:
             self._body()
         else:
             if self._graph is None:
-                # warm up on a side stream (allocator + lazy module init), then capture
+                # warm up on a side stream (allocator + lazy module init), roll the env back,
+                # then capture
+                snapshot = self.env.state_dict()
                 s = torch.cuda.Stream(device=self.env.device)
                 s.wait_stream(torch.cuda.current_stream(self.env.device))
                 with torch.cuda.stream(s):
                     self._body()
                 torch.cuda.current_stream(self.env.device).wait_stream(s)
                 torch.cuda.synchronize(self.env.device)
+                self.env.load_state_dict(snapshot)
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
                     self._body()

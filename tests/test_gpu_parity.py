@@ -112,7 +112,7 @@ class Tracker:
         assert self.max_state <= self.tol, self.max_state
         assert self.max_obs <= max(self.tol, self.F32_EPS), self.max_obs
         assert self.max_reward <= self.tol, self.max_reward
-        assert self.max_component <= 10 * self.tol, self.max_component
+        assert self.max_component <= max(10 * self.tol, self.F32_EPS), self.max_component
         assert self.episodes >= min_episodes
         if self.exact:
             assert self.flips == 0
