@@ -30,14 +30,20 @@
 namespace {
 
 #ifndef COPTER_F32_CTAS_PER_SM
-#define COPTER_F32_CTAS_PER_SM 4
+#define COPTER_F32_CTAS_PER_SM 8  // x 128 threads: 1024 resident envs per SM at <= 64 registers
 #endif
 
 #ifndef COPTER_BLOCK
-#define COPTER_BLOCK 256
+#define COPTER_BLOCK 128
 #endif
 #ifndef COPTER_LIBM_ONLY
 #define COPTER_LIBM_ONLY 0      // 1 (A/B knob): library sincosf, IEEE sqrt and division everywhere
+#endif
+#ifndef COPTER_PREFETCH
+#define COPTER_PREFETCH 0       // (A/B knob, persistent grids only) request the NEXT tile's loads before this tile's arithmetic
+#endif
+#ifndef COPTER_PERSISTENT
+#define COPTER_PERSISTENT 0     // 1 (A/B knob): one resident wave of CTAs walking the tiles with a grid stride
 #endif
 #ifndef COPTER_STREAMING
 #define COPTER_STREAMING 0      // 1: evict-first (ld/st .cs) hints on the state planes
@@ -375,11 +381,75 @@ __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, float* t
     __syncwarp();
 }
 
-// Folds the episodes that ended in this warp (flag `ended` per lane) into the CTA's shared
-// statistics: ballot/popc per cause bit, REDUX for the length sum, shuffle tree for the fp64
-// return sum; lane 0 then issues the shared-memory atomics.  Warp-uniform call.
 template <typename T>
-__device__ __forceinline__ void flush_episode_stats(double* block_stats, int lane, bool ended_lane, int ep_cause,
+struct StepArgs {
+    T* state; uint32_t* meta; const T* action; float* obs; T* reward; uint8_t* done;
+    const T* init_force; T* ep_return; double* stats; float* final_obs;
+    int64_t n, stride, env_offset; uint64_t seed; int k; int auto_reset;
+};
+template <typename T> using StepArgsBase = StepArgs<T>;
+
+// One env's inputs exactly as they sit in HBM (128-bit vectors), so that the loads of the
+// NEXT tile can be issued before the arithmetic of the current one without being decoded.
+template <typename T, int A> struct RawEnv {
+    typename Vec<T>::type plane[12 / Vec<T>::V];
+    T act[A];
+    uint32_t meta;
+};
+
+template <typename T, int A>
+__device__ __forceinline__ void load_raw(const StepArgsBase<T>& a, int64_t i, RawEnv<T, A>& r) {
+    using V4 = typename Vec<T>::type;
+    constexpr int V = Vec<T>::V;
+    const V4* planes = reinterpret_cast<const V4*>(a.state);
+#pragma unroll
+    for (int pl = 0; pl < 12 / V; ++pl)
+        r.plane[pl] = COPTER_STREAMING ? __ldcs(&planes[(int64_t)pl * a.stride + i]) : planes[(int64_t)pl * a.stride + i];
+    r.meta = a.meta[i];
+    if constexpr (A == 4 && sizeof(T) == 4) {
+        const float4 v = reinterpret_cast<const float4*>(a.action)[i];
+        r.act[0] = v.x; r.act[1] = v.y; r.act[2] = v.z; r.act[3] = v.w;
+    } else if constexpr (A == 4) {
+        const double2 v0 = reinterpret_cast<const double2*>(a.action)[2 * i];
+        const double2 v1 = reinterpret_cast<const double2*>(a.action)[2 * i + 1];
+        r.act[0] = v0.x; r.act[1] = v0.y; r.act[2] = v1.x; r.act[3] = v1.y;
+    } else if constexpr (A == 2 && sizeof(T) == 4) {
+        const float2 v = reinterpret_cast<const float2*>(a.action)[i];
+        r.act[0] = v.x; r.act[1] = v.y;
+    } else if constexpr (A == 2) {
+        const double2 v = reinterpret_cast<const double2*>(a.action)[i];
+        r.act[0] = v.x; r.act[1] = v.y;
+    } else {
+        r.act[0] = a.action[i];
+    }
+}
+
+template <typename T, int A>
+__device__ __forceinline__ void decode_raw(const RawEnv<T, A>& r, T (&s)[12], T (&m)[4], int& st, int& steps, uint32_t& episode) {
+    constexpr int V = Vec<T>::V;
+#pragma unroll
+    for (int pl = 0; pl < 12 / V; ++pl) {
+        const T* e = reinterpret_cast<const T*>(&r.plane[pl]);
+#pragma unroll
+        for (int j = 0; j < V; ++j) s[pl * V + j] = e[j];
+    }
+    st = (int)(r.meta & 3u); steps = (int)((r.meta >> 2) & 2047u); episode = r.meta >> 13;
+    // action row, clipped to [0,1] (task.py:91) and fanned out (_get_motors)
+    T act[A];
+#pragma unroll
+    for (int j = 0; j < A; ++j) act[j] = fmin(fmax(r.act[j], (T)0), (T)1);
+    if constexpr (A == 4) { m[0] = act[0]; m[1] = act[1]; m[2] = act[2]; m[3] = act[3]; }
+    else if constexpr (A == 2) { m[0] = act[0]; m[1] = act[1]; m[2] = act[1]; m[3] = act[0]; }   // attic lander2d.py:49-51
+    else { m[0] = m[1] = m[2] = m[3] = act[0]; }                                                // attic lander1d.py:47-49
+}
+
+// Folds the episodes that ended in this warp (flag `ended_lane`) into the statistics: ballot /
+// popc per cause bit, REDUX for the length sum, a shuffle tree for the fp64 return sum; lane 0
+// then issues a handful of global atomics into this warp's slot (COPTER_STATS_SLOTS rows, 128
+// bytes apart, so concurrent warps rarely hit the same line).  Nothing is issued when no
+// episode ended -- the common case.  Warp-uniform call.
+template <typename T>
+__device__ __forceinline__ void flush_episode_stats(double* stats, int lane, bool ended_lane, int ep_cause,
                                                     int ep_len, T ep_ret, bool has_returns) {
     const unsigned full = 0xffffffffu;
     const unsigned ended = __ballot_sync(full, ended_lane);
@@ -394,92 +464,80 @@ __device__ __forceinline__ void flush_episode_stats(double* block_stats, int lan
 #pragma unroll
     for (int c = 0; c < 6; ++c) by_cause[c] = __ballot_sync(full, ended_lane && ((ep_cause >> c) & 1));
     if (lane == 0) {
-        atomicAdd(&block_stats[COPTER_STAT_EPISODES], (double)__popc(ended));
-        atomicAdd(&block_stats[COPTER_STAT_LENGTH_SUM], (double)len_sum);
-        if (has_returns) atomicAdd(&block_stats[COPTER_STAT_RETURN_SUM], ret_sum);
+        double* row = stats + (size_t)((blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) % COPTER_STATS_SLOTS) * COPTER_STATS_LEN;
+        atomicAdd(&row[COPTER_STAT_EPISODES], (double)__popc(ended));
+        atomicAdd(&row[COPTER_STAT_LENGTH_SUM], (double)len_sum);
+        if (has_returns) atomicAdd(&row[COPTER_STAT_RETURN_SUM], ret_sum);
         // cause bits: LANDED, BONUS, OOB, ANGLE, CRASHED, TIMEOUT
         const int slot[6] = {COPTER_STAT_LANDED, COPTER_STAT_BONUS, COPTER_STAT_OOB, COPTER_STAT_ANGLE, COPTER_STAT_CRASHED, COPTER_STAT_TIMEOUT};
 #pragma unroll
-        for (int c = 0; c < 6; ++c) if (by_cause[c]) atomicAdd(&block_stats[slot[c]], (double)__popc(by_cause[c]));
+        for (int c = 0; c < 6; ++c) if (by_cause[c]) atomicAdd(&row[slot[c]], (double)__popc(by_cause[c]));
     }
+}
+
+// Executed env-steps: thread 0 of CTA 0 credits the launch with n * K up front; a warp whose
+// envs idled after finishing inside a K-fused launch takes the idle substeps back.
+__device__ __forceinline__ void credit_env_steps(double* stats, int64_t n, int k) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[COPTER_STAT_ENV_STEPS], (double)n * (double)k);
+}
+__device__ __forceinline__ void debit_idle_steps(double* stats, int lane, int idle) {
+    idle = __reduce_add_sync(0xffffffffu, idle);
+    if (idle && lane == 0)
+        atomicAdd(&stats[(size_t)((blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) % COPTER_STATS_SLOTS) * COPTER_STATS_LEN + COPTER_STAT_ENV_STEPS], -(double)idle);
 }
 
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
-template <typename T>
-struct StepArgs {
-    T* state; uint32_t* meta; const T* action; float* obs; T* reward; uint8_t* done;
-    const T* init_force; T* ep_return; double* stats; float* final_obs;
-    int64_t n, stride, env_offset; uint64_t seed; int k; int auto_reset;
-};
 
 template <typename T, int VARIANT, bool STATS>
 __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? COPTER_F32_CTAS_PER_SM : 2)
 copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant__ StepArgs<T> a) {
     constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A;
     __shared__ __align__(16) float tiles[kWarpsPerBlock][32 * O];
-    __shared__ double block_stats[STATS ? 10 : 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* tile = tiles[warp];
+    if (STATS) credit_env_steps(a.stats, a.n, a.k);
 
-    // Statistics: only the executed-step count lives in a register across tiles; episode events
-    // are folded into the CTA's shared counters at the end of the tile in which they happen
-    // (ballot/popc per cause, REDUX for the length sum), and each CTA issues one global atomic
-    // per statistic when it retires.
-    int n_steps = 0;
-
-    if (STATS) {
-        if (threadIdx.x < 10) block_stats[threadIdx.x] = 0.0;
-        __syncthreads();
-    }
-
+    // Software pipeline (fp32): the raw vectors of this thread's env in the NEXT tile are
+    // requested before the current tile's arithmetic starts, so every resident thread always
+    // has one tile of loads (68 B) in flight -- the kernel is latency-bound otherwise (ncu:
+    // 2/3 of the stall samples sat on the first use of the loaded state).
+    constexpr bool kPrefetch = COPTER_PREFETCH && sizeof(T) == 4;
     const int64_t n_tiles = (a.n + kBlock - 1) / kBlock;
+    RawEnv<T, A> cur, nxt;
+    if (kPrefetch) {
+        const int64_t i0 = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+        if (blockIdx.x < n_tiles && i0 < a.n) load_raw<T, A>(a, i0, cur);
+    }
     for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
         const int64_t row0 = tile_id * kBlock + warp * 32;       // first env of this warp
         const int64_t i = row0 + lane;
         const bool valid = i < a.n;
         const int rows = (int)max((int64_t)0, min((int64_t)32, a.n - row0));
 
+        if (kPrefetch) {
+            const int64_t inext = i + (int64_t)gridDim.x * kBlock;
+            if (inext < a.n) load_raw<T, A>(a, inext, nxt);
+        } else if (valid) {
+            load_raw<T, A>(a, i, cur);
+        }
+
         T s[12];
         T m[4] = {(T)0, (T)0, (T)0, (T)0};
         int st = ST_LANDED, steps = 1; uint32_t episode = 0;
         T total = (T)0; bool done_any = false;
-        T ret = (T)0, ep_ret = (T)0; int ep_cause = 0, ep_len = 0;     // STATS only
+        T ret = (T)0, ep_ret = (T)0; int ep_cause = 0, ep_len = 0, n_steps = 0;     // STATS only
 
         if (valid) {
-            load_state<T>(a.state, a.stride, i, s);
-            const uint32_t mw = a.meta[i];
-            st = (int)(mw & 3u); steps = (int)((mw >> 2) & 2047u); episode = mw >> 13;
-            // action row, clipped to [0,1] (task.py:91) and fanned out (_get_motors)
-            T act[A];
-            if constexpr (A == 4 && sizeof(T) == 4) {
-                const float4 v = reinterpret_cast<const float4*>(a.action)[i];
-                act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
-            } else if constexpr (A == 4) {
-                const double2 v0 = reinterpret_cast<const double2*>(a.action)[2 * i];
-                const double2 v1 = reinterpret_cast<const double2*>(a.action)[2 * i + 1];
-                act[0] = v0.x; act[1] = v0.y; act[2] = v1.x; act[3] = v1.y;
-            } else if constexpr (A == 2 && sizeof(T) == 4) {
-                const float2 v = reinterpret_cast<const float2*>(a.action)[i];
-                act[0] = v.x; act[1] = v.y;
-            } else if constexpr (A == 2) {
-                const double2 v = reinterpret_cast<const double2*>(a.action)[i];
-                act[0] = v.x; act[1] = v.y;
-            } else {
-                act[0] = a.action[i];
-            }
-#pragma unroll
-            for (int j = 0; j < A; ++j) act[j] = fmin(fmax(act[j], (T)0), (T)1);
-            if constexpr (A == 4) { m[0] = act[0]; m[1] = act[1]; m[2] = act[2]; m[3] = act[3]; }
-            else if constexpr (A == 2) { m[0] = act[0]; m[1] = act[1]; m[2] = act[1]; m[3] = act[0]; }   // attic lander2d.py:49-51
-            else { m[0] = m[1] = m[2] = m[3] = act[0]; }                                                // attic lander1d.py:47-49
+            decode_raw<T, A>(cur, s, m, st, steps, episode);
             if (STATS && a.ep_return) ret = a.ep_return[i];
         } else {
 #pragma unroll
             for (int j = 0; j < 12; ++j) s[j] = (T)0;
         }
+        if (kPrefetch) cur = nxt;
 
         Shaping<T> pre_sh = lander_shaping<T>(kp, s);
         // the action is fixed for the K substeps of a launch, so Eq. 6 (the fp64 stage) runs once
@@ -526,14 +584,10 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
             if (STATS && a.ep_return) a.ep_return[i] = ret;
         }
         if (a.obs) write_obs_rows<VARIANT, T>(a.obs, tile, lane, row0, rows, s);
-        if (STATS) flush_episode_stats<T>(block_stats, lane, done_any, ep_cause, ep_len, ep_ret, a.ep_return != nullptr);
-    }
-
-    if (STATS) {
-        n_steps = __reduce_add_sync(0xffffffffu, n_steps);
-        if (lane == 0 && n_steps) atomicAdd(&block_stats[COPTER_STAT_ENV_STEPS], (double)n_steps);
-        __syncthreads();
-        if (threadIdx.x < 10 && block_stats[threadIdx.x] != 0.0) atomicAdd(&a.stats[threadIdx.x], block_stats[threadIdx.x]);
+        if (STATS) {
+            flush_episode_stats<T>(a.stats, lane, done_any, ep_cause, ep_len, ep_ret, a.ep_return != nullptr);
+            if (a.k > 1) debit_idle_steps(a.stats, lane, valid ? a.k - n_steps : 0);
+        }
     }
 }
 
@@ -588,13 +642,8 @@ __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? COPTER_F32_CTAS_PER_S
 copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant__ RolloutArgs<T> a) {
     constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A;
     __shared__ __align__(16) float tiles[kWarpsPerBlock][32 * O];
-    __shared__ double block_stats[STATS ? 10 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int n_steps = 0;
-    if (STATS) {
-        if (threadIdx.x < 10) block_stats[threadIdx.x] = 0.0;
-        __syncthreads();
-    }
+    if (STATS) credit_env_steps(a.stats, a.n, a.n_steps);
     const int64_t n_tiles = (a.n + kBlock - 1) / kBlock;
     for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
         const int64_t row0 = tile_id * kBlock + warp * 32, i = row0 + lane;
@@ -639,7 +688,7 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
                 T r;
                 env_substep<T, VARIANT>(kp, s, st, steps, forces, pert, pre_sh, r, dn, cause);
                 total += r;
-                if (STATS) { ++n_steps; ret += r; }
+                if (STATS) ret += r;
                 if (a.reward_tn) a.reward_tn[(int64_t)t * a.n + i] = r;
                 if (a.done_tn) a.done_tn[(int64_t)t * a.n + i] = dn ? 1 : 0;
                 if (dn) {
@@ -652,7 +701,7 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
                     }
                 }
             }
-            if (STATS) flush_episode_stats<T>(block_stats, lane, dn, cause, ep_len, ep_ret, a.ep_return != nullptr);
+            if (STATS) flush_episode_stats<T>(a.stats, lane, dn, cause, ep_len, ep_ret, a.ep_return != nullptr);
         }
         if (valid) {
             store_state<T>(a.state, a.stride, i, s);
@@ -662,12 +711,6 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
             if (STATS && a.ep_return) a.ep_return[i] = ret;
         }
         if (a.obs) write_obs_rows<VARIANT, T>(a.obs, tiles[warp], lane, row0, rows, s);
-    }
-    if (STATS) {
-        n_steps = __reduce_add_sync(0xffffffffu, n_steps);
-        if (lane == 0 && n_steps) atomicAdd(&block_stats[COPTER_STAT_ENV_STEPS], (double)n_steps);
-        __syncthreads();
-        if (threadIdx.x < 10 && block_stats[threadIdx.x] != 0.0) atomicAdd(&a.stats[threadIdx.x], block_stats[threadIdx.x]);
     }
 }
 
@@ -742,9 +785,14 @@ int sm_count() {
     return sms;
 }
 
-// Persistent-style grid: at most one resident wave (SMs x CTAs/SM of this kernel), each CTA
-// walking the 256-env tiles with a grid stride.  The occupancy query runs once per kernel
-// instantiation (and never inside a CUDA-graph capture after the first, uncaptured call).
+// Grid: one CTA per tile of kBlock envs, scheduled by the hardware as CTAs retire.  Measured on
+// B200 (Lander3D fp32, 2^24 envs, K = 1): 6.7 TB/s, against 5.6 TB/s for a persistent grid of
+// SMs x resident CTAs walking the tiles with a grid stride -- persistent CTAs start together,
+// do identical work and stay phase-locked (everyone loads, then everyone computes, then
+// everyone stores), so DRAM sees bursts; CTAs that start whenever a slot frees up spread the
+// three phases evenly in time.  (COPTER_PERSISTENT=1 / COPTER_PREFETCH=1 keep the old shape for
+// A/B runs; profiles/README.md has the sweep.)  The kernels keep their tile loop, so a grid
+// capped at 2^31-1 CTAs still covers any n.
 template <auto Kernel>
 int grid_for(int64_t n) {
     static int per_sm = 0;
@@ -754,7 +802,7 @@ int grid_for(int64_t n) {
         per_sm = q;
     }
     const int64_t tiles = (n + kBlock - 1) / kBlock;
-    const int64_t cap = (int64_t)sm_count() * per_sm;
+    const int64_t cap = COPTER_PERSISTENT ? (int64_t)sm_count() * per_sm : (int64_t)0x7fffffff;
     return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 

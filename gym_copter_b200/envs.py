@@ -123,7 +123,7 @@ class CopterVecEnv:
         self._action = torch.zeros((n, self.action_size), dtype=dtype, device=dev)
         track_stats = track_stats or track_returns
         self.ep_return = torch.zeros(n, dtype=dtype, device=dev) if track_returns else None
-        self._stats = torch.zeros(_lib.STATS_LEN, dtype=torch.float64, device=dev) if track_stats else None
+        self._stats = torch.zeros((_lib.STATS_SLOTS, _lib.STATS_LEN), dtype=torch.float64, device=dev) if track_stats else None
         self.final_obs = torch.zeros((n, self.obs_size), dtype=torch.float32, device=dev) if keep_final_obs else None
         self._force = None
         self._is_reset = False
@@ -396,7 +396,7 @@ class CopterVecEnv:
         """
         if self._stats is None:
             raise CopterError('construct the env with track_stats=True')
-        v = self._stats.clone()
+        v = self._stats.sum(0)
         if reduce_group is not None:
             from .sharding import all_reduce_stats
             all_reduce_stats(v, None if reduce_group is True else reduce_group)

@@ -64,7 +64,10 @@ enum { COPTER_E_ARG = -1, COPTER_E_VARIANT = -2, COPTER_E_ALIGN = -3, COPTER_E_R
 /* flags for copter_step_* */
 enum { COPTER_F_AUTO_RESET = 1 };
 
-/* episode statistics vector (double[COPTER_STATS_LEN]); accumulated with atomics, never cleared by the library */
+/* episode statistics: double[COPTER_STATS_SLOTS][COPTER_STATS_LEN], accumulated with atomics and never
+   cleared by the library.  A CTA adds to slot (blockIdx.x % COPTER_STATS_SLOTS) so that the atomics of
+   concurrent CTAs land on different 128-byte lines; the statistic is the sum over the slots. */
+#define COPTER_STATS_SLOTS 64
 enum { COPTER_STAT_EPISODES = 0, COPTER_STAT_RETURN_SUM = 1, COPTER_STAT_LENGTH_SUM = 2,
        COPTER_STAT_LANDED = 3, COPTER_STAT_BONUS = 4, COPTER_STAT_CRASHED = 5, COPTER_STAT_OOB = 6,
        COPTER_STAT_ANGLE = 7, COPTER_STAT_TIMEOUT = 8, COPTER_STAT_ENV_STEPS = 9, COPTER_STATS_LEN = 16 };
@@ -102,7 +105,7 @@ typedef struct CopterBuffers {
     uint8_t*    done;        /* [n]                (unused by reset) */
     const void* init_force;  /* T[n][3] nullable: injected reset force (N) used instead of the Philox draw */
     void*       ep_return;   /* T[n]   nullable: running episode return, feeds COPTER_STAT_RETURN_SUM */
-    double*     stats;       /* [COPTER_STATS_LEN] nullable */
+    double*     stats;       /* [COPTER_STATS_SLOTS][COPTER_STATS_LEN] nullable */
     float*      final_obs;   /* [n][O] nullable: observation of the terminal state of envs that finished */
     int64_t     state_stride;/* vectors per state plane in the allocation; 0 means n. Lets a call step a
                                 sub-range [lo, lo+n) of a larger shard: pass state + lo vectors, stride = shard size */
