@@ -244,8 +244,16 @@ def main():
     peak = float(peaks.get('hbm_gbs', 6650.0))
     b_launch = bytes_per_launch_per_env(w, A, O)
     achieved = b_launch * n / (ms * 1e-3 / args.steps) / 1e9
+    traffic = None          # DRAM bytes per launch from the committed ncu --set full capture of this kernel
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
+            tj = json.load(f)
+        if tj['envs'] == n and tj['k_substeps'] == k and args.variant == 'Lander3D' and args.dtype == 'f32':
+            traffic = tj['dram_bytes_per_launch']
+    except Exception:
+        pass
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650',
+                'traffic': traffic, 'algorithmic_bytes_per_launch': b_launch * n, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650',
                 'kernel': 'copter_step_kernel<%s,%s,stats>' % (args.dtype, args.variant),
                 'bytes_per_env_per_launch': b_launch, 'env_steps_per_launch': n * k}
 
