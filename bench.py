@@ -193,6 +193,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION in the image prints a banner there)
+        os.environ['NCCL_DEBUG'] = os.environ.get('COPTER_NCCL_DEBUG', 'WARN')
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():

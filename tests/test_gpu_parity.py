@@ -492,3 +492,47 @@ def test_checkpoint_roundtrip(pkg):
         o1, r1, d1, _, _ = e1.step(act[t])
         o2, r2, d2, _, _ = e2.step(act[t])
         assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE.json sizes: size-independent properties on a 2^22-env shard
+# ---------------------------------------------------------------------------------------
+
+def test_full_size_sampled_parity_and_conservation(pkg):
+    """4 M envs (config 3's per-GPU shard is 2 M): (a) 4096 randomly chosen envs, re-run alone
+    by the C oracle from their global ids and their rows of the action tensors, agree with the
+    big batch; (b) episode bookkeeping is conserved: sum of done flags == episodes statistic,
+    sum over envs of the episode counters == the same, executed env-steps == N * T;
+    (c) stepping the second half of the batch as its own shard gives bit-identical results."""
+    from oracle.c_oracle import CEnvBatch
+    N, T, seed = 1 << 22, 120, 31337
+    g = torch.Generator(device='cuda').manual_seed(1)
+    env = pkg.CopterVecEnv('Lander3D', N, dtype=torch.float32, seed=seed, track_stats=True)
+    half = pkg.CopterVecEnv('Lander3D', N // 2, dtype=torch.float32, seed=seed, env_offset=N // 2)
+    idx = np.sort(np.random.default_rng(0).choice(N, 4096, replace=False))
+    idx_t = torch.as_tensor(idx, device='cuda')
+    orc = CEnvBatch('Lander3D', len(idx), seed=seed, env_ids=idx)
+    env.reset(); half.reset(); orc.reset()
+    done_total = 0
+    sync = np.ones(len(idx), bool)
+    worst = 0.0
+    for t in range(T):
+        a = 1.625e-2 * torch.randn((N, 4), device='cuda', generator=g)
+        if t % 4 == 0:
+            a[::5] = 2 * torch.rand((len(a[::5]), 4), device='cuda', generator=g) - 1
+        obs, r, term, _, _ = env.step(a)
+        o2, r2, t2, _, _ = half.step(a[N // 2:])
+        assert torch.equal(o2, obs[N // 2:]) and torch.equal(r2, r[N // 2:]) and torch.equal(t2, term[N // 2:])
+        done_total += int(term.sum().item())
+        o_obs, o_r, o_done, _ = orc.step(a[idx_t].cpu().numpy().astype(np.float64))
+        d = term[idx_t].cpu().numpy()
+        sync &= (d == o_done) & (env.status[idx_t].cpu().numpy() == orc.status)
+        x = env.state[idx_t].cpu().numpy()
+        scale = np.maximum(np.abs(orc.x).max(1, keepdims=True), 1.0)          # saturating commands present
+        worst = max(worst, float((np.abs(x - orc.x) / scale)[sync].max()),
+                    float((np.abs(r[idx_t].cpu().numpy() - o_r) / np.maximum(np.abs(o_r), 1))[sync].max()))
+    assert sync.sum() >= 0.99 * len(idx) and worst <= 1e-4, (sync.sum(), worst)
+    s = env.stats()
+    assert s['episodes'] == done_total == int(env.episodes.to(torch.int64).sum().item())
+    assert s['env_steps'] == N * T
+    assert torch.equal(half.state, env.state[N // 2:]) and torch.equal(half.meta, env.meta[N // 2:])
