@@ -13,6 +13,7 @@ ABI_VERSION = 1
 STATS_LEN = 16
 STATS_SLOTS = 64
 F_AUTO_RESET = 1
+CAUSE_LANDED, CAUSE_BONUS, CAUSE_OOB, CAUSE_ANGLE, CAUSE_CRASHED, CAUSE_TIMEOUT = 1, 2, 4, 8, 16, 32
 STATUS_CRASHED, STATUS_LANDED, STATUS_LEVELING, STATUS_AIRBORNE = 0, 1, 2, 3
 VARIANT_IDS = {'Lander3D': 0, 'Lander2D': 1, 'Lander1D': 2, 'Hover3D': 3, 'Hover2D': 4, 'Hover1D': 5}
 STAT_NAMES = ('episodes', 'return_sum', 'length_sum', 'landed', 'bonus', 'crashed', 'oob',
@@ -33,7 +34,7 @@ class CopterBuffers(C.Structure):
     _fields_ = [('state', C.c_void_p), ('meta', C.c_void_p), ('action', C.c_void_p),
                 ('obs', C.c_void_p), ('reward', C.c_void_p), ('done', C.c_void_p),
                 ('init_force', C.c_void_p), ('ep_return', C.c_void_p), ('stats', C.c_void_p),
-                ('final_obs', C.c_void_p), ('state_stride', C.c_int64)]
+                ('final_obs', C.c_void_p), ('cause', C.c_void_p), ('state_stride', C.c_int64)]
 
 
 class CopterActionSource(C.Structure):

@@ -384,7 +384,7 @@ __device__ __forceinline__ void write_obs_rows(float* __restrict__ obs, float* t
 template <typename T>
 struct StepArgs {
     T* state; uint32_t* meta; const T* action; float* obs; T* reward; uint8_t* done;
-    const T* init_force; T* ep_return; double* stats; float* final_obs;
+    const T* init_force; T* ep_return; double* stats; float* final_obs; uint8_t* cause;
     int64_t n, stride, env_offset; uint64_t seed; int k; int auto_reset;
 };
 template <typename T> using StepArgsBase = StepArgs<T>;
@@ -562,7 +562,8 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
                 if (STATS) { ++n_steps; ret += r; }
                 if (dn) {
                     done_any = true;
-                    if (STATS) { ep_cause = cause; ep_len = steps - 1; ep_ret = ret; ret = (T)0; }   // `steps` is 1 right after reset (task.py:191,197)
+                    ep_cause = cause;
+                    if (STATS) { ep_len = steps - 1; ep_ret = ret; ret = (T)0; }   // `steps` is 1 right after reset (task.py:191,197)
                     if (a.final_obs) {   // terminal observation; rows of unfinished envs stay untouched
 #pragma unroll
                         for (int j = 0; j < O; ++j) a.final_obs[i * O + j] = (float)s[Variant<VARIANT>::first + j];
@@ -581,6 +582,7 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
             a.meta[i] = (uint32_t)st | ((uint32_t)steps << 2) | (episode << 13);
             a.reward[i] = total;
             a.done[i] = done_any ? 1 : 0;
+            if (a.cause) a.cause[i] = (uint8_t)ep_cause;
             if (STATS && a.ep_return) a.ep_return[i] = ret;
         }
         if (a.obs) write_obs_rows<VARIANT, T>(a.obs, tile, lane, row0, rows, s);
@@ -836,7 +838,7 @@ int launch_step(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_
     StepArgs<T> a;
     a.state = (T*)b->state; a.meta = b->meta; a.action = (const T*)b->action; a.obs = b->obs;
     a.reward = (T*)b->reward; a.done = b->done; a.init_force = (const T*)b->init_force;
-    a.ep_return = (T*)b->ep_return; a.stats = b->stats; a.final_obs = b->final_obs;
+    a.ep_return = (T*)b->ep_return; a.stats = b->stats; a.final_obs = b->final_obs; a.cause = b->cause;
     a.n = n; a.stride = b->state_stride > 0 ? b->state_stride : n; a.env_offset = env_offset; a.seed = seed; a.k = k; a.auto_reset = (flags & COPTER_F_AUTO_RESET) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     switch (variant) {
@@ -980,6 +982,7 @@ int step_host(Pipeline* pl, const CopterParams* p, const CopterBuffers* dev, con
         b.init_force = dev->init_force ? (const T*)dev->init_force + lo * 3 : nullptr;
         b.ep_return = dev->ep_return ? (T*)dev->ep_return + lo : nullptr;
         b.final_obs = dev->final_obs ? dev->final_obs + lo * O : nullptr;
+        b.cause = dev->cause ? dev->cause + lo : nullptr;
         if ((ce = cudaMemcpyAsync((void*)b.action, (const T*)h_action + lo * A, sizeof(T) * m * A, cudaMemcpyHostToDevice, st)) != cudaSuccess) return (int)ce;
         const int e = launch_step<T>(p, &b, m, env_offset + lo, seed, k, variant, flags, st);
         if (e) return e;

@@ -77,6 +77,12 @@ class CopterVecEnv:
     track_returns  also keep a running per-env episode return (one more T[N] array read and
                  written per step) so that `stats()` reports return sums / means
     keep_final_obs  also record the terminal observation of finished envs (`info['final_obs']`)
+    write_obs    False: the step kernel skips the [N,O] observation write (40 of 165 B per env
+                 for Lander3D); on the fp32 path consumers can read the state planes in place
+                 instead (`planar_obs()`, `rollout.PlanarLinear`) -- the zero-copy observation
+    report_cause  record why each env finished (`info['cause']`, COPTER_CAUSE_* bits) and report
+                 the env's own step limit as `truncated` the way gymnasium's
+                 TimeLimit(max_episode_steps) wrapper does for the reference (gym_copter/__init__.py:9-13)
     kwargs       any CopterParams field, e.g. initial_altitude=5, max_steps=500 (task.py:32-38)
     """
 
@@ -85,7 +91,8 @@ class CopterVecEnv:
 
     def __init__(self, variant='Lander3D', num_envs=1, dtype=torch.float32, device=None, seed=0,
                  env_offset=0, k_substeps=1, auto_reset=True, track_stats=False,
-                 track_returns=False, keep_final_obs=False, **params):
+                 track_returns=False, keep_final_obs=False, write_obs=True, report_cause=False,
+                 **params):
         if variant not in VARIANT_IDS:
             raise ValueError('unknown variant %r' % (variant,))
         if dtype not in (torch.float32, torch.float64):
@@ -125,6 +132,8 @@ class CopterVecEnv:
         self.ep_return = torch.zeros(n, dtype=dtype, device=dev) if track_returns else None
         self._stats = torch.zeros((_lib.STATS_SLOTS, _lib.STATS_LEN), dtype=torch.float64, device=dev) if track_stats else None
         self.final_obs = torch.zeros((n, self.obs_size), dtype=torch.float32, device=dev) if keep_final_obs else None
+        self.write_obs = bool(write_obs)
+        self.cause = torch.zeros(n, dtype=torch.uint8, device=dev) if report_cause else None
         self._force = None
         self._is_reset = False
         self._pipeline = None
@@ -137,7 +146,8 @@ class CopterVecEnv:
         b = CopterBuffers()
         b.state, b.meta = self.state_planes.data_ptr(), self.meta.data_ptr()
         b.action = action.data_ptr() if action is not None else None
-        b.obs = self.obs.data_ptr()
+        b.obs = self.obs.data_ptr() if (self.write_obs or action is None) else None
+        b.cause = self.cause.data_ptr() if (self.cause is not None and action is not None) else None
         b.reward = (self.reward if reward is None else reward).data_ptr()
         b.done = (self.done if done is None else done).data_ptr()
         b.init_force = force.data_ptr() if force is not None else None
@@ -216,8 +226,12 @@ class CopterVecEnv:
         info = {}
         if self.final_obs is not None:
             info['final_obs'] = self.final_obs
-        return (self.obs, self.reward if reward_out is None else reward_out,
-                (self.done if done_out is None else done_out).view(torch.bool), self._truncated, info)
+        truncated = self._truncated
+        if self.cause is not None:
+            info['cause'] = self.cause
+            truncated = (self.cause & _lib.CAUSE_TIMEOUT) != 0
+        return (self.obs if self.write_obs else None, self.reward if reward_out is None else reward_out,
+                (self.done if done_out is None else done_out).view(torch.bool), truncated, info)
 
     # ---- fused multi-step rollout with on-device action sources -----------------------
 
@@ -347,6 +361,14 @@ class CopterVecEnv:
         return self
 
     # ---- state access -------------------------------------------------------------------
+
+    def planar_obs(self):
+        """Zero-copy observation on the fp32 path: the state planes themselves, [3, N, 4] float32
+        (plane p holds components 4p..4p+3 of dynamics/__init__.py:48-59).  For Lander3D the
+        observation is components 0..9, i.e. planes 0, 1 and the first two lanes of plane 2."""
+        if not self._f32:
+            raise CopterError('planar_obs() needs the float32 path (observations are float32)')
+        return self.state_planes
 
     @property
     def state(self):

@@ -20,10 +20,17 @@ class PolicyRollout:
     policy   callable obs[N,O] f32 -> action[N,A] (torch module or function; runs under no_grad)
     horizon  T env.step() calls per rollout
     store_obs  also keep obs_t (the observation the policy saw) in a [T, N, O] buffer
+    planar     the policy takes the env's fp32 state planes [3,N,4] in place (see PlanarLinear)
+               instead of the packed observation; combine with CopterVecEnv(write_obs=False)
     """
 
-    def __init__(self, env, policy, horizon, store_obs=False, use_cuda_graph=True):
+    def __init__(self, env, policy, horizon, store_obs=False, use_cuda_graph=True, planar=False):
         self.env, self.policy, self.horizon = env, policy, int(horizon)
+        self.planar = bool(planar)
+        if not planar and not env.write_obs:
+            raise CopterError('env was built with write_obs=False: use planar=True')
+        if planar and store_obs:
+            raise CopterError('store_obs needs the packed observation (planar=False)')
         n, dev = env.num_envs, env.device
         self.rewards = torch.zeros((self.horizon, n), dtype=env.dtype, device=dev)
         self.dones = torch.zeros((self.horizon, n), dtype=torch.uint8, device=dev)
@@ -38,7 +45,7 @@ class PolicyRollout:
         for t in range(self.horizon):
             if self.obs is not None:
                 self.obs[t].copy_(env.obs)
-            action = self.policy(env.obs)
+            action = self.policy(env.planar_obs() if self.planar else env.obs)
             if action.dtype != env.dtype:
                 action = action.to(env.dtype)
             env.step(action, reward_out=self.rewards[t], done_out=self.dones[t])
@@ -68,6 +75,28 @@ class PolicyRollout:
             self._graph.replay()
             self.env.launches += self.horizon
         return self.rewards, self.dones.view(torch.bool), self.last_obs
+
+
+class PlanarLinear(torch.nn.Module):
+    """
+    First layer of a policy that reads the env's fp32 state planes in place instead of a packed
+    [N,O] observation: y = sum_p planes[p][:, :w_p] @ W[:, 4p:4p+w_p].T + b, for the leading
+    `obs_size` state components (Lander3D: 10 = planes 0, 1 and half of plane 2).  Same result as
+    `linear(obs)` up to summation order; saves the observation write in the step kernel.
+    """
+
+    def __init__(self, linear, obs_size):
+        super().__init__()
+        self.linear, self.obs_size = linear, int(obs_size)
+
+    def forward(self, planes):
+        w, out = self.linear.weight, None
+        for p in range((self.obs_size + 3) // 4):
+            k = min(4, self.obs_size - 4 * p)
+            x = planes[p] if k == 4 else planes[p][:, :k]
+            y = x.to(w.dtype) @ w[:, 4 * p:4 * p + k].t()
+            out = y if out is None else out + y
+        return out if self.linear.bias is None else out + self.linear.bias
 
 
 def mlp_policy(obs_size, action_size, hidden=64, dtype=torch.bfloat16, device='cuda', seed=0):

@@ -61,6 +61,13 @@ enum { COPTER_LANDER3D = 0, COPTER_LANDER2D = 1, COPTER_LANDER1D = 2,
 
 enum { COPTER_E_ARG = -1, COPTER_E_VARIANT = -2, COPTER_E_ALIGN = -3, COPTER_E_RANGE = -4 };
 
+/* bits of CopterBuffers.cause: what ended the episode (several can hold at once).  LANDED = the
+   stale status was LANDED (envs/lander.py:64-66), BONUS = inside the target radius (:69-72), OOB /
+   ANGLE = envs/task.py:111,116, CRASHED = :121, TIMEOUT = the env's own step limit (:128), which is
+   what gymnasium's TimeLimit(max_episode_steps=1000) reports as `truncated`. */
+enum { COPTER_CAUSE_LANDED = 1, COPTER_CAUSE_BONUS = 2, COPTER_CAUSE_OOB = 4, COPTER_CAUSE_ANGLE = 8,
+       COPTER_CAUSE_CRASHED = 16, COPTER_CAUSE_TIMEOUT = 32 };
+
 /* flags for copter_step_* */
 enum { COPTER_F_AUTO_RESET = 1 };
 
@@ -107,6 +114,8 @@ typedef struct CopterBuffers {
     void*       ep_return;   /* T[n]   nullable: running episode return, feeds COPTER_STAT_RETURN_SUM */
     double*     stats;       /* [COPTER_STATS_SLOTS][COPTER_STATS_LEN] nullable */
     float*      final_obs;   /* [n][O] nullable: observation of the terminal state of envs that finished */
+    uint8_t*    cause;       /* [n] nullable (step only): why the env finished in this launch, bit set of
+                                COPTER_CAUSE_*; 0 when it did not finish */
     int64_t     state_stride;/* vectors per state plane in the allocation; 0 means n. Lets a call step a
                                 sub-range [lo, lo+n) of a larger shard: pass state + lo vectors, stride = shard size */
 } CopterBuffers;

@@ -155,3 +155,48 @@ def test_csv_export_matches_lander_py_format(pkg, tmp_path):
     first = lines[1].split(',')
     assert first[0] == '0.000000' and first[1] == '0.016250' and lines[2].split(',')[0] == '0.010000'
     assert abs(float(first[9]) - (-10.0)) < 1e-6
+
+
+def test_cause_and_timelimit_truncation(pkg):
+    """`truncated` mirrors gymnasium's TimeLimit(max_episode_steps): set exactly on the step on
+    which the env's own step limit fires (both fire on the same user step)."""
+    from gym_copter_b200._lib import CAUSE_TIMEOUT, CAUSE_OOB, CAUSE_ANGLE, CAUSE_CRASHED
+    n = 600
+    env = pkg.CopterVecEnv('Hover3D', n, dtype=torch.float64, seed=1, report_cause=True, max_steps=40)
+    orc = EnvBatch('Hover3D', n, seed=1, params=__import__('oracle.copter_oracle', fromlist=['OracleParams']).OracleParams(max_steps=40))
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(0)
+    seen = 0
+    for t in range(100):
+        a = (0.01656 * (1 + 0.3 * rng.uniform(-1, 1, (n, 4)))).astype(np.float32)
+        obs, r, term, trunc, info = env.step(a)
+        o_obs, o_r, o_done, o_info = orc.step(a.astype(np.float64))
+        assert np.array_equal(info['cause'].cpu().numpy(), o_info['cause'].astype(np.uint8))
+        assert np.array_equal(trunc.cpu().numpy(), (o_info['cause'] & CAUSE_TIMEOUT) != 0)
+        assert not (trunc & ~term).any()
+        seen |= int(np.bitwise_or.reduce(o_info['cause']))
+    assert seen & CAUSE_TIMEOUT and seen & (CAUSE_OOB | CAUSE_ANGLE | CAUSE_CRASHED)
+
+
+def test_zero_copy_observation_mode(pkg):
+    """write_obs=False changes nothing but the skipped observation write; a policy whose first
+    layer reads the state planes in place computes the same actions as one reading obs."""
+    n = 5000
+    a_env = pkg.CopterVecEnv('Lander3D', n, seed=9)
+    b_env = pkg.CopterVecEnv('Lander3D', n, seed=9, write_obs=False)
+    a_env.reset(); b_env.reset()
+    lin = torch.nn.Linear(10, 64).cuda()
+    planar = pkg.PlanarLinear(lin, 10)
+    g = torch.Generator(device='cuda').manual_seed(0)
+    for t in range(25):
+        act = 1.625e-2 * torch.randn((n, 4), device='cuda', generator=g)
+        obs, r1, d1, _, _ = a_env.step(act)
+        none, r2, d2, _, _ = b_env.step(act)
+        assert none is None and torch.equal(r1, r2) and torch.equal(d1, d2)
+        assert torch.equal(a_env.state, b_env.state)
+        with torch.no_grad():
+            y1, y2 = lin(obs), planar(b_env.planar_obs())
+        assert torch.allclose(y1, y2, rtol=1e-5, atol=1e-5)
+    ro = pkg.PolicyRollout(b_env, lambda planes: 0.0166 * (1 + 0.1 * torch.tanh(planar(planes)[:, :4])), 4, planar=True)
+    r, d, _ = ro.run()
+    assert r.shape == (4, n)

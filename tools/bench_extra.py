@@ -93,6 +93,26 @@ def policy():
         torch.cuda.empty_cache()
 
 
+def zerocopy():
+    n = 1 << 24
+    acts = [1.625e-2 * torch.randn((n, 4), device='cuda') for _ in range(4)]
+    for write_obs in (True, False):
+        env = g.LanderVec(n, seed=5, write_obs=write_obs)
+        env.reset()
+        it = [0]
+
+        def one():
+            env.step(acts[it[0] % 4]); it[0] += 1
+        for _ in range(20):
+            one()
+        ms = min(timed(one, 200) for _ in range(3))
+        b = 165 if write_obs else 125
+        print(json.dumps({'bench': 'Lander3D 2^24 envs fp32 K=1 write_obs=%s' % write_obs, 'ms_per_step': ms,
+                          'steps_per_s': n / ms * 1e3, 'bytes_per_env': b, 'gbs': b * n / ms / 1e6}), flush=True)
+        del env
+        torch.cuda.empty_cache()
+
+
 def fp64():
     n = 1 << 22
     env = g.Hover3DVec(n, dtype=torch.float64, seed=4)
@@ -105,6 +125,6 @@ def fp64():
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['config2', 'rollout', 'policy', 'fp64']
+    which = sys.argv[1:] or ['config2', 'rollout', 'policy', 'fp64', 'zerocopy']
     for w in which:
         globals()[w]()
