@@ -168,7 +168,9 @@ def test_cause_and_timelimit_truncation(pkg):
     rng = np.random.default_rng(0)
     seen = 0
     for t in range(100):
-        a = (0.01656 * (1 + 0.3 * rng.uniform(-1, 1, (n, 4)))).astype(np.float32)
+        a = 0.01656 * (1 + 0.02 * rng.uniform(-1, 1, (n, 4)))           # calm half: runs into the step limit
+        a[1::2, 1:3] *= 4.0                                              # other half: rolls over (task.py:116)
+        a = a.astype(np.float32)
         obs, r, term, trunc, info = env.step(a)
         o_obs, o_r, o_done, o_info = orc.step(a.astype(np.float64))
         assert np.array_equal(info['cause'].cpu().numpy(), o_info['cause'].astype(np.uint8))
