@@ -41,7 +41,13 @@ class CopterActionSource(C.Structure):
     _fields_ = [('kind', C.c_int32), ('reserved', C.c_int32), ('scale', C.c_double), ('offset', C.c_double)]
 
 
-SOURCE_KINDS = {'const': 0, 'randn': 1, 'uniform': 2}
+class CopterPidGains(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ('rate_kp', 'rate_ki', 'rate_kd', 'rate_windup', 'rate_big',
+                                          'pos_kp', 'pos_ki', 'pos_kd', 'pos_windup', 'pos_target',
+                                          'descent_kp', 'descent_kd')]
+
+
+SOURCE_KINDS = {'const': 0, 'randn': 1, 'uniform': 2, 'pid': 3}
 
 
 class CopterError(RuntimeError):
@@ -91,7 +97,9 @@ def load():
     for f in (lib.copter_reset_force_f32, lib.copter_reset_force_f64):
         f.argtypes, f.restype = [P, vp, vp, i64, i64, u64, vp], i32
     for f in (lib.copter_rollout_f32, lib.copter_rollout_f64):
-        f.argtypes, f.restype = [P, B, C.POINTER(CopterActionSource), i64, i64, u64, i64, i32, i32, i32, vp, vp, vp, vp], i32
+        f.argtypes, f.restype = [P, B, C.POINTER(CopterActionSource), i64, i64, u64, i64, i32, i32, i32, vp, vp, vp,
+                                 C.POINTER(CopterPidGains), vp, vp], i32
+    lib.copter_default_pid_gains.argtypes, lib.copter_default_pid_gains.restype = [C.POINTER(CopterPidGains)], None
     lib.copter_pipeline_create.argtypes, lib.copter_pipeline_create.restype = [i32, C.POINTER(vp)], i32
     lib.copter_pipeline_destroy.argtypes, lib.copter_pipeline_destroy.restype = [vp], i32
     for f in (lib.copter_step_host_f32, lib.copter_step_host_f64):
@@ -109,6 +117,16 @@ def check(code, what):
     if code < 0:
         raise CopterError('%s: %s' % (what, _ARG_ERRORS.get(code, 'error %d' % code)))
     raise CopterError('%s: CUDA error %d' % (what, code))
+
+
+def default_pid_gains(**overrides):
+    g = CopterPidGains()
+    load().copter_default_pid_gains(C.byref(g))
+    for k, v in overrides.items():
+        if not hasattr(g, k):
+            raise TypeError('unknown PID gain %r' % k)
+        setattr(g, k, float(v))
+    return g
 
 
 def default_params(**overrides):

@@ -607,6 +607,8 @@ struct RolloutArgs {
     T* reward_tn; uint8_t* done_tn; T* action_tn;
     int64_t n, stride, env_offset, first_step; uint64_t seed;
     int n_steps, auto_reset, src_kind; T src_scale, src_offset;
+    T* controller;              // [n][16] PID memories (COPTER_SRC_PID)
+    T rate_kp, rate_ki, rate_kd, rate_windup, rate_big, pos_kp, pos_ki, pos_kd, pos_windup, pos_target, descent_kp, descent_kd;
 };
 
 __device__ __forceinline__ float  log_t(float a)  { return logf(a); }
@@ -639,8 +641,64 @@ __device__ __forceinline__ void draw_action(const RolloutArgs<T>& a, uint64_t en
     for (int j = 0; j < A; ++j) act[j] = a.src_offset + a.src_scale * xi[j];
 }
 
-template <typename T, int VARIANT, bool STATS>
-__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? COPTER_F32_CTAS_PER_SM : 2)
+
+// ------------------------------------------------------------------------------------------
+// The reference's PID heuristic as an on-device action source (COPTER_SRC_PID).  Restates
+// attic/mars/pidcontrollers/__init__.py:12-146 (controllers) and attic/mars/lander3d.py:64-87
+// (the Lander3D heuristic and its quad-X mixer).  Each controller's memory is
+// (errorI, lastError, deltaError1, deltaError2).
+// ------------------------------------------------------------------------------------------
+template <typename T> struct PidMem { T errI, last, d1, d2; };
+
+// _PidController.compute (pidcontrollers/__init__.py:32-59)
+template <typename T>
+__device__ __forceinline__ T pid_compute(T kp, T ki, T kd, T windup, T target, T actual, PidMem<T>& m) {
+    const T error = target - actual;
+    T out = error * kp;
+    if (ki > (T)0) {
+        m.errI = fmin(fmax(m.errI + error, -windup), windup);       // constrainAbs (:61-67)
+        out += m.errI * ki;
+    }
+    if (kd > (T)0) {
+        const T de = error - m.last;
+        out += (m.d1 + m.d2 + de) * kd;
+        m.d2 = m.d1; m.d1 = de; m.last = error;
+    }
+    return out;
+}
+
+// AngularVelocityPidController.getDemand (:131-146): integral reset on a fast rotation
+template <typename T>
+__device__ __forceinline__ T rate_demand(const RolloutArgs<T>& a, T rate, PidMem<T>& m) {
+    if (abs_t(rate) > a.rate_big) { m.errI = (T)0; m.last = (T)0; }                      // reset() (:61-65)
+    return pid_compute<T>(a.rate_kp, a.rate_ki, a.rate_kd, a.rate_windup, (T)0, rate, m);
+}
+
+// _SetPointPidController.getDemand (:70-88): position error -> velocity set-point -> demand
+template <typename T>
+__device__ __forceinline__ T poshold_demand(const RolloutArgs<T>& a, T x, T dx, PidMem<T>& m) {
+    const T target_velocity = (a.pos_target - x) * (T)1;                                   // posPid(1, 0, 0)
+    return pid_compute<T>(a.pos_kp, a.pos_ki, a.pos_kd, a.pos_windup, target_velocity, dx, m);
+}
+
+// Lander3D.heuristic (attic/mars/lander3d.py:64-87) on the float32 observation the caller of
+// the reference would hold; `mem` = (phi_rate, theta_rate, x_poshold [fed y], y_poshold [fed x]).
+template <typename T>
+__device__ __forceinline__ void pid_heuristic(const RolloutArgs<T>& a, const T (&s)[12], PidMem<T> (&mem)[4], T (&act)[4]) {
+    T o[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) o[j] = (T)(float)s[j];
+    const T phi_todo = rate_demand<T>(a, o[7], mem[0]) + poshold_demand<T>(a, o[2], o[3], mem[2]);
+    const T theta_todo = rate_demand<T>(a, -o[9], mem[1]) + poshold_demand<T>(a, o[0], o[1], mem[3]);
+    const T descent_todo = o[4] * a.descent_kp + o[5] * a.descent_kd;                      // DescentPidController (:110-121)
+    const T t = (descent_todo + (T)1) / (T)2, r = phi_todo, p = theta_todo;
+    const T mix[4] = {t - r - p, t + r + p, t + r - p, t - r + p};                         // lander3d.py:87
+#pragma unroll
+    for (int j = 0; j < 4; ++j) act[j] = a.src_offset + a.src_scale * mix[j];
+}
+
+template <typename T, int VARIANT, bool STATS, bool PID>
+__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (PID ? 6 : COPTER_F32_CTAS_PER_SM) : 2)
 copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant__ RolloutArgs<T> a) {
     constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A;
     __shared__ __align__(16) float tiles[kWarpsPerBlock][32 * O];
@@ -664,11 +722,19 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
             for (int j = 0; j < 12; ++j) s[j] = (T)0;
         }
         Shaping<T> pre_sh = lander_shaping<T>(kp, s);
+        PidMem<T> mem[4];
+        if constexpr (PID) {
+            if (valid) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { const T* q = a.controller + i * 16 + 4 * c; mem[c].errI = q[0]; mem[c].last = q[1]; mem[c].d1 = q[2]; mem[c].d2 = q[3]; }
+            }
+        }
         for (int t = 0; t < a.n_steps; ++t) {
             bool dn = false; int cause = 0, ep_len = 0; T ep_ret = (T)0;
             if (valid) {
                 T act[A], m[4];
-                draw_action<T, A>(a, (uint64_t)(a.env_offset + i), (uint64_t)(a.first_step + t), act);
+                if constexpr (PID && A == 4) pid_heuristic<T>(a, s, mem, act);
+                else draw_action<T, A>(a, (uint64_t)(a.env_offset + i), (uint64_t)(a.first_step + t), act);
                 if (a.action_tn) {
 #pragma unroll
                     for (int j = 0; j < A; ++j) a.action_tn[((int64_t)t * a.n + i) * A + j] = act[j];
@@ -711,6 +777,10 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
             if (a.reward_sum) a.reward_sum[i] = total;
             if (a.done_any) a.done_any[i] = done_any ? 1 : 0;
             if (STATS && a.ep_return) a.ep_return[i] = ret;
+            if constexpr (PID) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { T* q = a.controller + i * 16 + 4 * c; q[0] = mem[c].errI; q[1] = mem[c].last; q[2] = mem[c].d1; q[3] = mem[c].d2; }
+            }
         }
         if (a.obs) write_obs_rows<VARIANT, T>(a.obs, tiles[warp], lane, row0, rows, s);
     }
@@ -853,20 +923,31 @@ int launch_step(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_
 
 template <typename T, int VARIANT>
 int launch_rollout_v(const KParams<T>& kp, const RolloutArgs<T>& a, cudaStream_t s) {
-    if (a.stats) copter_rollout_kernel<T, VARIANT, true><<<grid_for<copter_rollout_kernel<T, VARIANT, true>>(a.n), kBlock, 0, s>>>(kp, a);
-    else         copter_rollout_kernel<T, VARIANT, false><<<grid_for<copter_rollout_kernel<T, VARIANT, false>>(a.n), kBlock, 0, s>>>(kp, a);
+    if (a.src_kind == COPTER_SRC_PID) {
+        if constexpr (Variant<VARIANT>::A == 4) {
+            if (a.stats) copter_rollout_kernel<T, VARIANT, true, true><<<grid_for<copter_rollout_kernel<T, VARIANT, true, true>>(a.n), kBlock, 0, s>>>(kp, a);
+            else         copter_rollout_kernel<T, VARIANT, false, true><<<grid_for<copter_rollout_kernel<T, VARIANT, false, true>>(a.n), kBlock, 0, s>>>(kp, a);
+        } else {
+            return COPTER_E_VARIANT;          // the heuristic is defined for the four-motor envs only
+        }
+    } else {
+        if (a.stats) copter_rollout_kernel<T, VARIANT, true, false><<<grid_for<copter_rollout_kernel<T, VARIANT, true, false>>(a.n), kBlock, 0, s>>>(kp, a);
+        else         copter_rollout_kernel<T, VARIANT, false, false><<<grid_for<copter_rollout_kernel<T, VARIANT, false, false>>(a.n), kBlock, 0, s>>>(kp, a);
+    }
     return (int)cudaGetLastError();
 }
 
 template <typename T>
 int launch_rollout(const CopterParams* p, const CopterBuffers* b, const CopterActionSource* src, int64_t n,
                    int64_t env_offset, uint64_t seed, int64_t first_step, int n_steps, int variant, int flags,
-                   void* reward_tn, uint8_t* done_tn, void* action_tn, void* stream) {
+                   void* reward_tn, uint8_t* done_tn, void* action_tn, const CopterPidGains* gains, void* controller,
+                   void* stream) {
     int e = check_params(p);
     if (e) return e;
     if (!b || !b->state || !b->meta || !src) return COPTER_E_ARG;
+    if (src->kind == COPTER_SRC_PID && (!controller || !aligned16(controller))) return COPTER_E_ARG;
     if (n < 0 || env_offset < 0 || n_steps < 1 || first_step < 0 || (b->state_stride > 0 && b->state_stride < n)) return COPTER_E_RANGE;
-    if (src->kind < COPTER_SRC_CONST || src->kind > COPTER_SRC_UNIFORM) return COPTER_E_RANGE;
+    if (src->kind < COPTER_SRC_CONST || src->kind > COPTER_SRC_PID) return COPTER_E_RANGE;
     if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
     if (!aligned16(b->state) || (b->obs && !aligned16(b->obs))) return COPTER_E_ALIGN;
     if (n == 0) return 0;
@@ -878,6 +959,12 @@ int launch_rollout(const CopterParams* p, const CopterBuffers* b, const CopterAc
     a.n = n; a.stride = b->state_stride > 0 ? b->state_stride : n; a.env_offset = env_offset; a.first_step = first_step;
     a.seed = seed; a.n_steps = n_steps; a.auto_reset = (flags & COPTER_F_AUTO_RESET) ? 1 : 0;
     a.src_kind = src->kind; a.src_scale = (T)src->scale; a.src_offset = (T)src->offset;
+    CopterPidGains g;
+    if (gains) g = *gains; else copter_default_pid_gains(&g);
+    a.controller = (T*)controller;
+    a.rate_kp = (T)g.rate_kp; a.rate_ki = (T)g.rate_ki; a.rate_kd = (T)g.rate_kd; a.rate_windup = (T)g.rate_windup; a.rate_big = (T)g.rate_big;
+    a.pos_kp = (T)g.pos_kp; a.pos_ki = (T)g.pos_ki; a.pos_kd = (T)g.pos_kd; a.pos_windup = (T)g.pos_windup; a.pos_target = (T)g.pos_target;
+    a.descent_kp = (T)g.descent_kp; a.descent_kd = (T)g.descent_kd;
     cudaStream_t s = (cudaStream_t)stream;
     switch (variant) {
         case COPTER_LANDER3D: return launch_rollout_v<T, COPTER_LANDER3D>(kp, a, s);
@@ -1041,12 +1128,22 @@ int copter_step_f64(const CopterParams* p, const CopterBuffers* b, int64_t n, in
 }
 
 int copter_rollout_f32(const CopterParams* p, const CopterBuffers* b, const CopterActionSource* src, int64_t n, int64_t env_offset, uint64_t seed,
-                       int64_t first_step, int n_steps, int variant, int flags, float* reward_tn, uint8_t* done_tn, float* action_tn, void* stream) {
-    return launch_rollout<float>(p, b, src, n, env_offset, seed, first_step, n_steps, variant, flags, reward_tn, done_tn, action_tn, stream);
+                       int64_t first_step, int n_steps, int variant, int flags, float* reward_tn, uint8_t* done_tn, float* action_tn,
+                       const CopterPidGains* gains, float* controller, void* stream) {
+    return launch_rollout<float>(p, b, src, n, env_offset, seed, first_step, n_steps, variant, flags, reward_tn, done_tn, action_tn, gains, controller, stream);
 }
 int copter_rollout_f64(const CopterParams* p, const CopterBuffers* b, const CopterActionSource* src, int64_t n, int64_t env_offset, uint64_t seed,
-                       int64_t first_step, int n_steps, int variant, int flags, double* reward_tn, uint8_t* done_tn, double* action_tn, void* stream) {
-    return launch_rollout<double>(p, b, src, n, env_offset, seed, first_step, n_steps, variant, flags, reward_tn, done_tn, action_tn, stream);
+                       int64_t first_step, int n_steps, int variant, int flags, double* reward_tn, uint8_t* done_tn, double* action_tn,
+                       const CopterPidGains* gains, double* controller, void* stream) {
+    return launch_rollout<double>(p, b, src, n, env_offset, seed, first_step, n_steps, variant, flags, reward_tn, done_tn, action_tn, gains, controller, stream);
+}
+
+void copter_default_pid_gains(CopterPidGains* g) {
+    if (!g) return;
+    g->rate_kp = 1.0; g->rate_ki = 0.0; g->rate_kd = 1.0; g->rate_windup = 6.0;          // AngularVelocityPidController (:126-135)
+    g->rate_big = 40.0 * M_PI / 180.0;                                                    // BIG_DEGREES_PER_SECOND
+    g->pos_kp = 0.00001; g->pos_ki = 0.1; g->pos_kd = 4.0; g->pos_windup = 0.2; g->pos_target = 0.0;   // PositionHoldPidController (:102-107)
+    g->descent_kp = 1.15; g->descent_kd = 1.33;                                           // DescentPidController (:110-121)
 }
 
 int copter_dynamics_f32(const CopterParams* p, void* state, uint8_t* status, int32_t* ticks, void* perturb, const void* motors, int64_t n, void* stream) {

@@ -139,6 +139,7 @@ class CopterVecEnv:
         self._pipeline = None
         self._host = None
         self.rollout_step = 0       # global step index of the on-device action streams
+        self.controller = None      # [N,16] PID memories, allocated by rollout(source='pid')
 
     # ---- plumbing -----------------------------------------------------------------------
 
@@ -197,6 +198,8 @@ class CopterVecEnv:
                           self._stream()), 'copter_reset')
         self.launches += 1
         self._is_reset = True
+        if self.controller is not None:
+            self.controller.zero_()
         return self.obs, {}
 
     def step(self, action, reward_out=None, done_out=None):
@@ -236,7 +239,7 @@ class CopterVecEnv:
     # ---- fused multi-step rollout with on-device action sources -----------------------
 
     def rollout(self, n_steps, source='const', scale=None, offset=None, record_rewards=False,
-                record_dones=False, record_actions=False):
+                record_dones=False, record_actions=False, pid_gains=None):
         """
         `n_steps` env steps in ONE kernel launch, the commands generated on the device:
           source='const'    action = offset                 (default offset 1.625e-2: the
@@ -244,6 +247,9 @@ class CopterVecEnv:
           source='randn'    action = offset + scale*N(0,1)  (default scale 1.625e-2, offset 0:
                                                              `lander.py --random`)
           source='uniform'  action = offset + scale*U(-1,1) (default scale 1: the action space)
+          source='pid'      action = offset + scale*mixer(PID heuristic of attic/mars/lander3d.py:64-87
+                            on the previous observation); `pid_gains` = dict of CopterPidGains
+                            overrides; controller memories live in `self.controller` [N,16]
         Step for step identical to `n_steps` calls of step() with k_substeps=1 on the same
         commands.  Returns a dict: 'obs' (after the last step), 'reward_sum' [N], 'done_any'
         [N] bool, plus 'rewards' [T,N], 'dones' [T,N] bool, 'actions' [T,N,A] when recorded.
@@ -252,7 +258,15 @@ class CopterVecEnv:
             raise CopterError('rollout() called before reset()')
         if source not in SOURCE_KINDS:
             raise ValueError('source must be one of %s' % sorted(SOURCE_KINDS))
-        d_scale, d_off = {'const': (0.0, 1.625e-2), 'randn': (1.625e-2, 0.0), 'uniform': (1.0, 0.0)}[source]
+        d_scale, d_off = {'const': (0.0, 1.625e-2), 'randn': (1.625e-2, 0.0), 'uniform': (1.0, 0.0),
+                          'pid': (1.0, 0.0)}[source]
+        gains = None
+        if source == 'pid':
+            if self.action_size != 4:
+                raise CopterError('the PID heuristic drives the four-motor variants only')
+            if self.controller is None:
+                self.controller = torch.zeros((self.num_envs, 16), dtype=self.dtype, device=self.device)
+            gains = _lib.default_pid_gains(**(pid_gains or {}))
         src = CopterActionSource(SOURCE_KINDS[source], 0, d_scale if scale is None else float(scale),
                                  d_off if offset is None else float(offset))
         n, T = self.num_envs, int(n_steps)
@@ -268,7 +282,10 @@ class CopterVecEnv:
                           VARIANT_IDS[self.variant], _lib.F_AUTO_RESET if self.auto_reset else 0,
                           rew.data_ptr() if rew is not None else None,
                           dn.data_ptr() if dn is not None else None,
-                          act.data_ptr() if act is not None else None, self._stream()), 'copter_rollout')
+                          act.data_ptr() if act is not None else None,
+                          C.byref(gains) if gains is not None else None,
+                          self.controller.data_ptr() if self.controller is not None else None,
+                          self._stream()), 'copter_rollout')
         self.launches += 1
         self.rollout_step += T
         out.update(obs=self.obs, reward_sum=self.reward, done_any=self.done.view(torch.bool))

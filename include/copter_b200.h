@@ -155,15 +155,35 @@ int copter_step_f64(const CopterParams* p, const CopterBuffers* b, int64_t n, in
  * Optional per-step outputs: reward_tn T[n_steps][n], done_tn uint8[n_steps][n] (GAE-ready
  * layout), action_tn T[n_steps][n][A] (the commands used, before clipping).
  */
-enum { COPTER_SRC_CONST = 0, COPTER_SRC_RANDN = 1, COPTER_SRC_UNIFORM = 2 };
+enum { COPTER_SRC_CONST = 0, COPTER_SRC_RANDN = 1, COPTER_SRC_UNIFORM = 2, COPTER_SRC_PID = 3 };
 typedef struct CopterActionSource { int32_t kind; int32_t reserved; double scale; double offset; } CopterActionSource;
+
+/*
+ * COPTER_SRC_PID: the reference's PID landing heuristic evaluated on the device -- attic/mars/
+ * lander3d.py:64-87 (roll/pitch rate PIDs + position-hold PIDs + descent PD, quad-X mixer
+ * [t-r-p, t+r+p, t+r-p, t-r+p]) over attic/mars/pidcontrollers/__init__.py:12-146 -- fed, like
+ * the reference's caller loop (attic/mars/task.py:134-160), with the float32 observation of the
+ * previous step; action_j = offset + scale * mixer_j.  Four-motor variants only.  `controller`
+ * T[n][16] holds the four controllers' memories (errorI, lastError, deltaError1, deltaError2 for
+ * phi-rate, theta-rate, x_poshold, y_poshold); it persists across episodes exactly as the
+ * reference's controller objects do (they live in the env, not in an episode); zero it to start.
+ * `gains` NULL selects the reference's constants (copter_default_pid_gains).
+ */
+typedef struct CopterPidGains {
+    double rate_kp, rate_ki, rate_kd, rate_windup, rate_big;      /* AngularVelocityPidController */
+    double pos_kp, pos_ki, pos_kd, pos_windup, pos_target;        /* PositionHoldPidController */
+    double descent_kp, descent_kd;                                /* DescentPidController */
+} CopterPidGains;
+void copter_default_pid_gains(CopterPidGains* g);
 
 int copter_rollout_f32(const CopterParams* p, const CopterBuffers* b, const CopterActionSource* src,
                        int64_t n, int64_t env_offset, uint64_t seed, int64_t first_step, int n_steps,
-                       int variant, int flags, float* reward_tn, uint8_t* done_tn, float* action_tn, void* stream);
+                       int variant, int flags, float* reward_tn, uint8_t* done_tn, float* action_tn,
+                       const CopterPidGains* gains_or_null, float* controller_or_null, void* stream);
 int copter_rollout_f64(const CopterParams* p, const CopterBuffers* b, const CopterActionSource* src,
                        int64_t n, int64_t env_offset, uint64_t seed, int64_t first_step, int n_steps,
-                       int variant, int flags, double* reward_tn, uint8_t* done_tn, double* action_tn, void* stream);
+                       int variant, int flags, double* reward_tn, uint8_t* done_tn, double* action_tn,
+                       const CopterPidGains* gains_or_null, double* controller_or_null, void* stream);
 
 /*
  * Batched Dynamics.setMotors: state T[12/V][n][V], status uint8[n], ticks int32[n],

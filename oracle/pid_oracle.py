@@ -1,0 +1,64 @@
+"""
+TEST INFRASTRUCTURE ONLY -- numpy restatement, batched over envs, of the reference's PID
+landing heuristic: attic/mars/pidcontrollers/__init__.py:12-146 (controllers) and
+attic/mars/lander3d.py:64-87 (Lander3D.heuristic + quad-X mixer).  Pinned by executing the
+reference's controller classes themselves (the module is numpy-only and loads by file path)
+in tests/test_pid_oracle.py.
+"""
+import numpy as np
+
+
+class PidBatch:
+    """N copies of _PidController (pidcontrollers/__init__.py:12-67)."""
+
+    def __init__(self, n, kp, ki, kd, windup=0.2, dtype=np.float64):
+        self.kp, self.ki, self.kd, self.windup = kp, ki, kd, windup
+        self.err_i, self.last, self.d1, self.d2 = (np.zeros(n, dtype) for _ in range(4))
+
+    def compute(self, target, actual):
+        error = target - actual
+        out = error * self.kp
+        if self.ki > 0:
+            self.err_i = np.clip(self.err_i + error, -self.windup, self.windup)
+            out = out + self.err_i * self.ki
+        if self.kd > 0:
+            de = error - self.last
+            out = out + (self.d1 + self.d2 + de) * self.kd
+            self.d2, self.d1, self.last = self.d1, de, error
+        return out
+
+    def reset_where(self, w):
+        self.err_i = np.where(w, 0, self.err_i)
+        self.last = np.where(w, 0, self.last)
+
+
+class LanderHeuristicBatch:
+    """Lander3D.heuristic (attic/mars/lander3d.py:34-38, 64-87) for N envs."""
+
+    def __init__(self, n, dtype=np.float64, scale=1.0, offset=0.0, descent_kp=1.15, descent_kd=1.33):
+        T = np.dtype(dtype).type
+        self.T, self.scale, self.offset = T, T(scale), T(offset)
+        self.descent_kp, self.descent_kd = T(descent_kp), T(descent_kd)          # DescentPidController (:110-121)
+        self.phi_rate = PidBatch(n, T(1.0), T(0), T(1.0), T(6), dtype)          # AngularVelocityPidController (:124-135)
+        self.theta_rate = PidBatch(n, T(1.0), T(0), T(1.0), T(6), dtype)
+        self.x_poshold = PidBatch(n, T(0.00001), T(0.1), T(4.0), T(0.2), dtype)  # PositionHoldPidController (:102-107)
+        self.y_poshold = PidBatch(n, T(0.00001), T(0.1), T(4.0), T(0.2), dtype)
+        self.big = T(np.radians(40))
+
+    def _rate(self, pid, rate):
+        pid.reset_where(np.abs(rate) > self.big)                                  # :141-143
+        return pid.compute(self.T(0), rate)
+
+    def _poshold(self, pid, x, dx):
+        return pid.compute((self.T(0) - x) * self.T(1), dx)                       # :80-88 with posPid(1,0,0)
+
+    def act(self, obs):
+        """obs: [N,10] float32 observation of the previous step. Returns motors [N,4]."""
+        T = self.T
+        o = obs.astype(np.float32).astype(self.phi_rate.err_i.dtype)
+        phi_todo = self._rate(self.phi_rate, o[:, 7]) + self._poshold(self.x_poshold, o[:, 2], o[:, 3])
+        theta_todo = self._rate(self.theta_rate, -o[:, 9]) + self._poshold(self.y_poshold, o[:, 0], o[:, 1])
+        descent_todo = o[:, 4] * self.descent_kp + o[:, 5] * self.descent_kd
+        t, r, p = (descent_todo + T(1)) / T(2), phi_todo, theta_todo
+        mix = np.stack([t - r - p, t + r + p, t + r - p, t - r + p], -1)          # lander3d.py:87
+        return self.offset + self.scale * mix
