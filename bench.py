@@ -211,8 +211,9 @@ def main():
 
     dtype = torch.float32 if args.dtype == 'f32' else torch.float64
     n, k = args.envs_per_gpu, args.k_substeps
+    # headline env: exactly the 165 B/env/launch of SURVEY.md 8(d), no statistics side channel
     env = g.CopterVecEnv(args.variant, n, dtype=dtype, seed=2026, env_offset=rank * n,
-                         k_substeps=k, auto_reset=True, track_stats=True)
+                         k_substeps=k, auto_reset=True, track_stats=False)
     A, O, w = env.action_size, env.obs_size, (4 if dtype == torch.float32 else 8)
     actions = make_actions(torch, args.stream, n, A, args.pool, dtype, dev, 1234 + rank)
     env.reset()
@@ -223,7 +224,6 @@ def main():
 
     # ---- device-resident measurement ------------------------------------------------------
     run(env, args.warmup)
-    env.clear_stats()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = env.launches
     barrier()
@@ -235,7 +235,21 @@ def main():
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = env.launches - launches0
     value = world * n * k * args.steps / (ms * 1e-3)
-    stats = env.stats(reduce_group=True if world > 1 else None)    # the one (optional) collective
+    # episode bookkeeping of the same workload, from a statistics-enabled twin of the env (also
+    # used for the fused-substep side measurements); its all-reduce is the one optional collective
+    senv = g.CopterVecEnv(args.variant, n, dtype=dtype, seed=2026, env_offset=rank * n,
+                          k_substeps=k, auto_reset=True, track_stats=True)
+    senv.reset()
+    run(senv, args.warmup)
+    senv.clear_stats()
+    sv0, sv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_stat = min(args.steps, 200)
+    sv0.record()
+    run(senv, n_stat)
+    sv1.record()
+    barrier()
+    ms_with_stats = max_over_ranks(sv0.elapsed_time(sv1)) / n_stat
+    stats = senv.stats(reduce_group=True if world > 1 else None)
 
     peaks = {}
     try:
@@ -256,7 +270,7 @@ def main():
         pass
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': traffic, 'algorithmic_bytes_per_launch': b_launch * n, 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6650',
-                'kernel': 'copter_step_kernel<%s,%s,stats>' % (args.dtype, args.variant),
+                'kernel': 'copter_step_kernel<%s,%s>' % (args.dtype, args.variant),
                 'bytes_per_env_per_launch': b_launch, 'env_steps_per_launch': n * k}
 
     # ---- this box's own copy bandwidth, measured like MEASURED_PEAKS.json's hbm_gbs --------
@@ -290,22 +304,24 @@ def main():
     extras = {}
     if not args.no_extras and k == 1:
         for kk in (4, 16):
-            env.k_substeps = kk
-            run(env, 3)
+            senv.k_substeps = kk
+            run(senv, 3)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             steps_kk = max(10, args.steps // 4)
-            before = env.stats()['env_steps']
+            before = senv.stats()['env_steps']
             e0.record()
-            run(env, steps_kk)
+            run(senv, steps_kk)
             e1.record()
             barrier()
             ms_kk = max_over_ranks(e0.elapsed_time(e1))
-            done_steps = env.stats()['env_steps'] - before          # idle substeps are not counted
+            done_steps = senv.stats()['env_steps'] - before         # idle substeps are not counted
             extras['k%d' % kk] = {'value': world * done_steps / (ms_kk * 1e-3), 'unit': UNIT,
                                   'ms_per_launch': ms_kk / steps_kk,
                                   'note': 'executed env-steps only (envs idle after done within a launch)'}
-        env.k_substeps = 1
+        senv.k_substeps = 1
+    del senv
+    torch.cuda.empty_cache()
 
     # ---- end to end through the host-array API -------------------------------------------
     h = env.host_buffers()
@@ -354,7 +370,8 @@ def main():
                        'parallelism': 'env shards, one per GPU, no per-step communication'},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches,
             'clocks': clk.summary(),
-            'episodes': {kk: stats[kk] for kk in ('episodes', 'mean_length', 'landed', 'crashed', 'oob', 'angle', 'timeout')},
+            'episodes': dict({kk: stats[kk] for kk in ('episodes', 'mean_length', 'landed', 'crashed', 'oob', 'angle', 'timeout')},
+                             ms_per_step_with_statistics=ms_with_stats),
             'fused_substeps': extras,
         }
         print(json.dumps(line))

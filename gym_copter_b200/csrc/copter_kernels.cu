@@ -45,6 +45,9 @@ namespace {
 #ifndef COPTER_PERSISTENT
 #define COPTER_PERSISTENT 0     // 1 (A/B knob): one resident wave of CTAs walking the tiles with a grid stride
 #endif
+#ifndef COPTER_K1_SPECIALIZE
+#define COPTER_K1_SPECIALIZE 1   // dedicated code path for k_substeps == 1 (the HBM-bound case)
+#endif
 #ifndef COPTER_STREAMING
 #define COPTER_STREAMING 0      // 1: evict-first (ld/st .cs) hints on the state planes
 #endif
@@ -490,20 +493,104 @@ __device__ __forceinline__ void debit_idle_steps(double* stats, int lane, int id
 // kernels
 // ------------------------------------------------------------------------------------------
 
+// One tile (this thread's env `i`, already loaded as `cur`) through K substeps and out to HBM.
+// SINGLE = the K == 1 specialisation: no substep loop, no idle bookkeeping (about 40 fewer
+// instructions per env-step on the HBM-bound path).
+template <typename T, int VARIANT, bool STATS, bool SINGLE, bool PRELOADED>
+__device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T>& a,
+                                          const RawEnv<T, Variant<VARIANT>::A>& preloaded, float* tiles, int64_t tile_id) {
+    constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A;
+    // (recomputed here rather than passed in: cheaper than keeping five values live across the body)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row0 = tile_id * kBlock + warp * 32;           // first env of this warp
+    const int64_t i = row0 + lane;
+    const bool valid = i < a.n;
+    const int rows = (int)max((int64_t)0, min((int64_t)32, a.n - row0));
+    float* tile = tiles + warp * (32 * O);
+    T s[12];
+    T m[4] = {(T)0, (T)0, (T)0, (T)0};
+    int st = ST_LANDED, steps = 1; uint32_t episode = 0;
+    T total = (T)0; bool done_any = false;
+    T ret = (T)0, ep_ret = (T)0; int ep_cause = 0, ep_len = 0, n_steps = 0;     // STATS only
+
+    if (valid) {
+        if constexpr (PRELOADED) {
+            decode_raw<T, A>(preloaded, s, m, st, steps, episode);
+        } else {
+            RawEnv<T, A> cur;
+            load_raw<T, A>(a, i, cur);
+            decode_raw<T, A>(cur, s, m, st, steps, episode);
+        }
+        if (STATS && a.ep_return) ret = a.ep_return[i];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) s[j] = (T)0;
+    }
+
+    Shaping<T> pre_sh = lander_shaping<T>(kp, s);
+    // the action is fixed for the K substeps of a launch, so Eq. 6 (the fp64 stage) runs once
+    const Forces<T> forces = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
+
+    const int kmax = SINGLE ? 1 : a.k;
+    for (int k = 0; k < kmax; ++k) {
+        const bool live = valid && (SINGLE || !done_any);
+        if (!SINGLE && __all_sync(0xffffffffu, !live)) break;          // whole warp finished: idle
+        if (live) {
+            // the reset perturbation is consumed by the first step of an episode
+            T pert[3] = {(T)0, (T)0, (T)0};
+            if (steps == 1) {
+                T f[3];
+                if (a.init_force) { f[0] = a.init_force[3 * i]; f[1] = a.init_force[3 * i + 1]; f[2] = a.init_force[3 * i + 2]; }
+                else reset_force<T>(kp, a.seed, (uint64_t)(a.env_offset + i), episode, f);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) pert[j] = f[j] * kp.invM;      // dynamics/__init__.py:229
+            }
+            T r; bool dn; int cause;
+            env_substep<T, VARIANT>(kp, s, st, steps, forces, pert, pre_sh, r, dn, cause);
+            total += r;
+            if (STATS) { ++n_steps; ret += r; }
+            if (dn) {
+                done_any = true;
+                ep_cause = cause;
+                if (STATS) { ep_len = steps - 1; ep_ret = ret; ret = (T)0; }   // `steps` is 1 right after reset (task.py:191,197)
+                if (a.final_obs) {   // terminal observation; rows of unfinished envs stay untouched
+#pragma unroll
+                    for (int j = 0; j < O; ++j) a.final_obs[i * O + j] = (float)s[Variant<VARIANT>::first + j];
+                }
+                if (a.auto_reset) {
+                    reset_state<T>(kp, s, st, steps);
+                    episode = (episode + 1) & 0x7FFFFu;
+                    if (!SINGLE && Variant<VARIANT>::lander) pre_sh = lander_shaping<T>(kp, s);
+                }
+            }
+        }
+    }
+
+    if (valid) {
+        store_state<T>(a.state, a.stride, i, s);
+        a.meta[i] = (uint32_t)st | ((uint32_t)steps << 2) | (episode << 13);
+        a.reward[i] = total;
+        a.done[i] = done_any ? 1 : 0;
+        if (a.cause) a.cause[i] = (uint8_t)ep_cause;
+        if (STATS && a.ep_return) a.ep_return[i] = ret;
+    }
+    if (a.obs) write_obs_rows<VARIANT, T>(a.obs, tile, lane, row0, rows, s);
+    if (STATS) {
+        flush_episode_stats<T>(a.stats, lane, done_any, ep_cause, ep_len, ep_ret, a.ep_return != nullptr);
+        if (!SINGLE) debit_idle_steps(a.stats, lane, valid ? a.k - n_steps : 0);
+    }
+}
+
 template <typename T, int VARIANT, bool STATS>
 __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? COPTER_F32_CTAS_PER_SM : 2)
 copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant__ StepArgs<T> a) {
     constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A;
     __shared__ __align__(16) float tiles[kWarpsPerBlock][32 * O];
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* tile = tiles[warp];
     if (STATS) credit_env_steps(a.stats, a.n, a.k);
 
-    // Software pipeline (fp32): the raw vectors of this thread's env in the NEXT tile are
-    // requested before the current tile's arithmetic starts, so every resident thread always
-    // has one tile of loads (68 B) in flight -- the kernel is latency-bound otherwise (ncu:
-    // 2/3 of the stall samples sat on the first use of the loaded state).
+    // COPTER_PREFETCH (A/B knob, persistent grids): the raw vectors of this thread's env in the
+    // NEXT tile are requested before the current tile's arithmetic starts.
     constexpr bool kPrefetch = COPTER_PREFETCH && sizeof(T) == 4;
     const int64_t n_tiles = (a.n + kBlock - 1) / kBlock;
     RawEnv<T, A> cur, nxt;
@@ -512,84 +599,13 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
         if (blockIdx.x < n_tiles && i0 < a.n) load_raw<T, A>(a, i0, cur);
     }
     for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
-        const int64_t row0 = tile_id * kBlock + warp * 32;       // first env of this warp
-        const int64_t i = row0 + lane;
-        const bool valid = i < a.n;
-        const int rows = (int)max((int64_t)0, min((int64_t)32, a.n - row0));
-
         if (kPrefetch) {
-            const int64_t inext = i + (int64_t)gridDim.x * kBlock;
+            const int64_t inext = (tile_id + gridDim.x) * kBlock + threadIdx.x;
             if (inext < a.n) load_raw<T, A>(a, inext, nxt);
-        } else if (valid) {
-            load_raw<T, A>(a, i, cur);
         }
-
-        T s[12];
-        T m[4] = {(T)0, (T)0, (T)0, (T)0};
-        int st = ST_LANDED, steps = 1; uint32_t episode = 0;
-        T total = (T)0; bool done_any = false;
-        T ret = (T)0, ep_ret = (T)0; int ep_cause = 0, ep_len = 0, n_steps = 0;     // STATS only
-
-        if (valid) {
-            decode_raw<T, A>(cur, s, m, st, steps, episode);
-            if (STATS && a.ep_return) ret = a.ep_return[i];
-        } else {
-#pragma unroll
-            for (int j = 0; j < 12; ++j) s[j] = (T)0;
-        }
+        if (COPTER_K1_SPECIALIZE && a.k == 1) step_tile<T, VARIANT, STATS, true, kPrefetch>(kp, a, cur, &tiles[0][0], tile_id);
+        else                                  step_tile<T, VARIANT, STATS, false, kPrefetch>(kp, a, cur, &tiles[0][0], tile_id);
         if (kPrefetch) cur = nxt;
-
-        Shaping<T> pre_sh = lander_shaping<T>(kp, s);
-        // the action is fixed for the K substeps of a launch, so Eq. 6 (the fp64 stage) runs once
-        const Forces<T> forces = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
-
-        for (int k = 0; k < a.k; ++k) {
-            const bool live = valid && !done_any;
-            if (__all_sync(0xffffffffu, !live)) break;             // whole warp finished: idle
-            if (live) {
-                // the reset perturbation is consumed by the first step of an episode
-                T pert[3] = {(T)0, (T)0, (T)0};
-                if (steps == 1) {
-                    T f[3];
-                    if (a.init_force) { f[0] = a.init_force[3 * i]; f[1] = a.init_force[3 * i + 1]; f[2] = a.init_force[3 * i + 2]; }
-                    else reset_force<T>(kp, a.seed, (uint64_t)(a.env_offset + i), episode, f);
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) pert[j] = f[j] * kp.invM;      // dynamics/__init__.py:229
-                }
-                T r; bool dn; int cause;
-                env_substep<T, VARIANT>(kp, s, st, steps, forces, pert, pre_sh, r, dn, cause);
-                total += r;
-                if (STATS) { ++n_steps; ret += r; }
-                if (dn) {
-                    done_any = true;
-                    ep_cause = cause;
-                    if (STATS) { ep_len = steps - 1; ep_ret = ret; ret = (T)0; }   // `steps` is 1 right after reset (task.py:191,197)
-                    if (a.final_obs) {   // terminal observation; rows of unfinished envs stay untouched
-#pragma unroll
-                        for (int j = 0; j < O; ++j) a.final_obs[i * O + j] = (float)s[Variant<VARIANT>::first + j];
-                    }
-                    if (a.auto_reset) {
-                        reset_state<T>(kp, s, st, steps);
-                        episode = (episode + 1) & 0x7FFFFu;
-                        if (Variant<VARIANT>::lander) pre_sh = lander_shaping<T>(kp, s);
-                    }
-                }
-            }
-        }
-
-        if (valid) {
-            store_state<T>(a.state, a.stride, i, s);
-            a.meta[i] = (uint32_t)st | ((uint32_t)steps << 2) | (episode << 13);
-            a.reward[i] = total;
-            a.done[i] = done_any ? 1 : 0;
-            if (a.cause) a.cause[i] = (uint8_t)ep_cause;
-            if (STATS && a.ep_return) a.ep_return[i] = ret;
-        }
-        if (a.obs) write_obs_rows<VARIANT, T>(a.obs, tile, lane, row0, rows, s);
-        if (STATS) {
-            flush_episode_stats<T>(a.stats, lane, done_any, ep_cause, ep_len, ep_ret, a.ep_return != nullptr);
-            if (a.k > 1) debit_idle_steps(a.stats, lane, valid ? a.k - n_steps : 0);
-        }
     }
 }
 

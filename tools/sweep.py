@@ -18,10 +18,9 @@ VDIR = os.path.join(ROOT, 'tools', 'variants')
 SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
 
 VARIANTS = {}
-for ctas, block in ((8, 128), (16, 64), (4, 256), (6, 128), (10, 128)):
-    VARIANTS['np_c%d_b%d' % (ctas, block)] = ['-DCOPTER_F32_CTAS_PER_SM=%d' % ctas, '-DCOPTER_BLOCK=%d' % block]
+for k1 in (0, 1):
+    VARIANTS['k1spec%d' % k1] = ['-DCOPTER_K1_SPECIALIZE=%d' % k1]
 VARIANTS['persist_pf1_c3_b256'] = ['-DCOPTER_PERSISTENT=1', '-DCOPTER_PREFETCH=1', '-DCOPTER_F32_CTAS_PER_SM=3', '-DCOPTER_BLOCK=256']
-VARIANTS['persist_pf0_c4_b256'] = ['-DCOPTER_PERSISTENT=1', '-DCOPTER_PREFETCH=0', '-DCOPTER_F32_CTAS_PER_SM=4', '-DCOPTER_BLOCK=256']
 
 
 def build():
