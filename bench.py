@@ -184,6 +184,9 @@ def main():
     import torch
     import torch.distributed as dist
     import gym_copter_b200 as g
+    if int(os.environ.get('LOCAL_RANK', '0')) == 0 and not os.path.exists(g._lib.LIB_PATH):
+        from gym_copter_b200 import build as _b      # in-tree artefact missing (fresh clone): build it
+        _b.build()
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))

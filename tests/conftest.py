@@ -31,3 +31,15 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope='session')
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope='session', autouse=True)
+def _built_library():
+    """The CUDA library is built in-tree (git-ignored): (re)build it when missing or stale.
+    nvcc cross-compiles without a GPU, so this also works in the build container."""
+    try:
+        from gym_copter_b200 import build
+        build.build()
+    except Exception as e:      # leave it to the tests that need it to fail loudly
+        print('libcopter_b200.so build skipped: %r' % (e,))
+    yield
