@@ -157,3 +157,30 @@ def test_two_rank_sharding_over_gloo():
     for lo, hi, x, ep in gathered:
         assert np.array_equal(x, whole.dyn.x[lo:hi]) and np.array_equal(ep, whole.episode[lo:hi])
     assert sorted((lo, hi) for lo, hi, _, _ in gathered) == [(0, 768), (768, 1537)]
+
+
+def test_gymnasium_shell_is_guarded_and_registers():
+    """Without gymnasium nothing is registered; with a gymnasium-shaped module present (the
+    oracle's stand-in is enough: Env, spaces.Box, registration.register) the reference's id
+    shape is registered with the reference's time limit."""
+    import importlib
+    import sys
+    from gym_copter_b200 import gym_compat
+    had = sys.modules.get('gymnasium')
+    try:
+        for k in [k for k in sys.modules if k == 'gymnasium' or k.startswith('gymnasium.')]:
+            del sys.modules[k]
+        sys.modules['gymnasium'] = None          # forces ImportError
+        assert gym_compat.register_envs() == []
+        del sys.modules['gymnasium']
+        from oracle import refshim
+        refshim._install_gymnasium_shim()
+        ids = gym_compat.register_envs()
+        assert 'gym_copter_b200/Lander-v0' in ids and 'gym_copter_b200/Hover3D-v0' in ids and len(ids) == 7
+        reg = sys.modules['gymnasium.envs.registration'].registry
+        assert reg['gym_copter_b200/Lander-v0']['max_episode_steps'] == 1000
+    finally:
+        for k in [k for k in sys.modules if k == 'gymnasium' or k.startswith('gymnasium.')]:
+            del sys.modules[k]
+        if had is not None:
+            sys.modules['gymnasium'] = had
