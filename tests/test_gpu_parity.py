@@ -536,3 +536,35 @@ def test_full_size_sampled_parity_and_conservation(pkg):
     assert s['episodes'] == done_total == int(env.episodes.to(torch.int64).sum().item())
     assert s['env_steps'] == N * T
     assert torch.equal(half.state, env.state[N // 2:]) and torch.equal(half.meta, env.meta[N // 2:])
+
+
+# ---------------------------------------------------------------------------------------
+# randomised shapes (hypothesis): any n / k / shard offset / variant / seed
+# ---------------------------------------------------------------------------------------
+
+def test_random_shapes_vs_oracle(pkg):
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(n=st.integers(1, 700), k=st.integers(1, 7), off=st.integers(0, 2 ** 40),
+           seed=st.integers(0, 2 ** 64 - 1), variant=st.sampled_from(list(VARIANTS)),
+           f64=st.booleans(), auto=st.booleans())
+    def check(n, k, off, seed, variant, f64, auto):
+        dtype = torch.float64 if f64 else torch.float32
+        env = pkg.CopterVecEnv(variant, n, dtype=dtype, seed=seed, env_offset=off, k_substeps=k, auto_reset=auto)
+        orc = EnvBatch(variant, n, seed=seed, env_offset=off, auto_reset=auto)
+        assert np.array_equal(env.reset()[0].cpu().numpy(), orc.reset())
+        rng = np.random.default_rng(seed % 2 ** 32)
+        tr = Tracker(n, dtype, saturating=np.ones(n, bool))
+        for t in range(12):
+            a = np.where(rng.random((n, 1)) < 0.3, rng.uniform(-1, 1, (n, env.action_size)),
+                         HOVER * (1 + 0.2 * rng.standard_normal((n, env.action_size)))).astype(np.float32)
+            obs, r, term, _, _ = env.step(a)
+            o_obs, o_r, o_done, _ = orc.step(a.astype(np.float64), k_substeps=k)
+            tr.compare(term.cpu().numpy(), r.cpu().numpy(), env.state.cpu().numpy(), obs.cpu().numpy(),
+                       [env.steps.cpu().numpy(), env.status.cpu().numpy(), env.episodes.cpu().numpy()],
+                       o_done, o_r, orc.dyn.x, o_obs, [orc.steps, orc.dyn.status, orc.episode])
+        assert tr.max_state <= tr.tol and tr.max_reward <= tr.tol and tr.max_obs <= max(tr.tol, tr.F32_EPS)
+        assert tr.flips == 0 if f64 else tr.flips <= max(1, n // 50)
+
+    check()
