@@ -469,8 +469,8 @@ copter_dynamics_kernel(const __grid_constant__ KParams<T> kp, T* state, uint8_t*
 #pragma unroll
         for (int j = 0; j < 4; ++j) m[j] = motors[4 * i + j];
         const Forces<T> f = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
-        T inc[8];
-        const bool finished = dynamics_update<T, 6, true>(kp, s, st, f, p, inc);
+        T na, nc;
+        const bool finished = dynamics_update<T, 6, true>(kp, s, st, f, p, na, nc);
         store_state<T>(state, n, i, s);
         status[i] = (uint8_t)st;
         if (finished) {                                            // :194-197

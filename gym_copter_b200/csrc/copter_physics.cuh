@@ -138,6 +138,29 @@ __device__ __forceinline__ void sincos_t(float a, float* s, float* c) {
     }
 }
 __device__ __forceinline__ void sincos_t(double a, double* s, double* c) { sincos(a, s, c); }
+
+// sin/cos of roll, pitch and yaw together: ONE range test for the three angles on the fp32
+// path (all three are below pi/4 in every step that matters), then three polynomial pairs.
+__device__ __forceinline__ void sincos_poly(float a, float& s, float& c) {
+    const float z = a * a;
+    float ps = fmaf(z, -1.95152959e-4f, 8.33216087e-3f);
+    ps = fmaf(ps, z, -1.66666546e-1f);
+    s = fmaf(a * z, ps, a);
+    float pc = fmaf(z, 2.44331571e-5f, -1.38873163e-3f);
+    pc = fmaf(pc, z, 4.16666456e-2f);
+    pc = fmaf(pc, z, -0.5f);
+    c = fmaf(pc, z, 1.0f);
+}
+__device__ __forceinline__ void sincos3_t(float a, float b, float g, float& sa, float& ca, float& sb, float& cb, float& sg, float& cg) {
+    if (!COPTER_LIBM_ONLY && fmaxf(fmaxf(fabsf(a), fabsf(b)), fabsf(g)) <= 0.78539816f) {
+        sincos_poly(a, sa, ca); sincos_poly(b, sb, cb); sincos_poly(g, sg, cg);
+    } else {
+        sincosf(a, &sa, &ca); sincosf(b, &sb, &cb); sincosf(g, &sg, &cg);
+    }
+}
+__device__ __forceinline__ void sincos3_t(double a, double b, double g, double& sa, double& ca, double& sb, double& cb, double& sg, double& cg) {
+    sincos(a, &sa, &ca); sincos(b, &sb, &cb); sincos(g, &sg, &cg);
+}
 __device__ __forceinline__ float  sqrt_t(float a)  { return sqrtf(a); }
 __device__ __forceinline__ double sqrt_t(double a) { return sqrt(a); }
 // Reward-only helpers (never used for the state): on the fp32 path sqrt and the quotient of
@@ -226,17 +249,16 @@ __device__ __forceinline__ Forces<T> motor_forces(const KParams<T>& kp, T m0, T 
 // facade).  DIRECT enables the LANDED -> AIRBORNE take-off transition, unreachable through
 // _Task.step (task.py:86-94).  Returns true when the call ran to the end of setMotors
 // (perturbation cleared, ticks += 1), false on the ground-contact early return (:177).
-// `inc` receives the UNROUNDED Euler increments dt*ds of (x,dx,y,dy,z,dz,psi,dpsi) -- zero when
-// the state was not integrated -- for the reward (see shaping_delta).
+// `na` / `nc` receive the shaping numerators sum_j inc_j (2 s_j + inc_j) over (x,dx,y,dy,z,dz)
+// and (psi,dpsi), inc_j = dt*ds_j being the Euler increment BEFORE it is rounded into the
+// state (zero when the state was not integrated) -- see shaping_delta.
+// The hot case (AIRBORNE, not touching the ground) is tested first and is straight-line code.
 template <typename T, int NP, bool DIRECT>
 __device__ __forceinline__ bool dynamics_update(const KParams<T>& kp, T (&s)[12], int& st,
-                                                const Forces<T>& f, const T (&p)[NP], T (&inc)[8]) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) inc[j] = (T)0;
+                                                const Forces<T>& f, const T (&p)[NP], T& na, T& nc) {
+    na = (T)0; nc = (T)0;
     T sph, cph, sth, cth, sps, cps;
-    sincos_t(s[6], &sph, &cph);
-    sincos_t(s[8], &sth, &cth);
-    sincos_t(s[10], &sps, &cps);
+    sincos3_t(s[6], s[8], s[10], sph, cph, sth, cth, sps, cps);
     // third column of the body->inertial rotation times the body-Z thrust (:292-302)
     const T ax = f.bz * (sph * sps + cph * cps * sth);
     const T ay = f.bz * (cph * sps * sth - cps * sph);
@@ -244,16 +266,8 @@ __device__ __forceinline__ bool dynamics_update(const KParams<T>& kp, T (&s)[12]
 
     if (DIRECT && st == ST_LANDED && netz < (T)0) st = ST_AIRBORNE;   // :147-149
 
-    if (st == ST_LEVELING) {                                       // :152-156
-        s[6] = (T)0; s[8] = (T)0; st = ST_LANDED;
-        return true;
-    }
-    if (st == ST_AIRBORNE) {
-        if (s[4] > (T)0 && s[5] > (T)0) {                          // :162 (pre-step state)
-            // :165-171 -- "velx" is dy, "vely" is dz, only phi is angle-tested (sic)
-            st = (s[5] > kp.lvy || abs_t(s[3]) > kp.lvx || abs_t(s[6]) > kp.lang) ? ST_CRASHED : ST_LEVELING;
-            return false;                                          // :177
-        }
+    const bool touch = s[4] > (T)0 && s[5] > (T)0;                 // :162 (pre-step state)
+    if (st == ST_AIRBORNE && !touch) {                             // :159, :180-187
         const T dphi = s[7], dthe = s[9], dpsi = s[11];
         // Eq. 12 (:257-290) with Omega = 0 (:135); the perturbation is added twice (:263-287, :183)
         T d1 = ax, d3 = ay, d5 = netz;
@@ -264,14 +278,27 @@ __device__ __forceinline__ bool dynamics_update(const KParams<T>& kp, T (&s)[12]
         if constexpr (NP == 6) { d7 += (T)2 * p[3]; d9 += (T)2 * p[4]; d11 += (T)2 * p[5]; }
         // forward Euler, every derivative from the old state (:187)
         const T dt = kp.dt;
-        inc[0] = dt * s[1]; inc[1] = dt * d1; inc[2] = dt * s[3]; inc[3] = dt * d3;
-        inc[4] = dt * s[5]; inc[5] = dt * d5; inc[6] = dt * dpsi; inc[7] = dt * d11;
+        const T i0 = dt * s[1], i1 = dt * d1, i2 = dt * s[3], i3 = dt * d3, i4 = dt * s[5], i5 = dt * d5;
+        const T i10 = dt * dpsi, i11 = dt * d11;
+        na = i0 * ((T)2 * s[0] + i0) + i1 * ((T)2 * s[1] + i1) + i2 * ((T)2 * s[2] + i2)
+           + i3 * ((T)2 * s[3] + i3) + i4 * ((T)2 * s[4] + i4) + i5 * ((T)2 * s[5] + i5);
+        nc = i10 * ((T)2 * s[10] + i10) + i11 * ((T)2 * s[11] + i11);
         s[0] += dt * s[1];  s[1] += dt * d1;
         s[2] += dt * s[3];  s[3] += dt * d3;
         s[4] += dt * s[5];  s[5] += dt * d5;
         s[6] += dt * dphi;  s[7] += dt * d7;
         s[8] += dt * dthe;  s[9] += dt * d9;
         s[10] += dt * dpsi; s[11] += dt * d11;
+        return true;
+    }
+    if (st == ST_LEVELING) {                                       // :152-156
+        s[6] = (T)0; s[8] = (T)0; st = ST_LANDED;
+        return true;
+    }
+    if (st == ST_AIRBORNE) {                                       // touched the ground (:162-177)
+        // :165-171 -- "velx" is dy, "vely" is dz, only phi is angle-tested (sic)
+        st = (s[5] > kp.lvy || abs_t(s[3]) > kp.lvx || abs_t(s[6]) > kp.lang) ? ST_CRASHED : ST_LEVELING;
+        return false;                                              // :177
     }
     return true;
 }
@@ -292,19 +319,15 @@ __device__ __forceinline__ Shaping<T> lander_shaping(const KParams<T>& kp, const
 
 // reward = shaping(post) - shaping(pre) (envs/lander.py:58-62), evaluated without the
 // cancellation of two O(250..1e4) numbers:  sqrt(a1) - sqrt(a0) = (a1 - a0) / (sqrt(a1) + sqrt(a0))
-// with a1 - a0 = sum_j inc_j (2 pre_j + inc_j), where inc_j = dt*ds_j is the Euler increment
-// BEFORE it is rounded into the stored state.  In fp32 this keeps the reward error
-// proportional to |reward| (1e-5 measured) instead of |shaping| * 2^-24 (literal subtraction,
-// up to 1e-3) or ulp(state)/increment (differences of stored states, 3e-4 at |v| ~ 270 m/s);
-// in fp64 it agrees with the reference's literal subtraction to ~1e-13.
-// `pre8` = (x,dx,y,dy,z,dz,psi,dpsi) before the step, `inc` from dynamics_update.
+// with a1 - a0 = sum_j inc_j (2 pre_j + inc_j) (`na`, `nc` from dynamics_update), where
+// inc_j = dt*ds_j is the Euler increment BEFORE it is rounded into the stored state.  In fp32
+// this keeps the reward error proportional to |reward| (1e-5 measured) instead of
+// |shaping| * 2^-24 (literal subtraction, up to 1e-3) or ulp(state)/increment (differences of
+// stored states, 3e-4 at |v| ~ 270 m/s); in fp64 it agrees with the reference's literal
+// subtraction to ~1e-13.
 template <typename T>
-__device__ __forceinline__ T shaping_delta(const KParams<T>& kp, const T (&pre8)[8], const Shaping<T>& pre,
-                                           const T (&inc)[8], const Shaping<T>& post) {
-    T na = (T)0;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) na += inc[j] * ((T)2 * pre8[j] + inc[j]);
-    const T nc = inc[6] * ((T)2 * pre8[6] + inc[6]) + inc[7] * ((T)2 * pre8[7] + inc[7]);
+__device__ __forceinline__ T shaping_delta(const KParams<T>& kp, const Shaping<T>& pre, T na, T nc,
+                                           const Shaping<T>& post) {
     const T da = post.ra + pre.ra, dc = post.rc + pre.rc;
     const T ga = da > (T)0 ? reward_div(na, da) : (T)0;
     const T gc = dc > (T)0 ? reward_div(nc, dc) : (T)0;
@@ -321,15 +344,14 @@ __device__ __forceinline__ void env_substep(const KParams<T>& kp, T (&s)[12], in
                                             const Forces<T>& f, const T (&pert)[3], Shaping<T>& pre_sh,
                                             T& reward, bool& done, int& cause) {
     const int st0 = st;                                            // :81 stale status
-    const T pre8[8] = {s[0], s[1], s[2], s[3], s[4], s[5], s[10], s[11]};
-    T inc[8] = {(T)0, (T)0, (T)0, (T)0, (T)0, (T)0, (T)0, (T)0};
+    T na = (T)0, nc = (T)0;
     if (st0 != ST_LANDED)                                          // :86-94
-        dynamics_update<T, 3, false>(kp, s, st, f, pert, inc);
+        dynamics_update<T, 3, false>(kp, s, st, f, pert, na, nc);
     cause = 0;
     done = false;
     if (Variant<VARIANT>::lander) {
         const Shaping<T> sh = lander_shaping<T>(kp, s);            // lander.py:48-56
-        reward = shaping_delta<T>(kp, pre8, pre_sh, inc, sh);      // :58-62
+        reward = shaping_delta<T>(kp, pre_sh, na, nc, sh);         // :58-62
         pre_sh = sh;
         if (st0 == ST_LANDED) {                                    // :64-72
             done = true; cause |= CAUSE_LANDED;

@@ -18,9 +18,8 @@ VDIR = os.path.join(ROOT, 'tools', 'variants')
 SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
 
 VARIANTS = {}
-for k1 in (0, 1):
-    VARIANTS['k1spec%d' % k1] = ['-DCOPTER_K1_SPECIALIZE=%d' % k1]
-VARIANTS['persist_pf1_c3_b256'] = ['-DCOPTER_PERSISTENT=1', '-DCOPTER_PREFETCH=1', '-DCOPTER_F32_CTAS_PER_SM=3', '-DCOPTER_BLOCK=256']
+VARIANTS['current'] = []
+VARIANTS['libm_only'] = ['-DCOPTER_LIBM_ONLY=1']
 
 
 def build():
