@@ -163,22 +163,27 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
     // the action is fixed for the K substeps of a launch, so Eq. 6 (the fp64 stage) runs once
     const Forces<T> forces = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
 
+    // The reset perturbation is consumed by the first step of an episode (steps == 1).  Inside
+    // a launch that can only be substep 0: an env that resets mid-launch idles afterwards.
+    T pert[3] = {(T)0, (T)0, (T)0};
+    if (valid && steps == 1) {
+        T f[3];
+        if (a.init_force) { f[0] = a.init_force[3 * i]; f[1] = a.init_force[3 * i + 1]; f[2] = a.init_force[3 * i + 2]; }
+        else reset_force<T>(kp, a.seed, (uint64_t)(a.env_offset + i), episode, f);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) pert[j] = f[j] * kp.invM;              // dynamics/__init__.py:229
+    }
+
     const int kmax = SINGLE ? 1 : a.k;
+    constexpr int kUnroll = COPTER_K_UNROLL;
+#pragma unroll kUnroll
     for (int k = 0; k < kmax; ++k) {
         const bool live = valid && (SINGLE || !done_any);
         if (!SINGLE && __all_sync(0xffffffffu, !live)) break;          // whole warp finished: idle
         if (live) {
-            // the reset perturbation is consumed by the first step of an episode
-            T pert[3] = {(T)0, (T)0, (T)0};
-            if (steps == 1) {
-                T f[3];
-                if (a.init_force) { f[0] = a.init_force[3 * i]; f[1] = a.init_force[3 * i + 1]; f[2] = a.init_force[3 * i + 2]; }
-                else reset_force<T>(kp, a.seed, (uint64_t)(a.env_offset + i), episode, f);
-#pragma unroll
-                for (int j = 0; j < 3; ++j) pert[j] = f[j] * kp.invM;      // dynamics/__init__.py:229
-            }
             T r; bool dn; int cause;
             env_substep<T, VARIANT>(kp, s, st, steps, forces, pert, pre_sh, r, dn, cause);
+            if (!SINGLE) { pert[0] = (T)0; pert[1] = (T)0; pert[2] = (T)0; }
             total += r;
             if (STATS) { ++n_steps; ret += r; }
             if (dn) {

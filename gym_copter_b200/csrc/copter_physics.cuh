@@ -46,6 +46,9 @@ namespace copter {
 #ifndef COPTER_K1_SPECIALIZE
 #define COPTER_K1_SPECIALIZE 1   // dedicated code path for k_substeps == 1 (the HBM-bound case)
 #endif
+#ifndef COPTER_K_UNROLL
+#define COPTER_K_UNROLL 1         // unroll factor of the substep loop (A/B knob)
+#endif
 #ifndef COPTER_STREAMING
 #define COPTER_STREAMING 0      // 1: evict-first (ld/st .cs) hints on the state planes
 #endif

@@ -18,8 +18,8 @@ VDIR = os.path.join(ROOT, 'tools', 'variants')
 SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
 
 VARIANTS = {}
-VARIANTS['current'] = []
-VARIANTS['libm_only'] = ['-DCOPTER_LIBM_ONLY=1']
+for u in (1, 2, 4):
+    VARIANTS['unroll%d' % u] = ['-DCOPTER_K_UNROLL=%d' % u]
 
 
 def build():
