@@ -196,8 +196,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # keep stdout to the one JSON line (NCCL_DEBUG=VERSION in the image prints a banner there)
-        os.environ['NCCL_DEBUG'] = os.environ.get('COPTER_NCCL_DEBUG', 'WARN')
+        # keep stdout to the one JSON line: the image exports NCCL_DEBUG, whose version banner
+        # goes to stdout unless it is sent elsewhere
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
