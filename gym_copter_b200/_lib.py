@@ -100,6 +100,8 @@ def load():
         f.argtypes, f.restype = [P, B, C.POINTER(CopterActionSource), i64, i64, u64, i64, i32, i32, i32, vp, vp, vp,
                                  C.POINTER(CopterPidGains), vp, vp], i32
     lib.copter_default_pid_gains.argtypes, lib.copter_default_pid_gains.restype = [C.POINTER(CopterPidGains)], None
+    lib.copter_policy_mlp_f32.argtypes = [vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp]
+    lib.copter_policy_mlp_f32.restype = i32
     lib.copter_pipeline_create.argtypes, lib.copter_pipeline_create.restype = [i32, C.POINTER(vp)], i32
     lib.copter_pipeline_destroy.argtypes, lib.copter_pipeline_destroy.restype = [vp], i32
     for f in (lib.copter_step_host_f32, lib.copter_step_host_f64):

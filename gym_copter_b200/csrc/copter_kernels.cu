@@ -11,6 +11,7 @@
 // The device-side arithmetic (what each function restates, precision) is in copter_physics.cuh.
 
 #include "copter_physics.cuh"
+#include "copter_policy.cuh"
 
 namespace {
 
@@ -683,6 +684,21 @@ int launch_reset_force(const CopterParams* p, T* out, const uint32_t* episode, i
     return (int)cudaGetLastError();
 }
 
+template <int VARIANT>
+int launch_policy_v(const PolicyArgs& a, cudaStream_t s) {
+    using V = Variant<VARIANT>;
+    auto* kernel = copter_mlp_policy_kernel<V::first, V::O, V::A>;
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int q = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kernel, 128, 0) != cudaSuccess || q <= 0) q = 4;
+        per_sm = q;
+    }
+    const int64_t tiles = (a.n + 127) / 128, cap = (int64_t)sm_count() * per_sm;    // persistent: weights load once per CTA
+    kernel<<<(int)(tiles < cap ? tiles : cap), 128, 0, s>>>(a);
+    return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // host-buffer pipeline: the step for callers that hold numpy-style HOST arrays
 // ------------------------------------------------------------------------------------------
@@ -811,6 +827,29 @@ int copter_reset_force_f32(const CopterParams* p, float* out, const uint32_t* ep
 }
 int copter_reset_force_f64(const CopterParams* p, double* out, const uint32_t* ep, int64_t n, int64_t env_offset, uint64_t seed, void* stream) {
     return launch_reset_force<double>(p, out, ep, n, env_offset, seed, stream);
+}
+
+int copter_policy_mlp_f32(const void* state, int64_t state_stride, int64_t n, int variant, int hidden,
+                          const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
+                          float out_scale, float out_offset, float* action, void* stream) {
+    if (!state || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !action) return COPTER_E_ARG;
+    if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
+    if (n < 0 || hidden != kPolH || (state_stride > 0 && state_stride < n)) return COPTER_E_RANGE;
+    if (!aligned16(state)) return COPTER_E_ALIGN;
+    if (n == 0) return 0;
+    PolicyArgs a;
+    a.state = (const float*)state; a.stride = state_stride > 0 ? state_stride : n; a.n = n;
+    a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.w3 = w3; a.b3 = b3;
+    a.out_scale = out_scale; a.out_offset = out_offset; a.action = action;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (variant) {
+        case COPTER_LANDER3D: return launch_policy_v<COPTER_LANDER3D>(a, s);
+        case COPTER_LANDER2D: return launch_policy_v<COPTER_LANDER2D>(a, s);
+        case COPTER_LANDER1D: return launch_policy_v<COPTER_LANDER1D>(a, s);
+        case COPTER_HOVER3D:  return launch_policy_v<COPTER_HOVER3D>(a, s);
+        case COPTER_HOVER2D:  return launch_policy_v<COPTER_HOVER2D>(a, s);
+        default:              return launch_policy_v<COPTER_HOVER1D>(a, s);
+    }
 }
 
 int copter_pipeline_create(int n_streams, void** out) {

@@ -9,9 +9,12 @@ tensor in place and writes reward / done straight into row t of the [T, N] rollo
 so a rollout costs one graph launch instead of T x (policy kernels + 1) launches.
 """
 
+import ctypes as C
+
 import torch
 
-from ._lib import CopterError
+from . import _lib
+from ._lib import CopterError, VARIANT_IDS
 
 
 class PolicyRollout:
@@ -97,6 +100,47 @@ class PlanarLinear(torch.nn.Module):
             y = x.to(w.dtype) @ w[:, 4 * p:4 * p + k].t()
             out = y if out is None else out + y
         return out if self.linear.bias is None else out + self.linear.bias
+
+
+class FusedMLPPolicy:
+    """
+    The tanh MLP O -> 64 -> 64 -> A evaluated by ONE hand-written kernel (copter_policy_mlp_f32:
+    warp-level bf16 tensor-core MMAs with fp32 accumulation, activations in registers, tanh on
+    the MUFU pipe) straight from the env's fp32 state planes -- no observation tensor, no [N,64]
+    intermediates in HBM.  `net` is a torch.nn.Sequential(Linear, Tanh, Linear, Tanh, Linear,
+    Tanh) (e.g. mlp_policy(...).net); its weights are read in place, so optimizer updates to
+    fp32 parameters are picked up by the next call.  action = out_offset + out_scale * net(obs).
+    Use with PolicyRollout(..., planar=True) and CopterVecEnv(write_obs=False).
+    """
+
+    def __init__(self, env, net, out_scale=1.0, out_offset=0.0):
+        lin = [m for m in net if isinstance(m, torch.nn.Linear)]
+        if len(lin) != 3 or lin[0].out_features != 64 or lin[1].in_features != 64 or lin[1].out_features != 64 \
+                or lin[0].in_features != env.obs_size or lin[2].out_features != env.action_size:
+            raise CopterError('FusedMLPPolicy needs Linear(O,64), Linear(64,64), Linear(64,A) with tanh activations')
+        if env.dtype != torch.float32:
+            raise CopterError('FusedMLPPolicy reads the fp32 state planes: build the env with dtype=torch.float32')
+        self.env, self.lib = env, _lib.load()
+        self.params = []
+        for m in lin:
+            for p in (m.weight, m.bias):
+                if p is None or p.dtype != torch.float32 or p.device != env.device or not p.is_contiguous():
+                    raise CopterError('policy parameters must be contiguous fp32 tensors (with bias) on the env device')
+                self.params.append(p)
+        self.out_scale, self.out_offset = float(out_scale), float(out_offset)
+        self.action = torch.zeros((env.num_envs, env.action_size), dtype=torch.float32, device=env.device)
+        self.launches = 0
+
+    def __call__(self, planes=None):
+        env = self.env
+        with torch.cuda.device(env.device):
+            _lib.check(self.lib.copter_policy_mlp_f32(
+                env.state_planes.data_ptr(), env.num_envs, env.num_envs, VARIANT_IDS[env.variant], 64,
+                *[p.data_ptr() for p in self.params], C.c_float(self.out_scale), C.c_float(self.out_offset),
+                self.action.data_ptr(), C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)),
+                'copter_policy_mlp')
+        self.launches += 1
+        return self.action
 
 
 def mlp_policy(obs_size, action_size, hidden=64, dtype=torch.bfloat16, device='cuda', seed=0):

@@ -202,6 +202,20 @@ int copter_reset_force_f64(const CopterParams* p, double* out, const uint32_t* e
                            int64_t n, int64_t env_offset, uint64_t seed, void* stream);
 
 /*
+ * The policy network of the rollout loop the reference's consumers run on the host -- obs -> net
+ * -> clip -> env.step (attic/drl/3dtest.py:36-61) -- as one kernel: the tanh MLP
+ * O -> 64 -> 64 -> A of BASELINE.json configs[4], reading the env's fp32 state planes in place
+ * (observation = state components first..first+O-1 of the variant) and writing the action rows
+ * copter_step_f32 consumes:  action = out_offset + out_scale * tanh(W3 tanh(W2 tanh(W1 obs + b1) + b2) + b3).
+ * Weights use the torch.nn.Linear layouts W[out][in] (fp32, device memory); they and the
+ * activations are rounded to bf16 for the tensor-core MMAs (fp32 accumulation).  hidden must be 64.
+ */
+int copter_policy_mlp_f32(const void* state, int64_t state_stride, int64_t n, int variant, int hidden,
+                          const float* w1, const float* b1, const float* w2, const float* b2,
+                          const float* w3, const float* b3, float out_scale, float out_offset,
+                          float* action, void* stream);
+
+/*
  * The same step for callers that hold HOST arrays (the reference's callers pass numpy
  * arrays, lander.py:42-44).  The shard is cut into chunks of `chunk_envs`; for each chunk
  * the action rows are copied host->device, the step kernel runs on that sub-range, and

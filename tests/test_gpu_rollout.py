@@ -241,3 +241,32 @@ def test_pid_heuristic_rollout_vs_oracle(pkg, dtype, tol):
     assert s['bonus'] > 0.9 * s['episodes'] > 0            # a landing workload: soft touch-downs inside the target
     with pytest.raises(pkg.CopterError):
         pkg.CopterVecEnv('Lander2D', 8).rollout(1, source='pid')
+
+
+@pytest.mark.parametrize('variant', ['Lander3D', 'Lander2D', 'Hover3D', 'Lander1D'])
+def test_fused_mlp_policy_vs_torch_fp32(pkg, variant):
+    """The hand-written policy kernel (bf16 tensor-core MMAs, fp32 accumulation, MUFU tanh)
+    against the plain PyTorch fp32 evaluation of the same network on the same observations.
+    Tolerance: bf16 rounding of inputs, weights and two layers of activations (2^-9 relative
+    each) plus tanh.approx (2^-11) on outputs in [-1, 1]."""
+    n = 4099
+    env = pkg.CopterVecEnv(variant, n, seed=3)
+    env.reset()
+    g = torch.Generator(device='cuda').manual_seed(0)
+    for t in range(30):          # spread the states out
+        env.step(0.0166 * (1 + 0.3 * torch.randn((n, env.action_size), device='cuda', generator=g)))
+    pol = pkg.mlp_policy(env.obs_size, env.action_size, dtype=torch.float32, seed=5)
+    for p in pol.net.parameters():
+        p.data.mul_(3.0)         # push the activations into the curved part of tanh
+    fused = pkg.FusedMLPPolicy(env, pol.net, out_scale=0.5, out_offset=0.25)
+    got = fused()
+    with torch.no_grad():
+        ref = 0.25 + 0.5 * pol.net(env.obs)
+    err = (got - ref).abs()
+    assert got.shape == (n, env.action_size)
+    assert err.max().item() <= 2e-2 and err.mean().item() <= 3e-3, (err.max().item(), err.mean().item())
+    assert ref.std().item() > 0.05       # the comparison is not vacuous
+    # in the loop: same trajectories as the torch policy up to the policy's own rounding
+    ro = pkg.PolicyRollout(env, fused, 4, planar=True, use_cuda_graph=True)
+    r, d, _ = ro.run()
+    assert r.shape == (4, n) and torch.isfinite(r).all()

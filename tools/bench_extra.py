@@ -85,6 +85,20 @@ def policy():
             ms = timed(ro.run, 10)
             print(json.dumps({'bench': 'policy-in-loop Lander3D 2^23 envs, MLP 10-64-64-4 %s, T=%d, %s' % (str(dt).split('.')[-1], T, 'cuda graph' if graph else 'eager'),
                               'ms_per_env_step': ms / T, 'steps_per_s': n * T / ms * 1e3}), flush=True)
+        if dt == torch.bfloat16:
+            # the same network evaluated by the hand-written policy kernel, zero-copy from the state planes
+            env2 = g.LanderVec(n, seed=3, write_obs=False)
+            env2.reset()
+            pol32 = g.mlp_policy(10, 4, dtype=torch.float32)
+            fused = g.FusedMLPPolicy(env2, pol32.net, out_scale=0.2 * 0.0166, out_offset=0.0166)
+            ms_pol = timed(fused, 50)
+            for graph in (False, True):
+                ro = g.PolicyRollout(env2, fused, T, use_cuda_graph=graph, planar=True)
+                ro.run(); ro.run()
+                ms = timed(ro.run, 10)
+                print(json.dumps({'bench': 'policy-in-loop Lander3D 2^23 envs, FUSED MLP kernel 10-64-64-4, T=%d, %s' % (T, 'cuda graph' if graph else 'eager'),
+                                  'ms_per_env_step': ms / T, 'steps_per_s': n * T / ms * 1e3, 'policy_kernel_ms': ms_pol}), flush=True)
+            del env2
         # env-only share of the same loop
         a = torch.full((n, 4), 0.0166, device='cuda')
         ms_env = timed(lambda: env.step(a), 200)
