@@ -9,8 +9,8 @@
 // (mma.sync.m16n8k16, bf16 inputs, fp32 accumulation).  The accumulator fragment of layer L is
 // exactly the A-operand fragment of layer L+1 (n-tiles 2k, 2k+1 -> k-tile k), so between layers
 // there is only bias + tanh (MUFU.TANH) + bf16 packing, all in registers.  The kernel is bound
-// by the MUFU pipe (128 tanh per env), not by the tensor pipe or HBM, which is why the legacy
-// warp-level MMA is the right tool here and tcgen05/TMEM would buy nothing.
+// by the MUFU (XU) pipe -- 132 tanh per env; ncu: XU saturated, tensor pipe 27 % busy, HBM idle --
+// which is why the warp-level MMA is enough here and tcgen05/TMEM would buy nothing.
 // Weights live in shared memory as bf16, rows padded by 8 elements so that the B-fragment loads
 // of a warp hit 32 distinct banks.  Persistent CTAs (weights are loaded once per CTA).
 #pragma once
@@ -40,6 +40,21 @@ __device__ __forceinline__ float tanh_fast(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// hidden activations: bias add in fp32, then tanh.  COPTER_POLICY_TANH_BF16X2 (A/B knob) rounds
+// the pair to bf16 first and uses tanh.approx.bf16x2; it is not faster on B200 (the packed form
+// costs two XU slots) and is less accurate, so the default is two fp32 MUFU.TANH.
+#ifndef COPTER_POLICY_TANH_BF16X2
+#define COPTER_POLICY_TANH_BF16X2 0      // measured on B200: 0.435 ms vs 0.412 ms for two fp32 tanh (2^23 envs)
+#endif
+__device__ __forceinline__ uint32_t tanh_pack(float lo, float hi) {
+#if COPTER_POLICY_TANH_BF16X2
+    uint32_t y;
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(pack_bf16(lo, hi)));
+    return y;
+#else
+    return pack_bf16(tanh_fast(lo), tanh_fast(hi));
+#endif
 }
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -126,8 +141,8 @@ copter_mlp_policy_kernel(const __grid_constant__ PolicyArgs a) {
                 const int wr = (8 * nt + g) * (kPolW1Stride / 2);
                 mma_bf16(c, afrag, w1[wr + t], w1[wr + t + 4]);
                 const float bx = sm.b1[8 * nt + 2 * t], by = sm.b1[8 * nt + 2 * t + 1];
-                h[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(tanh_fast(c[0] + bx), tanh_fast(c[1] + by));   // rows g
-                h[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(tanh_fast(c[2] + bx), tanh_fast(c[3] + by));   // rows g+8
+                h[nt >> 1][(nt & 1) * 2 + 0] = tanh_pack(c[0] + bx, c[1] + by);   // rows g
+                h[nt >> 1][(nt & 1) * 2 + 1] = tanh_pack(c[2] + bx, c[3] + by);   // rows g+8
             }
             // ---- layer 2: [16 x 64] x [64 x 64] ------------------------------------------
             uint32_t h2[4][4];
@@ -138,8 +153,8 @@ copter_mlp_policy_kernel(const __grid_constant__ PolicyArgs a) {
 #pragma unroll
                 for (int kt = 0; kt < 4; ++kt) mma_bf16(c, h[kt], w2[wr + 8 * kt + t], w2[wr + 8 * kt + t + 4]);
                 const float bx = sm.b2[8 * nt + 2 * t], by = sm.b2[8 * nt + 2 * t + 1];
-                h2[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(tanh_fast(c[0] + bx), tanh_fast(c[1] + by));
-                h2[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(tanh_fast(c[2] + bx), tanh_fast(c[3] + by));
+                h2[nt >> 1][(nt & 1) * 2 + 0] = tanh_pack(c[0] + bx, c[1] + by);
+                h2[nt >> 1][(nt & 1) * 2 + 1] = tanh_pack(c[2] + bx, c[3] + by);
             }
             // ---- layer 3: [16 x 64] x [64 x 8] -------------------------------------------
             float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};

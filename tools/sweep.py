@@ -18,8 +18,8 @@ VDIR = os.path.join(ROOT, 'tools', 'variants')
 SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
 
 VARIANTS = {}
-for u in (1, 2, 4):
-    VARIANTS['unroll%d' % u] = ['-DCOPTER_K_UNROLL=%d' % u]
+for x2 in (0, 1):
+    VARIANTS['poltanh_bf16x2_%d' % x2] = ['-DCOPTER_POLICY_TANH_BF16X2=%d' % x2]
 
 
 def build():
@@ -59,7 +59,25 @@ def time_one(envs, k, steps, stats):
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / steps)
-    print(json.dumps({'ms': best, 'gbs': 165 * envs / best / 1e6, 'steps_per_s': envs * k / best * 1e3}))
+    out = {'ms': best, 'gbs': 165 * envs / best / 1e6, 'steps_per_s': envs * k / best * 1e3}
+    try:        # the policy kernel of this build: speed and error against the PyTorch fp32 network
+        pol = g.mlp_policy(10, 4, dtype=torch.float32, seed=5)
+        for p in pol.net.parameters():
+            p.data.mul_(3.0)
+        fused = g.FusedMLPPolicy(env, pol.net)
+        got = fused()
+        with torch.no_grad():
+            ref = pol.net(env.obs)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(20):
+            fused()
+        e1.record(); torch.cuda.synchronize()
+        out.update(policy_ms=e0.elapsed_time(e1) / 20, policy_max_err=(got - ref).abs().max().item(),
+                   policy_mean_err=(got - ref).abs().mean().item())
+    except Exception as e:
+        out['policy'] = repr(e)[:100]
+    print(json.dumps(out))
 
 
 def copy_peak():
