@@ -9,8 +9,8 @@
 // (mma.sync.m16n8k16, bf16 inputs, fp32 accumulation).  The accumulator fragment of layer L is
 // exactly the A-operand fragment of layer L+1 (n-tiles 2k, 2k+1 -> k-tile k), so between layers
 // there is only bias + tanh (MUFU.TANH) + bf16 packing, all in registers.  The kernel is bound
-// by the MUFU (XU) pipe -- 132 tanh per env; ncu: XU saturated, tensor pipe 27 % busy, HBM idle --
-// which is why the warp-level MMA is enough here and tcgen05/TMEM would buy nothing.
+// by the MUFU (XU) pipe -- 132 tanh per env; ncu: XU 62 %, tensor pipe 40 %, LSU 29 % busy, HBM
+// idle -- so the warp-level MMA is enough here: tcgen05/TMEM would not move the XU floor.
 // Weights live in shared memory as bf16, rows padded by 8 elements so that the B-fragment loads
 // of a warp hit 32 distinct banks.  Persistent CTAs (weights are loaded once per CTA).
 #pragma once
@@ -70,8 +70,11 @@ struct PolicyArgs {
 };
 
 // FIRST / OBS / ACT: observation window into the 12-state and action size of the env variant.
+#ifndef COPTER_POLICY_CTAS_PER_SM
+#define COPTER_POLICY_CTAS_PER_SM 3
+#endif
 template <int FIRST, int OBS, int ACT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, COPTER_POLICY_CTAS_PER_SM)
 copter_mlp_policy_kernel(const __grid_constant__ PolicyArgs a) {
     static_assert(OBS <= kPolIn && ACT <= kPolOut && FIRST + OBS <= 12, "policy tile shapes");
     __shared__ __align__(16) PolicySmem sm;

@@ -18,8 +18,8 @@ VDIR = os.path.join(ROOT, 'tools', 'variants')
 SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
 
 VARIANTS = {}
-for x2 in (0, 1):
-    VARIANTS['poltanh_bf16x2_%d' % x2] = ['-DCOPTER_POLICY_TANH_BF16X2=%d' % x2]
+for c in (3, 4, 5, 6):
+    VARIANTS['policy_ctas%d' % c] = ['-DCOPTER_POLICY_CTAS_PER_SM=%d' % c]
 
 
 def build():
