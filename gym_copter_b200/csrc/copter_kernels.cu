@@ -23,7 +23,6 @@ struct StepArgs {
     const T* init_force; T* ep_return; double* stats; float* final_obs; uint8_t* cause;
     int64_t n, stride, env_offset; uint64_t seed; int k; int auto_reset;
 };
-template <typename T> using StepArgsBase = StepArgs<T>;
 
 // One env's inputs exactly as they sit in HBM (128-bit vectors), so that the loads of the
 // NEXT tile can be issued before the arithmetic of the current one without being decoded.
@@ -34,7 +33,7 @@ template <typename T, int A> struct RawEnv {
 };
 
 template <typename T, int A>
-__device__ __forceinline__ void load_raw(const StepArgsBase<T>& a, int64_t i, RawEnv<T, A>& r) {
+__device__ __forceinline__ void load_raw(const StepArgs<T>& a, int64_t i, RawEnv<T, A>& r) {
     using V4 = typename Vec<T>::type;
     constexpr int V = Vec<T>::V;
     const V4* planes = reinterpret_cast<const V4*>(a.state);

@@ -15,7 +15,6 @@ consume.
 """
 
 import ctypes as C
-import math
 
 import numpy as np
 import torch

@@ -34,7 +34,7 @@ are defined in DESIGN.md and mirrored here):
     with identical injected forces.
 """
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 

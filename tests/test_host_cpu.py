@@ -163,7 +163,6 @@ def test_gymnasium_shell_is_guarded_and_registers():
     """Without gymnasium nothing is registered; with a gymnasium-shaped module present (the
     oracle's stand-in is enough: Env, spaces.Box, registration.register) the reference's id
     shape is registered with the reference's time limit."""
-    import importlib
     import sys
     from gym_copter_b200 import gym_compat
     had = sys.modules.get('gymnasium')

@@ -7,7 +7,6 @@ cache hints).  `build` cross-compiles the variants here (no GPU needed) into too
     python tools/sweep.py build
     gpurun -- python tools/sweep.py run [--envs N] [--k K]
 """
-import itertools
 import json
 import os
 import subprocess
