@@ -174,18 +174,12 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
         for (int j = 0; j < 3; ++j) pert[j] = f[j] * kp.invM;              // dynamics/__init__.py:229
     }
 
-    const int kmax = SINGLE ? 1 : a.k;
-    constexpr int kUnroll = COPTER_K_UNROLL;
-#pragma unroll kUnroll
-    for (int k = 0; k < kmax; ++k) {
-        const bool live = valid && (SINGLE || !done_any);
-        if (!SINGLE && __all_sync(0xffffffffu, !live)) break;          // whole warp finished: idle
-        if (live) {
+    if constexpr (SINGLE) {
+        if (valid) {
             T r; bool dn; int cause;
             env_substep<T, VARIANT>(kp, s, st, steps, forces, pert, pre_sh, r, dn, cause);
-            if (!SINGLE) { pert[0] = (T)0; pert[1] = (T)0; pert[2] = (T)0; }
-            total += r;
-            if (STATS) { ++n_steps; ret += r; }
+            total = r;
+            if (STATS) { n_steps = 1; ret += r; }
             if (dn) {
                 done_any = true;
                 ep_cause = cause;
@@ -197,8 +191,72 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
                 if (a.auto_reset) {
                     reset_state<T>(kp, s, st, steps);
                     episode = (episode + 1) & 0x7FFFFu;
-                    if (!SINGLE && Variant<VARIANT>::lander) pre_sh = lander_shaping<T>(kp, s);
                 }
+            }
+        }
+    } else {
+        // K substeps under one action.  The summed reward telescopes: sum_k (shaping_k - shaping_{k-1})
+        // = shaping_K - shaping_0, so the substep loop only accumulates the shaping numerators
+        // (two adds) and the square roots / quotients are evaluated once, after the loop.  The one
+        // exception is an over-angle ending, whose own step reward is REPLACED by the penalty
+        // (task.py:116-118): then the sum stops at the state before that step, recovered from
+        // a_prev = a_now - na, c_prev = c_now - nc and the previous dz.
+        T na_sum = (T)0, nc_sum = (T)0;
+        Shaping<T> end_sh = pre_sh;                  // shaping at which the telescoped sum ends
+        int executed = 0, mod_cause = 0;
+        constexpr int kUnroll = COPTER_K_UNROLL;
+#pragma unroll kUnroll
+        for (int k = 0; k < a.k; ++k) {
+            const bool live = valid && !done_any;
+            if (__all_sync(0xffffffffu, !live)) break;                 // whole warp finished: idle
+            if (live) {
+                const T dz_prev = s[5];
+                T na, nc; bool dn; int cause;
+                env_advance<T, VARIANT>(kp, s, st, steps, forces, pert, na, nc, dn, cause);
+                pert[0] = (T)0; pert[1] = (T)0; pert[2] = (T)0;
+                ++executed;
+                if (dn && (cause & CAUSE_ANGLE)) {
+                    if (Variant<VARIANT>::lander) {
+                        const Shaping<T> now = lander_shaping<T>(kp, s);
+                        end_sh.ra = reward_sqrt(fmax(now.ra * now.ra - na, (T)0));
+                        end_sh.rc = reward_sqrt(fmax(now.rc * now.rc - nc, (T)0));
+                        end_sh.pen = abs_t(dz_prev) > kp.dz_max ? kp.dz_penalty : (T)0;
+                    }
+                } else {
+                    na_sum += na; nc_sum += nc;
+                    if (dn && Variant<VARIANT>::lander) end_sh = lander_shaping<T>(kp, s);
+                }
+                if (dn) {
+                    done_any = true;
+                    ep_cause = cause; mod_cause = cause;
+                    if (STATS) ep_len = steps - 1;                     // `steps` is 1 right after reset (task.py:191,197)
+                    if (a.final_obs) {   // terminal observation; rows of unfinished envs stay untouched
+#pragma unroll
+                        for (int j = 0; j < O; ++j) a.final_obs[i * O + j] = (float)s[Variant<VARIANT>::first + j];
+                    }
+                    if (a.auto_reset) {
+                        reset_state<T>(kp, s, st, steps);
+                        episode = (episode + 1) & 0x7FFFFu;
+                    }
+                }
+            }
+        }
+        if (valid) {
+            if (Variant<VARIANT>::lander) {
+                if (!done_any) end_sh = lander_shaping<T>(kp, s);
+                total = shaping_delta<T>(kp, pre_sh, na_sum, nc_sum, end_sh);
+                // an over-angle ending contributes its penalty on top of the sum of the earlier steps
+                if (mod_cause & CAUSE_ANGLE) total -= kp.oob_penalty;
+                else total = apply_reward_modifiers<T>(kp, total, mod_cause);
+            } else {
+                // hover: +1 per executed step (attic hover.py:18-21); an over-angle step yields the penalty instead
+                total = (T)executed;
+                if (mod_cause & CAUSE_ANGLE) total += -kp.oob_penalty - (T)1;
+                else total = apply_reward_modifiers<T>(kp, total, mod_cause);
+            }
+            if (STATS) {
+                n_steps = executed; ret += total;
+                if (done_any) { ep_ret = ret; ret = (T)0; }
             }
         }
     }

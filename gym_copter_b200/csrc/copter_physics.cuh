@@ -337,36 +337,30 @@ __device__ __forceinline__ T shaping_delta(const KParams<T>& kp, const Shaping<T
     return -(kp.xyz_pf * ga + kp.yaw_pf * gc) - (post.pen - pre.pen);
 }
 
-// One reference _Task.step (envs/task.py:77-137) for one env held in registers.
-// `steps`/`st` are the env's counters; `pre_sh` is shaping(pre-step state) == prev_shaping
-// (the priming step of _reset sets it to shaping(s0) and every later step stores the
-// post-step value, task.py:197, lander.py:62), so it never has to live in HBM.  On return
-// `pre_sh` holds shaping(post).
+// One reference _Task.step (envs/task.py:77-137) for one env held in registers, WITHOUT the
+// reward: advances the dynamics, the status machine and the step counter and reports whether
+// the episode ended and why.  `na` / `nc` are the shaping numerators of this step (see
+// dynamics_update); the reward modifiers are encoded in `cause` (BONUS: + bonus, lander.py:69-72;
+// OOB: - penalty, task.py:111-113; ANGLE: reward := - penalty, task.py:116-118; the two are
+// exclusive because the reference tests them with if / elif).
 template <typename T, int VARIANT>
-__device__ __forceinline__ void env_substep(const KParams<T>& kp, T (&s)[12], int& st, int& steps,
-                                            const Forces<T>& f, const T (&pert)[3], Shaping<T>& pre_sh,
-                                            T& reward, bool& done, int& cause) {
+__device__ __forceinline__ void env_advance(const KParams<T>& kp, T (&s)[12], int& st, int& steps,
+                                            const Forces<T>& f, const T (&pert)[3], T& na, T& nc,
+                                            bool& done, int& cause) {
     const int st0 = st;                                            // :81 stale status
-    T na = (T)0, nc = (T)0;
+    na = (T)0; nc = (T)0;
     if (st0 != ST_LANDED)                                          // :86-94
         dynamics_update<T, 3, false>(kp, s, st, f, pert, na, nc);
     cause = 0;
     done = false;
-    if (Variant<VARIANT>::lander) {
-        const Shaping<T> sh = lander_shaping<T>(kp, s);            // lander.py:48-56
-        reward = shaping_delta<T>(kp, pre_sh, na, nc, sh);         // :58-62
-        pre_sh = sh;
-        if (st0 == ST_LANDED) {                                    // :64-72
-            done = true; cause |= CAUSE_LANDED;
-            if (sqrt_t(s[0] * s[0] + s[2] * s[2]) < kp.target_radius) { reward += kp.bonus; cause |= CAUSE_BONUS; }
-        }
-    } else {
-        reward = (T)1;                                             // attic hover.py:18-21
+    if (Variant<VARIANT>::lander && st0 == ST_LANDED) {            // lander.py:64-72
+        done = true; cause |= CAUSE_LANDED;
+        if (sqrt_t(s[0] * s[0] + s[2] * s[2]) < kp.target_radius) cause |= CAUSE_BONUS;
     }
     if (abs_t(s[0]) >= kp.bounds || abs_t(s[2]) >= kp.bounds) {    // task.py:111
-        done = true; reward -= kp.oob_penalty; cause |= CAUSE_OOB;
+        done = true; cause |= CAUSE_OOB;
     } else if (abs_t(s[6]) >= kp.max_angle || abs_t(s[8]) >= kp.max_angle) {   // :116
-        done = true; reward = -kp.oob_penalty; cause |= CAUSE_ANGLE;
+        done = true; cause |= CAUSE_ANGLE;
     } else if (st0 == ST_CRASHED) {                                // :121
         done = true;
     }
@@ -374,6 +368,35 @@ __device__ __forceinline__ void env_substep(const KParams<T>& kp, T (&s)[12], in
     if (steps == kp.max_steps) { done = true; cause |= CAUSE_TIMEOUT; }          // :128
     steps = min(steps + 1, 2047);                                  // :130 (11-bit field)
     if (!done) cause = 0;
+}
+
+// The reward modifiers of task.py:111-118 and lander.py:69-72 applied to a base reward.
+template <typename T>
+__device__ __forceinline__ T apply_reward_modifiers(const KParams<T>& kp, T r, int cause) {
+    if (cause & CAUSE_BONUS) r += kp.bonus;
+    if (cause & CAUSE_OOB) r -= kp.oob_penalty;
+    else if (cause & CAUSE_ANGLE) r = -kp.oob_penalty;
+    return r;
+}
+
+// env_advance + the step's reward.  `pre_sh` is shaping(pre-step state) == prev_shaping (the
+// priming step of _reset sets it to shaping(s0) and every later step stores the post-step
+// value, task.py:197, lander.py:62), so it never has to live in HBM; on return it holds
+// shaping(post).
+template <typename T, int VARIANT>
+__device__ __forceinline__ void env_substep(const KParams<T>& kp, T (&s)[12], int& st, int& steps,
+                                            const Forces<T>& f, const T (&pert)[3], Shaping<T>& pre_sh,
+                                            T& reward, bool& done, int& cause) {
+    T na, nc;
+    env_advance<T, VARIANT>(kp, s, st, steps, f, pert, na, nc, done, cause);
+    if (Variant<VARIANT>::lander) {
+        const Shaping<T> sh = lander_shaping<T>(kp, s);            // lander.py:48-56
+        reward = shaping_delta<T>(kp, pre_sh, na, nc, sh);         // :58-62
+        pre_sh = sh;
+    } else {
+        reward = (T)1;                                             // attic hover.py:18-21
+    }
+    reward = apply_reward_modifiers<T>(kp, reward, cause);
 }
 
 template <typename T>

@@ -17,8 +17,7 @@ VDIR = os.path.join(ROOT, 'tools', 'variants')
 SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
 
 VARIANTS = {}
-for c in (3, 4, 5, 6):
-    VARIANTS['policy_ctas%d' % c] = ['-DCOPTER_POLICY_CTAS_PER_SM=%d' % c]
+VARIANTS['current'] = []
 
 
 def build():
