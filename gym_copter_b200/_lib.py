@@ -13,6 +13,7 @@ ABI_VERSION = 1
 STATS_LEN = 16
 STATS_SLOTS = 64
 F_AUTO_RESET = 1
+MODEL_LIFT, MODEL_GYRO = 1, 2
 CAUSE_LANDED, CAUSE_BONUS, CAUSE_OOB, CAUSE_ANGLE, CAUSE_CRASHED, CAUSE_TIMEOUT = 1, 2, 4, 8, 16, 32
 STATUS_CRASHED, STATUS_LANDED, STATUS_LEVELING, STATUS_AIRBORNE = 0, 1, 2, 3
 VARIANT_IDS = {'Lander3D': 0, 'Lander2D': 1, 'Lander1D': 2, 'Hover3D': 3, 'Hover2D': 4, 'Hover1D': 5}
@@ -27,7 +28,7 @@ class CopterParams(C.Structure):
         'fps', 'initial_random_force', 'out_of_bounds_penalty', 'max_angle_deg', 'bounds',
         'initial_altitude',
         'target_radius', 'yaw_penalty_factor', 'xyz_penalty_factor', 'dz_max', 'dz_penalty',
-        'inside_radius_bonus')] + [('max_steps', C.c_int32), ('reserved', C.c_int32)]
+        'inside_radius_bonus', 'rho', 'lift_coefficient')] + [('max_steps', C.c_int32), ('dynamics_model', C.c_int32)]
 
 
 class CopterBuffers(C.Structure):

@@ -830,7 +830,8 @@ void copter_default_params(CopterParams* p) {
     p->max_angle_deg = 45; p->bounds = 10; p->initial_altitude = 10; p->max_steps = 1000;
     p->target_radius = 2; p->yaw_penalty_factor = 50; p->xyz_penalty_factor = 25;                  // lander.py:17-23
     p->dz_max = 10; p->dz_penalty = 100; p->inside_radius_bonus = 100;
-    p->reserved = 0;
+    p->rho = 1.225; p->lift_coefficient = 0.4;      // attic/mars/dynamics/__init__.py:83-84, ingenuity.py:55
+    p->dynamics_model = 0;
 }
 
 int copter_obs_size(int variant) {

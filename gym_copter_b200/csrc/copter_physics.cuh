@@ -76,9 +76,11 @@ template <> struct Variant<COPTER_HOVER1D>  { static constexpr int O = 2,  A = 1
 template <typename T>
 struct KParams {
     double kT, kR, kP, kY;        // B w^2/M, L B w^2/Ix, L B w^2/Iy, D w^2/Iz  (w = maxrpm*pi/30)
+    double kOm;                   // w when the gyroscopic coupling is live (COPTER_MODEL_GYRO), else 0
     double force_scale, force_off; // u32 -> U(-F,F): u * 2F/2^32 - F
     T G, dt, gphi, gthe, gpsi;    // (Iy-Iz)/Ix, (Iz-Ix)/Iy, (Ix-Iy)/Iz
     T lvx, lvy, lang, invM;
+    T jx, jy;                     // Jr/Ix, Jr/Iy
     T oob_penalty, max_angle, bounds, z0, target_radius;
     T yaw_pf, xyz_pf, dz_max, dz_penalty, bonus;
     int max_steps;
@@ -89,10 +91,17 @@ template <typename T>
 KParams<T> make_kparams(const CopterParams& p) {
     KParams<T> k;
     const double w = p.maxrpm * M_PI / 30.0;
-    k.kT = p.B * w * w / p.M;
-    k.kR = p.L * p.B * w * w / p.Ix;
-    k.kP = p.L * p.B * w * w / p.Iy;
+    // thrust per unit w^2 and the roll/pitch torque arm: live model B and L (dynamics/__init__.py:127-129),
+    // lift model 0.5 rho S C_L (L/2)^2 and 1 (attic/mars/dynamics/__init__.py:101,146-158)
+    const bool lift = (p.dynamics_model & COPTER_MODEL_LIFT) != 0;
+    const double b = lift ? 0.5 * p.rho * (0.05 * p.L * 4) * p.lift_coefficient * (p.L / 2) * (p.L / 2) : p.B;
+    const double arm = lift ? 1.0 : p.L;
+    k.kT = b * w * w / p.M;
+    k.kR = arm * b * w * w / p.Ix;
+    k.kP = arm * b * w * w / p.Iy;
     k.kY = p.D * w * w / p.Iz;
+    k.kOm = (p.dynamics_model & COPTER_MODEL_GYRO) ? w : 0.0;
+    k.jx = (T)(p.Jr / p.Ix); k.jy = (T)(p.Jr / p.Iy);
     k.force_scale = 2.0 * p.initial_random_force / 4294967296.0;
     k.force_off = -p.initial_random_force;
     k.G = (T)p.G;
@@ -231,7 +240,7 @@ __device__ __forceinline__ void reset_force(const KParams<T>& kp, uint64_t seed,
 // ------------------------------------------------------------------------------------------
 // dynamics
 // ------------------------------------------------------------------------------------------
-template <typename T> struct Forces { T bz, u2, u3, u4; };   // -U1/M, U2/Ix, U3/Iy, U4/Iz
+template <typename T> struct Forces { T bz, u2, u3, u4, om; };   // -U1/M, U2/Ix, U3/Iy, U4/Iz, Omega
 
 // dynamics/__init__.py:120-132.  Always evaluated in fp64 (see header comment).
 template <typename T>
@@ -244,6 +253,8 @@ __device__ __forceinline__ Forces<T> motor_forces(const KParams<T>& kp, T m0, T 
     f.u2 = (T)(kp.kR * ((q1 + q2) - (q0 + q3)));      // roll right  (:231-235)
     f.u3 = (T)(kp.kP * ((q1 + q3) - (q0 + q2)));      // pitch forward (:237-241)
     f.u4 = (T)(kp.kY * (s01 - s23));                  // yaw cw (:243-247)
+    // Omega: zero in the live model (:135); u4 of the UNSQUARED speeds in attic/mars (:143)
+    f.om = (T)(kp.kOm * (((double)m0 + (double)m1) - ((double)m2 + (double)m3)));
     return f;
 }
 
@@ -274,8 +285,8 @@ __device__ __forceinline__ bool dynamics_update(const KParams<T>& kp, T (&s)[12]
         const T dphi = s[7], dthe = s[9], dpsi = s[11];
         // Eq. 12 (:257-290) with Omega = 0 (:135); the perturbation is added twice (:263-287, :183)
         T d1 = ax, d3 = ay, d5 = netz;
-        T d7 = dpsi * dthe * kp.gphi + f.u2;
-        T d9 = -(dpsi * dphi * kp.gthe + f.u3);
+        T d7 = dpsi * dthe * kp.gphi - kp.jx * dthe * f.om + f.u2;
+        T d9 = -(dpsi * dphi * kp.gthe + kp.jy * dphi * f.om + f.u3);
         T d11 = dthe * dphi * kp.gpsi + f.u4;
         d1 += (T)2 * p[0]; d3 += (T)2 * p[1]; d5 += (T)2 * p[2];
         if constexpr (NP == 6) { d7 += (T)2 * p[3]; d9 += (T)2 * p[4]; d11 += (T)2 * p[5]; }

@@ -93,9 +93,22 @@ typedef struct CopterParams {
     double fps, initial_random_force, out_of_bounds_penalty, max_angle_deg, bounds, initial_altitude;
     /* envs/lander.py:17-23 */
     double target_radius, yaw_penalty_factor, xyz_penalty_factor, dz_max, dz_penalty, inside_radius_bonus;
+    /* alternate vehicle/world model of attic/mars/dynamics/__init__.py (see dynamics_model) */
+    double rho, lift_coefficient;
     int32_t max_steps;
-    int32_t reserved;
+    int32_t dynamics_model;     /* bit set of COPTER_MODEL_*; 0 = the live gym_copter/dynamics model */
 } CopterParams;
+
+/* dynamics_model bits.  The live model (0) is Dynamics.setMotors of gym_copter/dynamics/__init__.py:
+   thrust U1 = B sum(w^2), U2/U3 = L B (...), gyroscopic term Omega = 0 (:135).  The older
+   attic/mars/dynamics/__init__.py:135-164,249-290 differs in two ways that can be switched on
+   separately:
+     COPTER_MODEL_LIFT  rotor lift 0.5 rho S C_L (w L/2)^2 with S = 0.05 L 4 instead of B w^2, and
+                        roll/pitch torques U2/U3 = lift differences WITHOUT the arm length (:146-158);
+     COPTER_MODEL_GYRO  live rotor gyroscopic coupling: Omega = (w0+w1)-(w2+w3) (:143) entering
+                        phi'' as -Jr/Ix theta' Omega and theta'' as -Jr/Iy phi' Omega (:269-283).
+   With G = 3.721 and rho = 0.017 this is the Mars world of attic/mars/dynamics/ingenuity.py:69-71. */
+enum { COPTER_MODEL_LIFT = 1, COPTER_MODEL_GYRO = 2 };
 
 int copter_abi_version(void);
 void copter_default_params(CopterParams* p);

@@ -17,11 +17,11 @@ _VARIANT_ID = {v: i for i, v in enumerate(('Lander3D', 'Lander2D', 'Lander1D', '
 _FIELDS = ('B', 'D', 'M', 'L', 'Ix', 'Iy', 'Iz', 'Jr', 'maxrpm', 'landing_vel_x', 'landing_vel_y',
            'landing_angle', 'G', 'fps', 'initial_random_force', 'out_of_bounds_penalty', 'max_angle_deg',
            'bounds', 'initial_altitude', 'target_radius', 'yaw_penalty_factor', 'xyz_penalty_factor',
-           'dz_max', 'dz_penalty', 'inside_radius_bonus')
+           'dz_max', 'dz_penalty', 'inside_radius_bonus', 'rho', 'lift_coefficient')
 
 
 class _CParams(C.Structure):
-    _fields_ = [(f, C.c_double) for f in _FIELDS] + [('max_steps', C.c_int32), ('reserved', C.c_int32)]
+    _fields_ = [(f, C.c_double) for f in _FIELDS] + [('max_steps', C.c_int32), ('dynamics_model', C.c_int32)]
 
 
 _lib = None
@@ -50,7 +50,8 @@ class CEnvBatch:
         self.variant, self.vid, self.n = variant, _VARIANT_ID[variant], n
         self.obs_size, self.act_size = len(VARIANTS[variant][1]), VARIANTS[variant][2]
         op = params or OracleParams()
-        self.p = _CParams(**{f: float(getattr(op, f)) for f in _FIELDS}, max_steps=int(op.max_steps))
+        self.p = _CParams(**{f: float(getattr(op, f)) for f in _FIELDS}, max_steps=int(op.max_steps),
+                          dynamics_model=int(op.dynamics_model))
         self.seed, self.auto_reset, self.nthreads = seed, auto_reset, nthreads
         self.env_ids = (np.arange(n, dtype=np.uint64) + np.uint64(env_offset) if env_ids is None
                         else np.ascontiguousarray(env_ids, dtype=np.uint64))

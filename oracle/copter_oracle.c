@@ -33,7 +33,8 @@ typedef struct {
     double landing_vel_x, landing_vel_y, landing_angle, G;
     double fps, initial_random_force, out_of_bounds_penalty, max_angle_deg, bounds, initial_altitude;
     double target_radius, yaw_penalty_factor, xyz_penalty_factor, dz_max, dz_penalty, inside_radius_bonus;
-    int32_t max_steps, reserved;
+    double rho, lift_coefficient;
+    int32_t max_steps, dynamics_model;       /* bit 0: lift-model thrust, bit 1: live gyroscopic Omega (attic/mars) */
 } OracleParams;
 
 /* variant tables: Lander3D, Lander2D, Lander1D, Hover3D, Hover2D, Hover1D */
@@ -65,11 +66,20 @@ void oracle_reset_force(uint64_t seed, uint64_t env, uint32_t episode, double sc
 /* dynamics/__init__.py:114-197.  Returns 1 when the call reached :194-197 (perturbation
    cleared, ticks += 1), 0 on the :177 early return. */
 static int set_motors(const OracleParams* p, double* x, int32_t* status, double* pt, const double m[4]) {
-    double o[4];
-    for (int j = 0; j < 4; ++j) { const double w = m[j] * p->maxrpm * M_PI / 30; o[j] = w * w; }   /* :120-124 */
-    const double U1 = p->B * (((o[0] + o[1]) + o[2]) + o[3]);
-    const double U2 = p->L * p->B * ((o[1] + o[2]) - (o[0] + o[3]));
-    const double U3 = p->L * p->B * ((o[1] + o[3]) - (o[0] + o[2]));
+    double o[4], w[4], U1, U2, U3;
+    for (int j = 0; j < 4; ++j) { w[j] = m[j] * p->maxrpm * M_PI / 30; o[j] = w[j] * w[j]; }   /* :120-124 */
+    if (p->dynamics_model & 1) {          /* attic/mars/dynamics/__init__.py:146-158 */
+        double lift[4];
+        const double S = .05 * p->L * 4;
+        for (int j = 0; j < 4; ++j) { const double v = w[j] * p->L / 2; lift[j] = 0.5 * p->rho * S * p->lift_coefficient * (v * v); }
+        U1 = ((lift[0] + lift[1]) + lift[2]) + lift[3];
+        U2 = (lift[1] + lift[2]) - (lift[0] + lift[3]);
+        U3 = (lift[1] + lift[3]) - (lift[0] + lift[2]);
+    } else {
+        U1 = p->B * (((o[0] + o[1]) + o[2]) + o[3]);
+        U2 = p->L * p->B * ((o[1] + o[2]) - (o[0] + o[3]));
+        U3 = p->L * p->B * ((o[1] + o[3]) - (o[0] + o[2]));
+    }
     const double U4 = p->D * ((o[0] + o[1]) - (o[2] + o[3]));
     const double cph = cos(x[6]), cth = cos(x[8]), cps = cos(x[10]);
     const double sph = sin(x[6]), sth = sin(x[8]), sps = sin(x[10]);
@@ -84,7 +94,8 @@ static int set_motors(const OracleParams* p, double* x, int32_t* status, double*
             *status = (x[5] > p->landing_vel_y || fabs(x[3]) > p->landing_vel_x || fabs(x[6]) > p->landing_angle) ? CRASHED : LEVELING;
             return 0;
         }
-        const double dphi = x[7], dthe = x[9], dpsi = x[11], Omega = 0;
+        const double dphi = x[7], dthe = x[9], dpsi = x[11];
+        const double Omega = (p->dynamics_model & 2) ? (w[0] + w[1]) - (w[2] + w[3]) : 0;   /* :135 vs attic/mars :143 */
         double d[12];
         d[0] = x[1]; d[1] = ax + pt[0]; d[2] = x[3]; d[3] = ay + pt[1]; d[4] = x[5]; d[5] = netz + pt[2];
         d[6] = dphi;

@@ -86,6 +86,10 @@ class OracleParams:
     dz_max: float = 10
     dz_penalty: float = 100
     inside_radius_bonus: float = 100
+    # attic/mars/dynamics/__init__.py:83-84,101 and ingenuity.py:55: the alternate vehicle/world model
+    rho: float = 1.225
+    lift_coefficient: float = 0.4
+    dynamics_model: int = 0          # bit 0: lift-model thrust, bit 1: live gyroscopic Omega
 
 
 # ---------------------------------------------------------------------------------------
@@ -198,9 +202,18 @@ class DynamicsBatch:
         # :120-132  motor values -> rad/s -> thrust and torques (Eq. 6)
         om = m * T(p.maxrpm) * T(np.pi) / T(30)
         o = om ** 2
-        U1 = T(p.B) * (((o[:, 0] + o[:, 1]) + o[:, 2]) + o[:, 3])
-        U2 = T(p.L) * T(p.B) * ((o[:, 1] + o[:, 2]) - (o[:, 0] + o[:, 3]))     # :231-235
-        U3 = T(p.L) * T(p.B) * ((o[:, 1] + o[:, 3]) - (o[:, 0] + o[:, 2]))     # :237-241
+        if p.dynamics_model & 1:
+            # attic/mars/dynamics/__init__.py:146-158: rotor lift 0.5 rho S C_L v^2, v = w L/2,
+            # S = .05 L 4 (:100); U2/U3 are lift differences without the arm length
+            S = T(.05) * T(p.L) * T(4)
+            lift = T(0.5) * T(p.rho) * S * T(p.lift_coefficient) * ((om * T(p.L) / T(2)) ** 2)
+            U1 = ((lift[:, 0] + lift[:, 1]) + lift[:, 2]) + lift[:, 3]
+            U2 = (lift[:, 1] + lift[:, 2]) - (lift[:, 0] + lift[:, 3])
+            U3 = (lift[:, 1] + lift[:, 3]) - (lift[:, 0] + lift[:, 2])
+        else:
+            U1 = T(p.B) * (((o[:, 0] + o[:, 1]) + o[:, 2]) + o[:, 3])
+            U2 = T(p.L) * T(p.B) * ((o[:, 1] + o[:, 2]) - (o[:, 0] + o[:, 3]))     # :231-235
+            U3 = T(p.L) * T(p.B) * ((o[:, 1] + o[:, 3]) - (o[:, 0] + o[:, 2]))     # :237-241
         U4 = T(p.D) * ((o[:, 0] + o[:, 1]) - (o[:, 2] + o[:, 3]))             # :243-247
 
         # :139-143  body-Z thrust rotated to NED with the CURRENT angles (:292-302, :339-350)
@@ -240,7 +253,8 @@ class DynamicsBatch:
         pt = self.perturb
         dphi, dthe, dpsi = x[:, 7], x[:, 9], x[:, 11]
         Ix, Iy, Iz, Jr = T(p.Ix), T(p.Iy), T(p.Iz), T(p.Jr)
-        Omega = T(0)
+        # :135 Omega = 0 in the live model; attic/mars/dynamics/__init__.py:143: u4 of the unsquared speeds
+        Omega = ((om[:, 0] + om[:, 1]) - (om[:, 2] + om[:, 3])) if (p.dynamics_model & 2) else T(0)
         d = np.empty_like(x)
         d[:, 0] = x[:, 1]
         d[:, 1] = ax + pt[:, 0]

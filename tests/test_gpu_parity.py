@@ -568,3 +568,44 @@ def test_random_shapes_vs_oracle(pkg):
         assert tr.flips == 0 if f64 else tr.flips <= max(1, n // 50)
 
     check()
+
+
+# ---------------------------------------------------------------------------------------
+# alternate vehicle / world model (attic/mars): lift-model thrust, gyroscopic Omega, Mars G / rho
+# ---------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('dtype', [torch.float64, torch.float32])
+@pytest.mark.parametrize('model', [1, 2, 3])
+def test_mars_model_vs_oracle(pkg, model, dtype):
+    from oracle.copter_oracle import OracleParams
+    world = dict(G=3.721, rho=0.017, lift_coefficient=0.4, dynamics_model=model)
+    N, T = 1500, 400
+    S = .05 * 0.35 * 4
+    if model & 1:
+        hover_w = np.sqrt(1.38 * world['G'] / 4 / (0.5 * world['rho'] * S * 0.4)) / (0.35 / 2)
+    else:
+        hover_w = np.sqrt(1.38 * world['G'] / 4 / 5e-3)
+    hover = hover_w / (15000 * np.pi / 30)
+    env = pkg.CopterVecEnv('Hover3D', N, dtype=dtype, seed=21, **world)
+    orc = EnvBatch('Hover3D', N, params=OracleParams(**world), seed=21)
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(model)
+    tr = Tracker(N, dtype)
+    for t in range(T):
+        a = (hover * (1 + 0.15 * rng.uniform(-1, 1, (N, 4)))).astype(np.float32)
+        obs, r, term, _, _ = env.step(a)
+        o_obs, o_r, o_done, _ = orc.step(a.astype(np.float64))
+        tr.compare(term.cpu().numpy(), r.cpu().numpy(), env.state.cpu().numpy(), obs.cpu().numpy(),
+                   [env.steps.cpu().numpy(), env.status.cpu().numpy()], o_done, o_r, orc.dyn.x, o_obs,
+                   [orc.steps, orc.dyn.status])
+    tr.finish(min_episodes=10)
+    assert np.abs(orc.dyn.x[:, 7]).max() > 1e-3
+    # and through the Dynamics facade (take-off from the ground under Mars gravity)
+    d = pkg.Dynamics(params=world, num=64, dtype=dtype)
+    o = DynamicsBatch(64, OracleParams(**world), np.float64)
+    d.setState(np.zeros(12)); o.set_state(np.zeros((64, 12)))
+    for t in range(150):
+        m = np.clip(1.3 * hover * (1 + 0.05 * rng.uniform(-1, 1, (64, 4))), 0, 1).astype(np.float32).astype(np.float64)
+        d.setMotors(m); o.set_motors(m)
+        assert np.array_equal(d.getStatus().cpu().numpy(), o.status)
+    assert merr(d.state.cpu().numpy(), o.x) <= TOL[dtype] and (o.status == STATUS_AIRBORNE).all()

@@ -41,7 +41,8 @@ def test_params_struct_matches_header_and_reference_constants(lib):
             p.initial_altitude, p.max_steps) == (100, 30, 100, 45, 10, 10, 1000)
     assert (p.target_radius, p.yaw_penalty_factor, p.xyz_penalty_factor, p.dz_max, p.dz_penalty,
             p.inside_radius_bonus) == (2, 50, 25, 10, 100, 100)
-    assert C.sizeof(CopterParams) == 25 * 8 + 8
+    assert (p.rho, p.lift_coefficient, p.dynamics_model) == (1.225, 0.4, 0)
+    assert C.sizeof(CopterParams) == 27 * 8 + 8
     assert [lib.copter_obs_size(v) for v in range(6)] == [10, 6, 2, 12, 6, 2]
     assert [lib.copter_action_size(v) for v in range(6)] == [4, 2, 1, 4, 2, 1]
     assert lib.copter_obs_size(6) == -2 and lib.copter_action_size(-1) == -2
