@@ -195,40 +195,25 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
             }
         }
     } else {
-        // K substeps under one action.  The summed reward telescopes: sum_k (shaping_k - shaping_{k-1})
-        // = shaping_K - shaping_0, so the substep loop only accumulates the shaping numerators
-        // (two adds) and the square roots / quotients are evaluated once, after the loop.  The one
-        // exception is an over-angle ending, whose own step reward is REPLACED by the penalty
-        // (task.py:116-118): then the sum stops at the state before that step, recovered from
-        // a_prev = a_now - na, c_prev = c_now - nc and the previous dz.
-        T na_sum = (T)0, nc_sum = (T)0;
-        Shaping<T> end_sh = pre_sh;                  // shaping at which the telescoped sum ends
-        int executed = 0, mod_cause = 0;
+        // K substeps under one action: the summed reward telescopes (RewardRun, copter_physics.cuh)
+        RewardRun<T> run;
+        run_begin<T, VARIANT>(kp, run, s);
+        T na = (T)0, nc = (T)0, dz_prev = s[5]; int cause = 0;
         constexpr int kUnroll = COPTER_K_UNROLL;
 #pragma unroll kUnroll
         for (int k = 0; k < a.k; ++k) {
             const bool live = valid && !done_any;
             if (__all_sync(0xffffffffu, !live)) break;                 // whole warp finished: idle
             if (live) {
-                const T dz_prev = s[5];
-                T na, nc; bool dn; int cause;
+                dz_prev = s[5];
+                bool dn;
                 env_advance<T, VARIANT>(kp, s, st, steps, forces, pert, na, nc, dn, cause);
                 pert[0] = (T)0; pert[1] = (T)0; pert[2] = (T)0;
-                ++executed;
-                if (dn && (cause & CAUSE_ANGLE)) {
-                    if (Variant<VARIANT>::lander) {
-                        const Shaping<T> now = lander_shaping<T>(kp, s);
-                        end_sh.ra = reward_sqrt(fmax(now.ra * now.ra - na, (T)0));
-                        end_sh.rc = reward_sqrt(fmax(now.rc * now.rc - nc, (T)0));
-                        end_sh.pen = abs_t(dz_prev) > kp.dz_max ? kp.dz_penalty : (T)0;
-                    }
-                } else {
-                    na_sum += na; nc_sum += nc;
-                    if (dn && Variant<VARIANT>::lander) end_sh = lander_shaping<T>(kp, s);
-                }
+                run_step<T>(run, na, nc, cause);
                 if (dn) {
                     done_any = true;
-                    ep_cause = cause; mod_cause = cause;
+                    ep_cause = cause;
+                    total = run_reward<T, VARIANT>(kp, run, s, cause, na, nc, dz_prev);
                     if (STATS) ep_len = steps - 1;                     // `steps` is 1 right after reset (task.py:191,197)
                     if (a.final_obs) {   // terminal observation; rows of unfinished envs stay untouched
 #pragma unroll
@@ -242,20 +227,9 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
             }
         }
         if (valid) {
-            if (Variant<VARIANT>::lander) {
-                if (!done_any) end_sh = lander_shaping<T>(kp, s);
-                total = shaping_delta<T>(kp, pre_sh, na_sum, nc_sum, end_sh);
-                // an over-angle ending contributes its penalty on top of the sum of the earlier steps
-                if (mod_cause & CAUSE_ANGLE) total -= kp.oob_penalty;
-                else total = apply_reward_modifiers<T>(kp, total, mod_cause);
-            } else {
-                // hover: +1 per executed step (attic hover.py:18-21); an over-angle step yields the penalty instead
-                total = (T)executed;
-                if (mod_cause & CAUSE_ANGLE) total += -kp.oob_penalty - (T)1;
-                else total = apply_reward_modifiers<T>(kp, total, mod_cause);
-            }
+            if (!done_any) total = run_reward<T, VARIANT>(kp, run, s, 0, na, nc, dz_prev);
             if (STATS) {
-                n_steps = executed; ret += total;
+                n_steps = run.steps; ret += total;
                 if (done_any) { ep_ret = ret; ret = (T)0; }
             }
         }
@@ -409,7 +383,7 @@ __device__ __forceinline__ void pid_heuristic(const RolloutArgs<T>& a, const T (
 }
 
 template <typename T, int VARIANT, bool STATS, bool PID>
-__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (PID ? 6 : COPTER_F32_CTAS_PER_SM) : 2)
+__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (PID ? 5 : COPTER_F32_CTAS_PER_SM) : 2)
 copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant__ RolloutArgs<T> a) {
     constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A;
     __shared__ __align__(16) float tiles[kWarpsPerBlock][32 * O];
@@ -433,6 +407,11 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
             for (int j = 0; j < 12; ++j) s[j] = (T)0;
         }
         Shaping<T> pre_sh = lander_shaping<T>(kp, s);
+        // without per-step reward output the launch's reward sum telescopes per episode (RewardRun)
+        const bool per_step = a.reward_tn != nullptr;
+        RewardRun<T> run;
+        run_begin<T, VARIANT>(kp, run, s);
+        T na = (T)0, nc = (T)0, dz_prev = s[5];
         PidMem<T> mem[4];
         if constexpr (PID) {
             if (valid) {
@@ -464,11 +443,22 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 3; ++j) pert[j] = f[j] * kp.invM;
                 }
-                T r;
-                env_substep<T, VARIANT>(kp, s, st, steps, forces, pert, pre_sh, r, dn, cause);
-                total += r;
-                if (STATS) ret += r;
-                if (a.reward_tn) a.reward_tn[(int64_t)t * a.n + i] = r;
+                if (per_step) {
+                    T r;
+                    env_substep<T, VARIANT>(kp, s, st, steps, forces, pert, pre_sh, r, dn, cause);
+                    total += r;
+                    if (STATS) ret += r;
+                    a.reward_tn[(int64_t)t * a.n + i] = r;
+                } else {
+                    dz_prev = s[5];
+                    env_advance<T, VARIANT>(kp, s, st, steps, forces, pert, na, nc, dn, cause);
+                    run_step<T>(run, na, nc, cause);
+                    if (dn) {
+                        const T seg = run_reward<T, VARIANT>(kp, run, s, cause, na, nc, dz_prev);
+                        total += seg;
+                        if (STATS) ret += seg;
+                    }
+                }
                 if (a.done_tn) a.done_tn[(int64_t)t * a.n + i] = dn ? 1 : 0;
                 if (dn) {
                     done_any = true;
@@ -478,9 +468,15 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
                         episode = (episode + 1) & 0x7FFFFu;
                         pre_sh = lander_shaping<T>(kp, s);
                     }
+                    run_begin<T, VARIANT>(kp, run, s);
                 }
             }
             if (STATS) flush_episode_stats<T>(a.stats, lane, dn, cause, ep_len, ep_ret, a.ep_return != nullptr);
+        }
+        if (valid && !per_step) {
+            const T seg = run_reward<T, VARIANT>(kp, run, s, 0, na, nc, dz_prev);      // the episode still open at launch end
+            total += seg;
+            if (STATS) ret += seg;
         }
         if (valid) {
             store_state<T>(a.state, a.stride, i, s);

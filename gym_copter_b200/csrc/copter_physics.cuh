@@ -410,6 +410,51 @@ __device__ __forceinline__ void env_substep(const KParams<T>& kp, T (&s)[12], in
     reward = apply_reward_modifiers<T>(kp, reward, cause);
 }
 
+// ------------------------------------------------------------------------------------------
+// Telescoped reward of a run of consecutive steps of ONE episode.  sum_k (shaping_k -
+// shaping_{k-1}) = shaping_end - shaping_start, so a fused loop only accumulates the shaping
+// numerators (two adds per step) and the square roots / quotients are evaluated once, by
+// segment_reward(), when the run ends (episode finished, or last step of the launch).
+// An over-angle ending REPLACES its own step reward by the penalty (task.py:116-118): that
+// step's numerators are then left out of the sums and the run ends at the state before it,
+// recovered from a_prev = a_now - na, c_prev = c_now - nc and the previous dz.
+// Hover variants: +1 per step (attic hover.py:18-21) with the same modifiers.
+// ------------------------------------------------------------------------------------------
+template <typename T> struct RewardRun { Shaping<T> start; T na, nc; int steps; };
+
+template <typename T, int VARIANT>
+__device__ __forceinline__ void run_begin(const KParams<T>& kp, RewardRun<T>& run, const T (&s)[12]) {
+    if (Variant<VARIANT>::lander) run.start = lander_shaping<T>(kp, s);
+    run.na = (T)0; run.nc = (T)0; run.steps = 0;
+}
+
+// one executed step: `cause` is the step's ending cause (0 if the episode goes on)
+template <typename T>
+__device__ __forceinline__ void run_step(RewardRun<T>& run, T na, T nc, int cause) {
+    ++run.steps;
+    if (!(cause & CAUSE_ANGLE)) { run.na += na; run.nc += nc; }
+}
+
+// reward of the run; `s` is the state after its last step (before any auto-reset), `cause` /
+// `na` / `nc` / `dz_prev` belong to that last step
+template <typename T, int VARIANT>
+__device__ __forceinline__ T run_reward(const KParams<T>& kp, const RewardRun<T>& run, const T (&s)[12],
+                                        int cause, T na, T nc, T dz_prev) {
+    const bool replaced = (cause & CAUSE_ANGLE) != 0;
+    if (Variant<VARIANT>::lander) {
+        Shaping<T> end = lander_shaping<T>(kp, s);
+        if (replaced) {
+            end.ra = reward_sqrt(fmax(end.ra * end.ra - na, (T)0));
+            end.rc = reward_sqrt(fmax(end.rc * end.rc - nc, (T)0));
+            end.pen = abs_t(dz_prev) > kp.dz_max ? kp.dz_penalty : (T)0;
+        }
+        const T total = shaping_delta<T>(kp, run.start, run.na, run.nc, end);
+        return replaced ? total - kp.oob_penalty : apply_reward_modifiers<T>(kp, total, cause);
+    }
+    const T total = (T)run.steps;
+    return replaced ? total - (T)1 - kp.oob_penalty : apply_reward_modifiers<T>(kp, total, cause);
+}
+
 template <typename T>
 __device__ __forceinline__ void reset_state(const KParams<T>& kp, T (&s)[12], int& st, int& steps) {
     // envs/task.py:149,164-171,191,197 and dynamics/__init__.py:215-217

@@ -57,10 +57,12 @@ def test_rollout_equals_single_steps_and_oracle(pkg, variant, source, dtype):
     within the path's tolerance."""
     n, T, seed = 1500, 120, 77
     fused = pkg.CopterVecEnv(variant, n, dtype=dtype, seed=seed, track_returns=True)
+    lean = pkg.CopterVecEnv(variant, n, dtype=dtype, seed=seed, track_returns=True)     # no per-step rewards: telescoped sums
     single = pkg.CopterVecEnv(variant, n, dtype=dtype, seed=seed, track_returns=True)
     orc = EnvBatch(variant, n, seed=seed)
-    fused.reset(); single.reset(); orc.reset()
+    fused.reset(); lean.reset(); single.reset(); orc.reset()
     out = fused.rollout(T, source=source, record_rewards=True, record_dones=True, record_actions=True)
+    out_lean = lean.rollout(T, source=source, record_dones=True)
     acts = out['actions']
     tol = 1e-9 if dtype == torch.float64 else 1e-4
     ulps = 1e-12 if dtype == torch.float64 else 1e-5
@@ -81,7 +83,14 @@ def test_rollout_equals_single_steps_and_oracle(pkg, variant, source, dtype):
     assert merr(fused.state.cpu().numpy(), single.state.cpu().numpy()) <= ulps
     assert merr(out['obs'].cpu().numpy(), single.obs.cpu().numpy()) <= max(ulps, 1.2e-7)
     assert merr(out['reward_sum'].cpu().numpy(), rsum.cpu().numpy()) <= 10 * ulps
+    # the telescoped path: same states and flags, reward sums equal up to summation order
+    assert torch.equal(out_lean['dones'], out['dones']) and torch.equal(lean.meta, fused.meta)
+    assert merr(lean.state.cpu().numpy(), fused.state.cpu().numpy()) <= ulps
+    assert merr(out_lean['reward_sum'].cpu().numpy(), rsum.cpu().numpy()) <= (1e-10 if dtype == torch.float64 else 1e-4)
+    ls = lean.stats()
     fs, ss = fused.stats(), single.stats()
+    assert ls['episodes'] == ss['episodes'] and ls['length_sum'] == ss['length_sum']
+    assert abs(ls['return_sum'] - ss['return_sum']) <= 1e-5 * max(1.0, abs(ss['return_sum']))
     for k in ('episodes', 'length_sum', 'landed', 'bonus', 'crashed', 'oob', 'angle', 'timeout', 'env_steps'):
         assert fs[k] == ss[k], k
     assert abs(fs['return_sum'] - ss['return_sum']) <= 1e-6 * max(1.0, abs(ss['return_sum']))
