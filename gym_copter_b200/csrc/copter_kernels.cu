@@ -497,6 +497,117 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Policy-in-the-loop rollout in ONE launch (BASELINE.json configs[4]): for
+// n_steps steps, each warp evaluates the tanh MLP policy for its 32 envs (policy_forward_warp,
+// copter_policy.cuh) from the state its lanes hold in registers, and every lane then advances
+// its own env by one reference step with the resulting command.  State, flight status and the
+// running shaping never touch HBM between steps; what leaves the SM per env-step is the row t
+// of the [T, N] rollout buffers the learner asks for.  Step for step identical to
+// copter_policy_mlp_f32 followed by copter_step_f32 (k = 1), n_steps times.
+// ------------------------------------------------------------------------------------------
+struct PolicyRolloutArgs {
+    float* state; uint32_t* meta; float* obs; float* reward_sum; uint8_t* done_any;
+    const float* init_force; float* ep_return; double* stats;
+    float* reward_tn; uint8_t* done_tn; float* action_tn; float* obs_tn;
+    int64_t n, stride, env_offset; uint64_t seed; int n_steps, auto_reset;
+    PolicyWeights w;
+};
+
+#ifndef COPTER_POLICY_ROLLOUT_CTAS_PER_SM
+#define COPTER_POLICY_ROLLOUT_CTAS_PER_SM 5   // measured (tools/sweep_policy.py): 3: 0.413, 4: 0.420, 5: 0.400, 6: 0.425 ms per env-step
+#endif
+
+template <int VARIANT, bool STATS>
+__global__ void __launch_bounds__(128, COPTER_POLICY_ROLLOUT_CTAS_PER_SM)
+copter_policy_rollout_kernel(const __grid_constant__ KParams<float> kp, const __grid_constant__ PolicyRolloutArgs a) {
+    using T = float;
+    static_assert(kBlock == 128, "policy kernels are written for 4 warps per CTA");
+    constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A, FIRST = Variant<VARIANT>::first;
+    __shared__ __align__(16) PolicySmem sm;
+    __shared__ __align__(16) PolicyWarpTile wtile[4];
+    __shared__ __align__(16) float tiles[4][32 * O];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    policy_load_weights<O, A>(sm, a.w);
+    __syncthreads();
+    if (STATS) credit_env_steps(a.stats, a.n, a.n_steps);
+
+    const int64_t n_tiles = (a.n + kBlock - 1) / kBlock;
+    for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+        const int64_t row0 = tile_id * kBlock + warp * 32, i = row0 + lane;
+        if (row0 >= a.n) continue;                                   // warp-uniform
+        const bool valid = i < a.n;
+        const int rows = (int)min((int64_t)32, a.n - row0);
+        T s[12];
+        int st = ST_LANDED, steps = 1; uint32_t episode = 0;
+        T total = (T)0, ret = (T)0; bool done_any = false;
+        if (valid) {
+            load_state<T>(a.state, a.stride, i, s);
+            const uint32_t mw = a.meta[i];
+            st = (int)(mw & 3u); steps = (int)((mw >> 2) & 2047u); episode = mw >> 13;
+            if (STATS && a.ep_return) ret = a.ep_return[i];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) s[j] = (T)0;
+        }
+        Shaping<T> pre_sh = lander_shaping<T>(kp, s);
+        for (int t = 0; t < a.n_steps; ++t) {
+            // the observation the policy acts on at step t
+            if (a.obs_tn) write_obs_rows<VARIANT, T>(a.obs_tn + (int64_t)t * a.n * O, tiles[warp], lane, row0, rows, s);
+            T act[A];
+            policy_forward_warp<FIRST, O, A>(sm, wtile[warp], lane, s, a.w.out_scale, a.w.out_offset, act);
+            bool dn = false; int cause = 0, ep_len = 0; T ep_ret = (T)0;
+            if (valid) {
+                T m[4];
+                if (a.action_tn) {
+                    T* row = a.action_tn + ((int64_t)t * a.n + i) * A;
+                    if constexpr (A == 4) *reinterpret_cast<float4*>(row) = make_float4(act[0], act[1], act[2], act[3]);
+                    else if constexpr (A == 2) *reinterpret_cast<float2*>(row) = make_float2(act[0], act[1]);
+                    else row[0] = act[0];
+                }
+#pragma unroll
+                for (int j = 0; j < A; ++j) act[j] = fmin(fmax(act[j], (T)0), (T)1);         // task.py:91
+                if constexpr (A == 4) { m[0] = act[0]; m[1] = act[1]; m[2] = act[2]; m[3] = act[3]; }
+                else if constexpr (A == 2) { m[0] = act[0]; m[1] = act[1]; m[2] = act[1]; m[3] = act[0]; }
+                else { m[0] = m[1] = m[2] = m[3] = act[0]; }
+                const Forces<T> forces = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
+                T pert[3] = {(T)0, (T)0, (T)0};
+                if (steps == 1) {
+                    T f[3];
+                    if (a.init_force) { f[0] = a.init_force[3 * i]; f[1] = a.init_force[3 * i + 1]; f[2] = a.init_force[3 * i + 2]; }
+                    else reset_force<T>(kp, a.seed, (uint64_t)(a.env_offset + i), episode, f);
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) pert[j] = f[j] * kp.invM;
+                }
+                T r;
+                env_substep<T, VARIANT>(kp, s, st, steps, forces, pert, pre_sh, r, dn, cause);
+                total += r;
+                if (STATS) ret += r;
+                if (a.reward_tn) a.reward_tn[(int64_t)t * a.n + i] = r;
+                if (a.done_tn) a.done_tn[(int64_t)t * a.n + i] = dn ? 1 : 0;
+                if (dn) {
+                    done_any = true;
+                    if (STATS) { ep_len = steps - 1; ep_ret = ret; ret = (T)0; }
+                    if (a.auto_reset) {
+                        reset_state<T>(kp, s, st, steps);
+                        episode = (episode + 1) & 0x7FFFFu;
+                        pre_sh = lander_shaping<T>(kp, s);
+                    }
+                }
+            }
+            if (STATS) flush_episode_stats<T>(a.stats, lane, dn, cause, ep_len, ep_ret, a.ep_return != nullptr);
+        }
+        if (valid) {
+            store_state<T>(a.state, a.stride, i, s);
+            a.meta[i] = (uint32_t)st | ((uint32_t)steps << 2) | (episode << 13);
+            if (a.reward_sum) a.reward_sum[i] = total;
+            if (a.done_any) a.done_any[i] = done_any ? 1 : 0;
+            if (STATS && a.ep_return) a.ep_return[i] = ret;
+        }
+        if (a.obs) write_obs_rows<VARIANT, T>(a.obs, tiles[warp], lane, row0, rows, s);
+    }
+}
+
 template <typename T, int VARIANT>
 __global__ void __launch_bounds__(kBlock)
 copter_reset_kernel(const __grid_constant__ KParams<T> kp, T* state, uint32_t* meta, float* obs, T* ep_return, int64_t n, int64_t stride) {
@@ -741,19 +852,41 @@ int launch_reset_force(const CopterParams* p, T* out, const uint32_t* episode, i
     return (int)cudaGetLastError();
 }
 
-template <int VARIANT>
-int launch_policy_v(const PolicyArgs& a, cudaStream_t s) {
-    using V = Variant<VARIANT>;
-    auto* kernel = copter_mlp_policy_kernel<V::first, V::O, V::A>;
+// persistent grids for the policy kernels: the weights are converted to bf16 fragments once per CTA
+template <auto Kernel>
+int persistent_grid_for(int64_t n) {
     static int per_sm = 0;
     if (per_sm == 0) {
         int q = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kernel, 128, 0) != cudaSuccess || q <= 0) q = 4;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, Kernel, 128, 0) != cudaSuccess || q <= 0) q = 4;
         per_sm = q;
     }
-    const int64_t tiles = (a.n + 127) / 128, cap = (int64_t)sm_count() * per_sm;    // persistent: weights load once per CTA
-    kernel<<<(int)(tiles < cap ? tiles : cap), 128, 0, s>>>(a);
+    const int64_t tiles = (n + 127) / 128, cap = (int64_t)sm_count() * per_sm;
+    return (int)(tiles < cap ? tiles : cap);
+}
+
+template <int VARIANT>
+int launch_policy_v(const PolicyArgs& a, cudaStream_t s) {
+    using V = Variant<VARIANT>;
+    copter_mlp_policy_kernel<V::first, V::O, V::A><<<persistent_grid_for<copter_mlp_policy_kernel<V::first, V::O, V::A>>(a.n), 128, 0, s>>>(a);
     return (int)cudaGetLastError();
+}
+
+template <int VARIANT>
+int launch_policy_rollout_v(const KParams<float>& kp, const PolicyRolloutArgs& a, cudaStream_t s) {
+    if (a.stats) copter_policy_rollout_kernel<VARIANT, true><<<persistent_grid_for<copter_policy_rollout_kernel<VARIANT, true>>(a.n), 128, 0, s>>>(kp, a);
+    else         copter_policy_rollout_kernel<VARIANT, false><<<persistent_grid_for<copter_policy_rollout_kernel<VARIANT, false>>(a.n), 128, 0, s>>>(kp, a);
+    return (int)cudaGetLastError();
+}
+
+bool policy_ok(const CopterMlpPolicy* m) {
+    return m && m->w1 && m->b1 && m->w2 && m->b2 && m->w3 && m->b3;
+}
+PolicyWeights policy_weights(const CopterMlpPolicy* m) {
+    PolicyWeights w;
+    w.w1 = m->w1; w.b1 = m->b1; w.w2 = m->w2; w.b2 = m->b2; w.w3 = m->w3; w.b3 = m->b3;
+    w.out_scale = m->out_scale; w.out_offset = m->out_offset;
+    return w;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -893,12 +1026,12 @@ int copter_policy_mlp_f32(const void* state, int64_t state_stride, int64_t n, in
     if (!state || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !action) return COPTER_E_ARG;
     if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
     if (n < 0 || hidden != kPolH || (state_stride > 0 && state_stride < n)) return COPTER_E_RANGE;
-    if (!aligned16(state)) return COPTER_E_ALIGN;
+    if (!aligned16(state) || !aligned16(action)) return COPTER_E_ALIGN;
     if (n == 0) return 0;
     PolicyArgs a;
     a.state = (const float*)state; a.stride = state_stride > 0 ? state_stride : n; a.n = n;
-    a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.w3 = w3; a.b3 = b3;
-    a.out_scale = out_scale; a.out_offset = out_offset; a.action = action;
+    a.w.w1 = w1; a.w.b1 = b1; a.w.w2 = w2; a.w.b2 = b2; a.w.w3 = w3; a.w.b3 = b3;
+    a.w.out_scale = out_scale; a.w.out_offset = out_offset; a.action = action;
     cudaStream_t s = (cudaStream_t)stream;
     switch (variant) {
         case COPTER_LANDER3D: return launch_policy_v<COPTER_LANDER3D>(a, s);
@@ -907,6 +1040,35 @@ int copter_policy_mlp_f32(const void* state, int64_t state_stride, int64_t n, in
         case COPTER_HOVER3D:  return launch_policy_v<COPTER_HOVER3D>(a, s);
         case COPTER_HOVER2D:  return launch_policy_v<COPTER_HOVER2D>(a, s);
         default:              return launch_policy_v<COPTER_HOVER1D>(a, s);
+    }
+}
+
+int copter_policy_rollout_f32(const CopterParams* p, const CopterBuffers* b, const CopterMlpPolicy* policy, int64_t n,
+                              int64_t env_offset, uint64_t seed, int n_steps, int variant, int flags,
+                              float* reward_tn, uint8_t* done_tn, float* action_tn, float* obs_tn, void* stream) {
+    int e = check_params(p);
+    if (e) return e;
+    if (!b || !b->state || !b->meta || !policy_ok(policy)) return COPTER_E_ARG;
+    if (n < 0 || env_offset < 0 || n_steps < 1 || policy->hidden != kPolH || (b->state_stride > 0 && b->state_stride < n)) return COPTER_E_RANGE;
+    if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
+    if (!aligned16(b->state) || (b->obs && !aligned16(b->obs)) || (action_tn && !aligned16(action_tn)) || (obs_tn && !aligned16(obs_tn))) return COPTER_E_ALIGN;
+    if (n == 0) return 0;
+    const KParams<float> kp = make_kparams<float>(*p);
+    PolicyRolloutArgs a;
+    a.state = (float*)b->state; a.meta = b->meta; a.obs = b->obs; a.reward_sum = (float*)b->reward; a.done_any = b->done;
+    a.init_force = (const float*)b->init_force; a.ep_return = (float*)b->ep_return; a.stats = b->stats;
+    a.reward_tn = reward_tn; a.done_tn = done_tn; a.action_tn = action_tn; a.obs_tn = obs_tn;
+    a.n = n; a.stride = b->state_stride > 0 ? b->state_stride : n; a.env_offset = env_offset; a.seed = seed;
+    a.n_steps = n_steps; a.auto_reset = (flags & COPTER_F_AUTO_RESET) ? 1 : 0;
+    a.w = policy_weights(policy);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (variant) {
+        case COPTER_LANDER3D: return launch_policy_rollout_v<COPTER_LANDER3D>(kp, a, s);
+        case COPTER_LANDER2D: return launch_policy_rollout_v<COPTER_LANDER2D>(kp, a, s);
+        case COPTER_LANDER1D: return launch_policy_rollout_v<COPTER_LANDER1D>(kp, a, s);
+        case COPTER_HOVER3D:  return launch_policy_rollout_v<COPTER_HOVER3D>(kp, a, s);
+        case COPTER_HOVER2D:  return launch_policy_rollout_v<COPTER_HOVER2D>(kp, a, s);
+        default:              return launch_policy_rollout_v<COPTER_HOVER1D>(kp, a, s);
     }
 }
 

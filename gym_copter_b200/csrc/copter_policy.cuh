@@ -1,18 +1,22 @@
 // copter_policy.cuh -- the small tanh MLP policy of BASELINE.json configs[4] (O -> 64 -> 64 -> A,
-// SURVEY.md 8d "config 5") as ONE kernel that reads the env's fp32 state planes in place and
-// writes the action rows the step kernel consumes.  In PyTorch this policy costs 4.2 ms per
-// step for 2^23 envs (three GEMMs with [N,64] intermediates through HBM plus separate tanh
-// passes) against 0.21 ms for the env step itself; here the 64-wide activations never leave
-// registers.
+// SURVEY.md 8d "config 5") evaluated by a warp for its 32 envs straight from the fp32 state each
+// lane holds in registers.  Two kernels use it (copter_kernels.cu): copter_mlp_policy_kernel
+// (state planes -> action rows, for policy-in-the-loop rollouts that step with copter_step_*)
+// and copter_policy_rollout_kernel (policy + env step for T steps in ONE launch, the state
+// never leaving registers).  In PyTorch this policy costs 4.2 ms per step for 2^23 envs (three
+// GEMMs with [N,64] intermediates through HBM plus separate tanh passes) against 0.21 ms for
+// the env step itself.
 //
-// One warp = 32 envs = two 16-row tiles of warp-level tensor-core MMAs
-// (mma.sync.m16n8k16, bf16 inputs, fp32 accumulation).  The accumulator fragment of layer L is
-// exactly the A-operand fragment of layer L+1 (n-tiles 2k, 2k+1 -> k-tile k), so between layers
-// there is only bias + tanh (MUFU.TANH) + bf16 packing, all in registers.  The kernel is bound
-// by the MUFU (XU) pipe -- 132 tanh per env; ncu: XU 62 %, tensor pipe 40 %, LSU 29 % busy, HBM
-// idle -- so the warp-level MMA is enough here: tcgen05/TMEM would not move the XU floor.
-// Weights live in shared memory as bf16, rows padded by 8 elements so that the B-fragment loads
-// of a warp hit 32 distinct banks.  Persistent CTAs (weights are loaded once per CTA).
+// One warp = 32 envs = two 16-row tiles of warp-level tensor-core MMAs (mma.sync.m16n8k16,
+// bf16 inputs, fp32 accumulation).  The accumulator fragment of layer L is exactly the
+// A-operand fragment of layer L+1 (n-tiles 2k, 2k+1 -> k-tile k), so between layers there is
+// only tanh (MUFU.TANH) + bf16 packing, all in registers; the bias enters as the accumulator's
+// initial value, and layer 3 consumes each pair of layer-2 n-tiles as soon as it exists, so the
+// second hidden activation is never held whole.  Both row tiles share every weight fragment
+// load.  The kernel is bound by the MUFU (XU) pipe -- 132 tanh per env -- which is why the
+// warp-level MMA is enough here: tcgen05/TMEM would not move the XU floor.
+// Weights live in shared memory as bf16 in FRAGMENT ORDER (the 64-/128-bit word a lane needs
+// for an MMA sits at [tile][lane]), so B operands arrive as conflict-free LDS.64 / LDS.128.
 #pragma once
 
 #include <cuda_bf16.h>
@@ -22,14 +26,24 @@ namespace copter {
 constexpr int kPolH = 64;            // hidden width
 constexpr int kPolIn = 16;           // observation padded to one k-tile
 constexpr int kPolOut = 8;           // actions padded to one n-tile
-constexpr int kPolW1Stride = kPolIn + 8, kPolW2Stride = kPolH + 8, kPolXStride = kPolIn + 8;
+constexpr int kPolXStride = kPolIn + 8;   // bf16 elements per env row of the input tile (48 B: ldmatrix rows hit distinct banks)
+
+// torch.nn.Linear layouts: W[out][in], b[out], fp32 device memory
+struct PolicyWeights {
+    const float *w1, *b1, *w2, *b2, *w3, *b3;
+    float out_scale, out_offset;     // action = out_offset + out_scale * tanh(.)
+};
 
 struct PolicySmem {
-    __nv_bfloat16 w1[kPolH * kPolW1Stride];      // [64][16 (+8)]
-    __nv_bfloat16 w2[kPolH * kPolW2Stride];      // [64][64 (+8)]
-    __nv_bfloat16 w3[kPolOut * kPolW2Stride];    // [ 8][64 (+8)]
-    float b1[kPolH], b2[kPolH], b3[kPolOut];
-    __nv_bfloat16 x[4][32 * kPolXStride];        // per warp: 32 envs x 16 inputs (+8)
+    uint2 w1[8][32];                 // layer 1: [n-tile][lane] -> {b0, b1} of the single k-tile
+    uint4 w2[8][2][32];              // layer 2: [n-tile][k-tile pair][lane] -> {b0, b1 of k-tile 2p, b0, b1 of k-tile 2p+1}
+    uint4 w3[2][32];                 // layer 3: [k-tile pair][lane]
+    float4 b1[8][4], b2[8][4], b3[4];   // [n-tile][t] -> bias of columns 2t, 2t+1, twice: an accumulator quad as loaded
+};
+// per-warp scratch: the bf16 input rows (ldmatrix source) and the fp32 pre-activation action rows
+struct PolicyWarpTile {
+    __nv_bfloat16 x[32 * kPolXStride];
+    float act[32 * 4];
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -41,9 +55,9 @@ __device__ __forceinline__ float tanh_fast(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// hidden activations: bias add in fp32, then tanh.  COPTER_POLICY_TANH_BF16X2 (A/B knob) rounds
-// the pair to bf16 first and uses tanh.approx.bf16x2; it is not faster on B200 (the packed form
-// costs two XU slots) and is less accurate, so the default is two fp32 MUFU.TANH.
+// hidden activations.  COPTER_POLICY_TANH_BF16X2 (A/B knob) rounds the pair to bf16 first and
+// uses tanh.approx.bf16x2; it is not faster on B200 (the packed form costs two XU slots) and is
+// less accurate, so the default is two fp32 MUFU.TANH.
 #ifndef COPTER_POLICY_TANH_BF16X2
 #define COPTER_POLICY_TANH_BF16X2 0      // measured on B200: 0.435 ms vs 0.412 ms for two fp32 tanh (2^23 envs)
 #endif
@@ -56,57 +70,181 @@ __device__ __forceinline__ uint32_t tanh_pack(float lo, float hi) {
     return pack_bf16(tanh_fast(lo), tanh_fast(hi));
 #endif
 }
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+// D = A B + D
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// D = A B + C with C = the bias quad (x, y, x, y: the lane's two columns for both row halves) exactly
+// as one LDS.128 delivers it, so no register is moved to build the accumulator
+__device__ __forceinline__ void mma_bf16_bias(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, const float4& c) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c.x), "f"(c.y), "f"(c.z), "f"(c.w));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(smem_row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+// Weights -> shared memory: bf16, zero-padded to the tile shapes, in mma.m16n8k16 B-fragment
+// order.  For the lane (g = lane / 4, t = lane % 4), n-tile nt and k-tile kt the fragment is
+//   b0 = W[8 nt + g][16 kt + 2t, +1],  b1 = W[8 nt + g][16 kt + 8 + 2t, +1]      (B[k][n] = W[n][k]).
+// Call with the whole CTA, then __syncthreads().
+template <int OBS, int ACT>
+__device__ __forceinline__ void policy_load_weights(PolicySmem& sm, const PolicyWeights& w) {
+    const auto w1 = [&](int n, int k) { return k < OBS ? w.w1[n * OBS + k] : 0.0f; };
+    const auto w2 = [&](int n, int k) { return w.w2[n * kPolH + k]; };
+    const auto w3 = [&](int n, int k) { return n < ACT ? w.w3[n * kPolH + k] : 0.0f; };
+    for (int e = threadIdx.x; e < 8 * 32; e += blockDim.x) {
+        const int nt = e >> 5, lane = e & 31, n = 8 * nt + (lane >> 2), k = 2 * (lane & 3);
+        sm.w1[nt][lane] = make_uint2(pack_bf16(w1(n, k), w1(n, k + 1)), pack_bf16(w1(n, k + 8), w1(n, k + 9)));
+    }
+    for (int e = threadIdx.x; e < 8 * 2 * 32; e += blockDim.x) {
+        const int nt = e >> 6, kp = (e >> 5) & 1, lane = e & 31, n = 8 * nt + (lane >> 2), k = 32 * kp + 2 * (lane & 3);
+        sm.w2[nt][kp][lane] = make_uint4(pack_bf16(w2(n, k), w2(n, k + 1)), pack_bf16(w2(n, k + 8), w2(n, k + 9)),
+                                         pack_bf16(w2(n, k + 16), w2(n, k + 17)), pack_bf16(w2(n, k + 24), w2(n, k + 25)));
+    }
+    for (int e = threadIdx.x; e < 2 * 32; e += blockDim.x) {
+        const int kp = e >> 5, lane = e & 31, n = lane >> 2, k = 32 * kp + 2 * (lane & 3);
+        sm.w3[kp][lane] = make_uint4(pack_bf16(w3(n, k), w3(n, k + 1)), pack_bf16(w3(n, k + 8), w3(n, k + 9)),
+                                     pack_bf16(w3(n, k + 16), w3(n, k + 17)), pack_bf16(w3(n, k + 24), w3(n, k + 25)));
+    }
+    for (int e = threadIdx.x; e < 8 * 4; e += blockDim.x) {
+        const int c = 8 * (e >> 2) + 2 * (e & 3);
+        sm.b1[e >> 2][e & 3] = make_float4(w.b1[c], w.b1[c + 1], w.b1[c], w.b1[c + 1]);
+        sm.b2[e >> 2][e & 3] = make_float4(w.b2[c], w.b2[c + 1], w.b2[c], w.b2[c + 1]);
+    }
+    if (threadIdx.x < 4) {
+        const int c = 2 * threadIdx.x;
+        const float x = c < ACT ? w.b3[c] : 0.0f, y = c + 1 < ACT ? w.b3[c + 1] : 0.0f;
+        sm.b3[threadIdx.x] = make_float4(x, y, x, y);
+    }
+}
+
+// The policy for the 32 envs of a warp.  `s` is this lane's env state (zeros for a lane without
+// an env); the observation is components FIRST .. FIRST+OBS-1.  Returns the lane's action row
+// (before the env's clip).  Warp-uniform call: every lane must take part.
+template <int FIRST, int OBS, int ACT>
+__device__ __forceinline__ void policy_forward_warp(const PolicySmem& sm, PolicyWarpTile& wt, int lane, const float (&s)[12],
+                                                    float out_scale, float out_offset, float (&action)[ACT]) {
+    static_assert(OBS <= kPolIn && ACT <= 4 && FIRST + OBS <= 12, "policy tile shapes");
+    const int g = lane >> 2, t = lane & 3;
+
+    // this lane's observation -> 16 bf16 inputs (zero padded) -> the warp's input tile
+    uint32_t xin[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float lo = (2 * j < OBS) ? s[(FIRST + 2 * j) % 12] : 0.0f;
+        const float hi = (2 * j + 1 < OBS) ? s[(FIRST + 2 * j + 1) % 12] : 0.0f;
+        xin[j] = pack_bf16(lo, hi);
+    }
+    uint4* xrow = reinterpret_cast<uint4*>(wt.x + lane * kPolXStride);
+    xrow[0] = make_uint4(xin[0], xin[1], xin[2], xin[3]);
+    xrow[1] = make_uint4(xin[4], xin[5], xin[6], xin[7]);
+    __syncwarp();
+
+    // layer-1 A fragments of both row tiles: four 8x8 matrices each (rows 0-7 / 8-15 x k 0-7 / 8-15)
+    uint32_t a1[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int j = lane >> 3, r = lane & 7;
+        ldmatrix_x4(a1[mt], wt.x + (16 * mt + 8 * (j & 1) + r) * kPolXStride + 8 * (j >> 1));
+    }
+
+    // ---- layer 1: [32 x 16] x [16 x 64], activations kept as the A fragments of layer 2 ----
+    uint32_t h[2][4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const uint2 b = sm.w1[nt][lane];
+        const float4 bias = sm.b1[nt][t];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            float c[4];
+            mma_bf16_bias(c, a1[mt], b.x, b.y, bias);
+            h[mt][nt >> 1][(nt & 1) * 2 + 0] = tanh_pack(c[0], c[1]);      // rows g
+            h[mt][nt >> 1][(nt & 1) * 2 + 1] = tanh_pack(c[2], c[3]);      // rows g + 8
+        }
+    }
+
+    // ---- layer 2: [32 x 64] x [64 x 64], two n-tiles at a time, each pair feeding one k-tile of
+    // ---- layer 3: [32 x 64] x [64 x 8]
+    float c3[2][4];
+#pragma unroll
+    for (int kt3 = 0; kt3 < 4; ++kt3) {
+        uint32_t a3[2][4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int nt = 2 * kt3 + half;
+            const float4 bias = sm.b2[nt][t];
+            float c[2][4];
+#pragma unroll
+            for (int kp = 0; kp < 2; ++kp) {
+                const uint4 b = sm.w2[nt][kp][lane];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    if (kp == 0) mma_bf16_bias(c[mt], h[mt][0], b.x, b.y, bias);
+                    else         mma_bf16(c[mt], h[mt][2], b.x, b.y);
+                    mma_bf16(c[mt], h[mt][2 * kp + 1], b.z, b.w);
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                a3[mt][half * 2 + 0] = tanh_pack(c[mt][0], c[mt][1]);
+                a3[mt][half * 2 + 1] = tanh_pack(c[mt][2], c[mt][3]);
+            }
+        }
+        const uint4 b = sm.w3[kt3 >> 1][lane];
+        const uint32_t b0 = (kt3 & 1) ? b.z : b.x, b1 = (kt3 & 1) ? b.w : b.y;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            if (kt3 == 0) mma_bf16_bias(c3[mt], a3[mt], b0, b1, sm.b3[t]);
+            else          mma_bf16(c3[mt], a3[mt], b0, b1);
+        }
+    }
+
+    // lanes t < 2 hold columns 2t, 2t+1 (< 4) of rows g and g + 8 of each row tile: hand every
+    // env's pre-activation row back to its own lane, which applies the output tanh once
+    if (t < 2) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            *reinterpret_cast<float2*>(wt.act + (16 * mt + g) * 4 + 2 * t) = make_float2(c3[mt][0], c3[mt][1]);
+            *reinterpret_cast<float2*>(wt.act + (16 * mt + g + 8) * 4 + 2 * t) = make_float2(c3[mt][2], c3[mt][3]);
+        }
+    }
+    __syncwarp();
+    const float4 pre = *reinterpret_cast<const float4*>(wt.act + lane * 4);
+    const float p[4] = {pre.x, pre.y, pre.z, pre.w};
+#pragma unroll
+    for (int j = 0; j < ACT; ++j) action[j] = fmaf(out_scale, tanh_fast(p[j]), out_offset);
+    __syncwarp();
 }
 
 struct PolicyArgs {
     const float* state; int64_t stride, n;           // fp32 state planes [3][stride][4]
-    const float *w1, *b1, *w2, *b2, *w3, *b3;        // torch.nn.Linear layouts: W[out][in], b[out]
-    float out_scale, out_offset;                     // action = out_offset + out_scale * tanh(.)
+    PolicyWeights w;
     float* action;                                   // [n][act]
 };
 
-// FIRST / OBS / ACT: observation window into the 12-state and action size of the env variant.
 #ifndef COPTER_POLICY_CTAS_PER_SM
-#define COPTER_POLICY_CTAS_PER_SM 3
+#define COPTER_POLICY_CTAS_PER_SM 5      // measured (tools/sweep_policy.py, 2^23 envs): 3: 0.386, 4: 0.373, 5: 0.359, 6: 0.368 ms
 #endif
+
+// state planes -> action rows.  Persistent CTAs: the weights are converted once per CTA.
 template <int FIRST, int OBS, int ACT>
 __global__ void __launch_bounds__(128, COPTER_POLICY_CTAS_PER_SM)
 copter_mlp_policy_kernel(const __grid_constant__ PolicyArgs a) {
-    static_assert(OBS <= kPolIn && ACT <= kPolOut && FIRST + OBS <= 12, "policy tile shapes");
     __shared__ __align__(16) PolicySmem sm;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-
-    // weights -> shared memory (bf16), zero-padded to the tile shapes
-    for (int e = threadIdx.x; e < kPolH * kPolW1Stride; e += blockDim.x) {
-        const int r = e / kPolW1Stride, c = e % kPolW1Stride;
-        sm.w1[e] = __float2bfloat16(c < OBS ? a.w1[r * OBS + c] : 0.0f);
-    }
-    for (int e = threadIdx.x; e < kPolH * kPolW2Stride; e += blockDim.x) {
-        const int r = e / kPolW2Stride, c = e % kPolW2Stride;
-        sm.w2[e] = __float2bfloat16(c < kPolH ? a.w2[r * kPolH + c] : 0.0f);
-    }
-    for (int e = threadIdx.x; e < kPolOut * kPolW2Stride; e += blockDim.x) {
-        const int r = e / kPolW2Stride, c = e % kPolW2Stride;
-        sm.w3[e] = __float2bfloat16((r < ACT && c < kPolH) ? a.w3[r * kPolH + c] : 0.0f);
-    }
-    for (int e = threadIdx.x; e < kPolH; e += blockDim.x) { sm.b1[e] = a.b1[e]; sm.b2[e] = a.b2[e]; }
-    if (threadIdx.x < kPolOut) sm.b3[threadIdx.x] = threadIdx.x < ACT ? a.b3[threadIdx.x] : 0.0f;
+    __shared__ __align__(16) PolicyWarpTile wtile[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    policy_load_weights<OBS, ACT>(sm, a.w);
     __syncthreads();
-
-    __nv_bfloat16* x = sm.x[warp];
-    const uint32_t* w1 = reinterpret_cast<const uint32_t*>(sm.w1);
-    const uint32_t* w2 = reinterpret_cast<const uint32_t*>(sm.w2);
-    const uint32_t* w3 = reinterpret_cast<const uint32_t*>(sm.w3);
-    const uint32_t* xw = reinterpret_cast<const uint32_t*>(x);
 
     const int64_t n_warp_tiles = (a.n + 31) / 32;
     for (int64_t wt = (int64_t)blockIdx.x * 4 + warp; wt < n_warp_tiles; wt += (int64_t)gridDim.x * 4) {
-        const int64_t row0 = wt * 32, i = row0 + lane;
-        // this lane's env: 12 state components -> 16 bf16 inputs (observation window, zero padded)
+        const int64_t i = wt * 32 + lane;
         float s[12];
         if (i < a.n) {
             const float4* planes = reinterpret_cast<const float4*>(a.state);
@@ -119,64 +257,13 @@ copter_mlp_policy_kernel(const __grid_constant__ PolicyArgs a) {
 #pragma unroll
             for (int j = 0; j < 12; ++j) s[j] = 0.0f;
         }
-        uint32_t xin[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float lo = (2 * j < OBS) ? s[(FIRST + 2 * j) % 12] : 0.0f;
-            const float hi = (2 * j + 1 < OBS) ? s[(FIRST + 2 * j + 1) % 12] : 0.0f;
-            xin[j] = pack_bf16(lo, hi);
+        float act[ACT];
+        policy_forward_warp<FIRST, OBS, ACT>(sm, wtile[warp], lane, s, a.w.out_scale, a.w.out_offset, act);
+        if (i < a.n) {
+            if constexpr (ACT == 4) reinterpret_cast<float4*>(a.action)[i] = make_float4(act[0], act[1], act[2], act[3]);
+            else if constexpr (ACT == 2) reinterpret_cast<float2*>(a.action)[i] = make_float2(act[0], act[1]);
+            else a.action[i] = act[0];
         }
-        uint4* xrow = reinterpret_cast<uint4*>(x + lane * kPolXStride);
-        xrow[0] = make_uint4(xin[0], xin[1], xin[2], xin[3]);
-        xrow[1] = make_uint4(xin[4], xin[5], xin[6], xin[7]);
-        __syncwarp();
-
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {                       // rows 16*mt .. 16*mt+15 of the warp's 32 envs
-            // ---- layer 1: [16 x 16] x [16 x 64] ------------------------------------------
-            uint32_t afrag[4];
-            const int r0 = (16 * mt + g) * (kPolXStride / 2), r1 = (16 * mt + g + 8) * (kPolXStride / 2);
-            afrag[0] = xw[r0 + t]; afrag[1] = xw[r1 + t]; afrag[2] = xw[r0 + t + 4]; afrag[3] = xw[r1 + t + 4];
-            uint32_t h[4][4];                                  // activations as A fragments of the next layer, per k-tile
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                const int wr = (8 * nt + g) * (kPolW1Stride / 2);
-                mma_bf16(c, afrag, w1[wr + t], w1[wr + t + 4]);
-                const float bx = sm.b1[8 * nt + 2 * t], by = sm.b1[8 * nt + 2 * t + 1];
-                h[nt >> 1][(nt & 1) * 2 + 0] = tanh_pack(c[0] + bx, c[1] + by);   // rows g
-                h[nt >> 1][(nt & 1) * 2 + 1] = tanh_pack(c[2] + bx, c[3] + by);   // rows g+8
-            }
-            // ---- layer 2: [16 x 64] x [64 x 64] ------------------------------------------
-            uint32_t h2[4][4];
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                const int wr = (8 * nt + g) * (kPolW2Stride / 2);
-#pragma unroll
-                for (int kt = 0; kt < 4; ++kt) mma_bf16(c, h[kt], w2[wr + 8 * kt + t], w2[wr + 8 * kt + t + 4]);
-                const float bx = sm.b2[8 * nt + 2 * t], by = sm.b2[8 * nt + 2 * t + 1];
-                h2[nt >> 1][(nt & 1) * 2 + 0] = tanh_pack(c[0] + bx, c[1] + by);
-                h2[nt >> 1][(nt & 1) * 2 + 1] = tanh_pack(c[2] + bx, c[3] + by);
-            }
-            // ---- layer 3: [16 x 64] x [64 x 8] -------------------------------------------
-            float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            const int wr = g * (kPolW2Stride / 2);
-#pragma unroll
-            for (int kt = 0; kt < 4; ++kt) mma_bf16(c, h2[kt], w3[wr + 8 * kt + t], w3[wr + 8 * kt + t + 4]);
-            // columns 2t, 2t+1 of rows g and g+8
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int64_t row = row0 + 16 * mt + g + 8 * half;
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int col = 2 * t + q;
-                    if (row < a.n && col < ACT)
-                        a.action[row * ACT + col] = a.out_offset + a.out_scale * tanh_fast(c[2 * half + q] + sm.b3[col]);
-                }
-            }
-        }
-        __syncwarp();
     }
 }
 

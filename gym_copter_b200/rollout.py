@@ -143,6 +143,57 @@ class FusedMLPPolicy:
         return self.action
 
 
+class FusedPolicyRollout:
+    """
+    The whole policy-in-the-loop horizon as ONE kernel launch (copter_policy_rollout_f32): every
+    warp evaluates the tanh MLP O -> 64 -> 64 -> A for its 32 envs from the state its lanes hold
+    in registers and steps them, T times, writing only row t of the [T, N] rollout buffers.
+    Step for step identical to PolicyRollout(env, FusedMLPPolicy(env, net, ...), T, planar=True).
+
+    env        a float32 CopterVecEnv with k_substeps == 1
+    net        torch.nn.Sequential(Linear(O,64), Tanh, Linear(64,64), Tanh, Linear(64,A), Tanh);
+               weights are read in place (fp32), so optimizer updates are seen by the next run()
+    horizon    T
+    store_obs / store_actions   also record obs_t [T,N,O] (what the policy saw) / action_t [T,N,A]
+                                (the command before the env's clip), e.g. for a PPO update
+    """
+
+    def __init__(self, env, net, horizon, out_scale=1.0, out_offset=0.0, store_obs=False, store_actions=False):
+        probe = FusedMLPPolicy(env, net, out_scale, out_offset)       # same parameter checks
+        if env.k_substeps != 1:
+            raise CopterError('FusedPolicyRollout steps with k_substeps == 1')
+        self.env, self.lib, self.horizon = env, probe.lib, int(horizon)
+        if self.horizon < 1:
+            raise CopterError('horizon must be >= 1')
+        self.params = probe.params
+        self.policy = _lib.CopterMlpPolicy(*[p.data_ptr() for p in self.params], 64, float(out_scale), float(out_offset))
+        n, dev = env.num_envs, env.device
+        self.rewards = torch.zeros((self.horizon, n), dtype=torch.float32, device=dev)
+        self.dones = torch.zeros((self.horizon, n), dtype=torch.uint8, device=dev)
+        self.obs = torch.zeros((self.horizon, n, env.obs_size), dtype=torch.float32, device=dev) if store_obs else None
+        self.actions = torch.zeros((self.horizon, n, env.action_size), dtype=torch.float32, device=dev) if store_actions else None
+        self.launches_per_rollout = 1
+
+    def run(self):
+        """One horizon. Returns (rewards [T,N], dones [T,N] bool view, last_obs [N,O] or None)."""
+        env = self.env
+        if not env._is_reset:
+            raise CopterError('reset() the env before rolling out')
+        with torch.cuda.device(env.device):
+            b = env._buffers(None, env._force)
+            if not env.write_obs:
+                b.obs = None
+            _lib.check(self.lib.copter_policy_rollout_f32(
+                C.byref(env.params), C.byref(b), C.byref(self.policy), env.num_envs, env.env_offset,
+                env.seed_value & 0xFFFFFFFFFFFFFFFF, self.horizon, VARIANT_IDS[env.variant],
+                _lib.F_AUTO_RESET if env.auto_reset else 0, self.rewards.data_ptr(), self.dones.data_ptr(),
+                self.actions.data_ptr() if self.actions is not None else None,
+                self.obs.data_ptr() if self.obs is not None else None,
+                C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)), 'copter_policy_rollout')
+        env.launches += 1
+        return self.rewards, self.dones.view(torch.bool), env.obs if env.write_obs else None
+
+
 def mlp_policy(obs_size, action_size, hidden=64, dtype=torch.bfloat16, device='cuda', seed=0):
     """The small tanh MLP of SURVEY.md 8d config 5 (O -> 64 -> 64 -> A), random init."""
     g = torch.Generator(device='cpu').manual_seed(seed)

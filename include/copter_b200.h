@@ -17,6 +17,8 @@
  *                              with the constant / --random command streams generated on the device
  *   copter_dynamics_{f32,f64}  Dynamics.setMotors driven directly (take-off style use)
  *                              dynamics/__init__.py:114-197,210-229
+ *   copter_policy_mlp_f32,     the consumer's loop obs -> net -> clip -> env.step (attic/drl/3dtest.py:36-61):
+ *   copter_policy_rollout_f32  the network alone, and network + step fused over a whole horizon
  *   copter_step_host_{f32,f64} the same step for callers holding HOST buffers (numpy actions as in
  *                              lander.py:42-44), host<->device copies pipelined inside the call
  *
@@ -227,6 +229,28 @@ int copter_policy_mlp_f32(const void* state, int64_t state_stride, int64_t n, in
                           const float* w1, const float* b1, const float* w2, const float* b2,
                           const float* w3, const float* b3, float out_scale, float out_offset,
                           float* action, void* stream);
+
+/*
+ * Policy-in-the-loop rollout in ONE launch: for n_steps steps, action_t = policy(obs_t) with the
+ * MLP of copter_policy_mlp_f32 evaluated from the env state held in registers, then one
+ * reference step (k_substeps = 1) under that action -- the whole caller loop of
+ * attic/drl/3dtest.py:36-61 (obs -> net -> clip -> env.step) for T steps without the state,
+ * the observation or the action ever passing through HBM.  Step for step identical to
+ * copter_policy_mlp_f32 followed by copter_step_f32.  b->action is unused; b->reward / b->done
+ * (nullable) receive the per-env reward sum and "any episode finished" flag of the launch,
+ * b->obs (nullable) the observation after the last step.  Optional per-step outputs (nullable):
+ * reward_tn float[n_steps][n], done_tn uint8[n_steps][n], action_tn float[n_steps][n][A] (the
+ * commands before the env's clip), obs_tn float[n_steps][n][O] (the observation the policy
+ * acted on at step t).
+ */
+typedef struct CopterMlpPolicy {
+    const float *w1, *b1, *w2, *b2, *w3, *b3;   /* torch.nn.Linear layouts W[out][in], b[out]; fp32 device memory */
+    int32_t hidden;                             /* must be 64 */
+    float out_scale, out_offset;                /* action = out_offset + out_scale * tanh(.) */
+} CopterMlpPolicy;
+int copter_policy_rollout_f32(const CopterParams* p, const CopterBuffers* b, const CopterMlpPolicy* policy,
+                              int64_t n, int64_t env_offset, uint64_t seed, int n_steps, int variant, int flags,
+                              float* reward_tn, uint8_t* done_tn, float* action_tn, float* obs_tn, void* stream);
 
 /*
  * The same step for callers that hold HOST arrays (the reference's callers pass numpy

@@ -279,3 +279,59 @@ def test_fused_mlp_policy_vs_torch_fp32(pkg, variant):
     ro = pkg.PolicyRollout(env, fused, 4, planar=True, use_cuda_graph=True)
     r, d, _ = ro.run()
     assert r.shape == (4, n) and torch.isfinite(r).all()
+
+
+@pytest.mark.parametrize('variant,n', [('Lander3D', 4099), ('Lander2D', 1000), ('Hover3D', 257), ('Lander1D', 31)])
+def test_fused_policy_rollout_equals_policy_kernel_plus_step(pkg, variant, n):
+    """copter_policy_rollout_f32 (policy + env step for T steps in one launch, state in
+    registers) against the same network evaluated by copter_policy_mlp_f32 and stepped by
+    copter_step_f32, launch by launch: done flags, recorded actions / observations, final state
+    and counters are bit-identical, rewards agree to a few ulp (ragged n covers partly filled warps)."""
+    T = 150
+    envs = [pkg.CopterVecEnv(variant, n, seed=11, track_returns=True) for _ in range(2)]
+    pol = pkg.mlp_policy(envs[0].obs_size, envs[0].action_size, dtype=torch.float32, seed=2)
+    for p in pol.net.parameters():
+        p.data.mul_(2.0)
+    # commands around hover so that episodes end inside the horizon in several ways
+    scale, offset = 0.03, 0.0166
+    for e in envs:
+        e.reset()
+    fused = pkg.FusedPolicyRollout(envs[0], pol.net, T, out_scale=scale, out_offset=offset, store_obs=True, store_actions=True)
+    r1, d1, last1 = fused.run()
+    two = pkg.FusedMLPPolicy(envs[1], pol.net, out_scale=scale, out_offset=offset)
+    rewards, dones, actions, obs = [], [], [], []
+    for t in range(T):
+        obs.append(envs[1].obs.clone())
+        a = two()
+        actions.append(a.clone())
+        o, r, d, _, _ = envs[1].step(a)
+        rewards.append(r.clone()); dones.append(d.clone())
+    assert torch.equal(torch.stack(actions), fused.actions)
+    assert torch.equal(torch.stack(obs), fused.obs)
+    # same device arithmetic, but the compiler may contract the reward's FMAs differently in the
+    # two kernels: rewards at a few ulp; everything that feeds back into the loop bit for bit
+    assert merr(r1.cpu().numpy(), torch.stack(rewards).cpu().numpy()) <= 1e-5
+    assert torch.equal(torch.stack(dones), d1)
+    assert torch.equal(envs[0].state, envs[1].state) and torch.equal(envs[0].meta, envs[1].meta)
+    assert torch.equal(last1, envs[1].obs)
+    s0, s1 = envs[0].stats(), envs[1].stats()
+    assert s0['episodes'] == s1['episodes'] and s0['env_steps'] == s1['env_steps'] == n * T
+    assert abs(s0['return_sum'] - s1['return_sum']) <= 1e-6 * max(1.0, abs(s1['return_sum']))
+    if variant in ('Lander3D', 'Lander2D'):      # the variants that can tip over inside the horizon
+        assert d1.any() and not d1.all()
+    # a second horizon continues from where the first one stopped
+    r2, _, _ = fused.run()
+    assert torch.isfinite(r2).all()
+
+
+def test_fused_policy_rollout_argument_errors(pkg):
+    env = pkg.CopterVecEnv('Lander3D', 64)
+    bad = torch.nn.Sequential(torch.nn.Linear(10, 32), torch.nn.Tanh(), torch.nn.Linear(32, 32), torch.nn.Tanh(),
+                              torch.nn.Linear(32, 4), torch.nn.Tanh()).cuda()
+    with pytest.raises(pkg.CopterError):
+        pkg.FusedPolicyRollout(env, bad, 4)
+    good = pkg.mlp_policy(10, 4, dtype=torch.float32).net
+    with pytest.raises(pkg.CopterError):
+        pkg.FusedPolicyRollout(env, good, 4).run()          # not reset
+    with pytest.raises(pkg.CopterError):
+        pkg.FusedPolicyRollout(pkg.CopterVecEnv('Lander3D', 64, k_substeps=2), good, 4)

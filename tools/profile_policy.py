@@ -1,8 +1,20 @@
-import sys, torch
-import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import gym_copter_b200 as g
-env = g.LanderVec(1 << 23, seed=1, write_obs=False); env.reset()
+"""Developer tool: the launches `ncu -k regex:policy` captures for profiles/ (policy kernel alone,
+then the fused policy + step rollout kernel, 2^23 envs)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gym_copter_b200 as g  # noqa: E402
+
+env = g.LanderVec(1 << 23, seed=1, write_obs=False)
+env.reset()
 pol = g.mlp_policy(10, 4, dtype=torch.float32, seed=5)
-fused = g.FusedMLPPolicy(env, pol.net)
-for _ in range(3): fused()
+fused = g.FusedMLPPolicy(env, pol.net, out_scale=0.2 * 0.0166, out_offset=0.0166)
+for _ in range(3):
+    fused()
+ro = g.FusedPolicyRollout(env, pol.net, 8, out_scale=0.2 * 0.0166, out_offset=0.0166)
+for _ in range(2):
+    ro.run()
 torch.cuda.synchronize()

@@ -1,0 +1,78 @@
+#!/usr/bin/env python3
+"""
+Developer tool: A/B builds of the policy kernels (occupancy target, tanh form).  `build`
+cross-compiles the variants here into tools/variants/; `run` times each on the GPU box (one
+subprocess per variant, selected through COPTER_B200_LIB): the policy kernel alone and the fused
+policy + step rollout, Lander3D, 2^23 envs.
+
+    python tools/sweep_policy.py build
+    gpurun -- python tools/sweep_policy.py run
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VDIR = os.path.join(ROOT, 'tools', 'variants')
+SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
+
+VARIANTS = {
+    'pol_base': [],
+    'pol_r3': ['-DCOPTER_POLICY_ROLLOUT_CTAS_PER_SM=3', '-DCOPTER_POLICY_CTAS_PER_SM=3'],
+    'pol_r5': ['-DCOPTER_POLICY_ROLLOUT_CTAS_PER_SM=5', '-DCOPTER_POLICY_CTAS_PER_SM=5'],
+    'pol_r6': ['-DCOPTER_POLICY_ROLLOUT_CTAS_PER_SM=6', '-DCOPTER_POLICY_CTAS_PER_SM=6'],
+    'pol_bf16x2': ['-DCOPTER_POLICY_TANH_BF16X2=1'],
+}
+VARIANTS.update(json.loads(os.environ.get('COPTER_SWEEP_EXTRA', '{}')))
+
+
+def build():
+    os.makedirs(VDIR, exist_ok=True)
+    procs = []
+    for name, flags in VARIANTS.items():
+        out = os.path.join(VDIR, 'lib_%s.so' % name)
+        cmd = ['nvcc', '-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
+               '-Xcompiler', '-fPIC', '-shared'] + flags + ['-o', out, SRC]
+        procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for n, p in procs:
+        o, _ = p.communicate()
+        print(n, 'rc', p.returncode, o[-300:] if p.returncode else '')
+
+
+def time_one():
+    import torch
+    sys.path.insert(0, ROOT)
+    import gym_copter_b200 as g
+    n, T = 1 << 23, 16
+    env = g.LanderVec(n, seed=3, write_obs=False)
+    env.reset()
+    pol = g.mlp_policy(10, 4, dtype=torch.float32, seed=5)
+
+    def timed(fn, reps):
+        fn(); fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    fused = g.FusedMLPPolicy(env, pol.net, out_scale=0.2 * 0.0166, out_offset=0.0166)
+    ms_pol = timed(fused, 30)
+    ro = g.FusedPolicyRollout(env, pol.net, T, out_scale=0.2 * 0.0166, out_offset=0.0166)
+    ms = timed(ro.run, 8) / T
+    print(json.dumps({'policy_kernel_ms': ms_pol, 'rollout_ms_per_env_step': ms, 'rollout_steps_per_s': n / ms * 1e3}))
+
+
+def run():
+    for name in VARIANTS:
+        lib = os.path.join(VDIR, 'lib_%s.so' % name)
+        if not os.path.exists(lib):
+            print(name, 'missing'); continue
+        env = dict(os.environ, COPTER_B200_LIB=lib)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), 'one'], env=env, capture_output=True, text=True, timeout=600)
+        print(name, (r.stdout.strip().splitlines() or [r.stderr[-300:]])[-1], flush=True)
+
+
+if __name__ == '__main__':
+    {'build': build, 'run': run, 'one': time_one}[sys.argv[1]]()
