@@ -132,22 +132,34 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = host_cores()
-    per_step = max(0.5, min(3.0, 60.0 / max(1, args.steps + args.warmup)))
+    # bounded sample: the whole --steps/--warmup run stays near two minutes whatever K and W are
+    per_step = max(0.05, min(3.0, 100.0 / max(1, args.steps + args.warmup)))
+    from oracle.scalar_port import make_pool, run_parallel, run_stream
+    pool = make_pool(cores) if cores > 1 else None
     rates = []
     t0 = time.perf_counter()
     for i in range(args.warmup + args.steps):
-        r = cpu_port_rate(args.stream, per_step, cores)
+        if pool is not None:
+            r = run_parallel(args.stream, per_step, cores, pool)
+        else:
+            n, el = run_stream(args.stream, per_step)
+            r = n / el
         if i >= args.warmup:
             rates.append(r)
+    if pool is not None:
+        pool.close()
+        pool.join()
     value = sum(rates) / len(rates)
-    sample = ('%d processes x one ScalarLander env loop each, %s action stream, %.1f s per step, '
-              'reset on done' % (cores, args.stream, per_step))
+    sample = ('%d processes x one ScalarLander env loop each (oracle/scalar_port.py, the reference\'s per-object '
+              'execution style), %s action stream, %.2f s of stepping per bench step, reset on done'
+              % (cores, args.stream, per_step))
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_step * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
-        'config': {'workload': 'Lander3D single-env Python objects on host cores', 'stream': args.stream},
+        'config': {'workload': 'Lander3D, reset on done: a bounded sample of the b200 arm\'s workload stepped as single-env '
+                               'Python objects on the host cores', 'action_stream': args.stream},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'wall_s': time.perf_counter() - t0}))

@@ -200,18 +200,31 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
         run_begin<T, VARIANT>(kp, run, s);
         T na = (T)0, nc = (T)0, dz_prev = s[5]; int cause = 0;
         constexpr int kUnroll = COPTER_K_UNROLL;
+        bool live = valid;                                             // has an env that has not finished in this launch
 #pragma unroll kUnroll
         for (int k = 0; k < a.k; ++k) {
-            const bool live = valid && !done_any;
             if (__all_sync(0xffffffffu, !live)) break;                 // whole warp finished: idle
+            // Straight-line substep when every live env of the warp is in the common case (airborne,
+            // clear of the ground, past the first step of its episode, small angles): no status
+            // machine, no perturbation, one predicated region.  Anything else takes the general step.
+            const bool hot = airborne_hot<T>(s, st, steps);
+            const bool fast = COPTER_FAST_SUBSTEP && __all_sync(0xffffffffu, (int)!live | (int)hot);
             if (live) {
                 dz_prev = s[5];
                 bool dn;
-                env_advance<T, VARIANT>(kp, s, st, steps, forces, pert, na, nc, dn, cause);
-                pert[0] = (T)0; pert[1] = (T)0; pert[2] = (T)0;
-                run_step<T>(run, na, nc, cause);
+                if (fast) {
+                    const int end = airborne_substep<T, VARIANT>(kp, s, steps, forces, na, nc);
+                    ++run.steps;
+                    if (!(end & END_ANGLE)) { run.na += na; run.nc += nc; }
+                    dn = end != 0;
+                    if (dn) cause = airborne_cause(end);
+                } else {
+                    env_advance<T, VARIANT>(kp, s, st, steps, forces, pert, na, nc, dn, cause);
+                    pert[0] = (T)0; pert[1] = (T)0; pert[2] = (T)0;
+                    run_step<T>(run, na, nc, cause);
+                }
                 if (dn) {
-                    done_any = true;
+                    live = false;
                     ep_cause = cause;
                     total = run_reward<T, VARIANT>(kp, run, s, cause, na, nc, dz_prev);
                     if (STATS) ep_len = steps - 1;                     // `steps` is 1 right after reset (task.py:191,197)
@@ -226,6 +239,7 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
                 }
             }
         }
+        done_any = valid && !live;
         if (valid) {
             if (!done_any) total = run_reward<T, VARIANT>(kp, run, s, 0, na, nc, dz_prev);
             if (STATS) {

@@ -49,6 +49,9 @@ namespace copter {
 #ifndef COPTER_K_UNROLL
 #define COPTER_K_UNROLL 1         // unroll factor of the substep loop (A/B knob)
 #endif
+#ifndef COPTER_FAST_SUBSTEP
+#define COPTER_FAST_SUBSTEP 1     // 0 (A/B knob): every substep of a K-fused launch takes the general env_advance
+#endif
 #ifndef COPTER_STREAMING
 #define COPTER_STREAMING 0      // 1: evict-first (ld/st .cs) hints on the state planes
 #endif
@@ -267,42 +270,57 @@ __device__ __forceinline__ Forces<T> motor_forces(const KParams<T>& kp, T m0, T 
 // and (psi,dpsi), inc_j = dt*ds_j being the Euler increment BEFORE it is rounded into the
 // state (zero when the state was not integrated) -- see shaping_delta.
 // The hot case (AIRBORNE, not touching the ground) is tested first and is straight-line code.
+// The AIRBORNE, not-touching-the-ground case of setMotors (:180-197): Eq. 12 and one forward Euler
+// step from the sines / cosines of the current angles.  PERT: the reset perturbation `p` is added
+// (twice, :263-287 and :183) to the first NP rate derivatives.  Shared by dynamics_update and the
+// straight-line substep of the K-fused loop (airborne_substep), so both produce the same bits.
+template <typename T, int NP, bool PERT>
+__device__ __forceinline__ void airborne_integrate(const KParams<T>& kp, T (&s)[12], const Forces<T>& f, const T (&p)[NP],
+                                                   T sph, T cph, T sth, T cth, T sps, T cps, T& na, T& nc) {
+    // third column of the body->inertial rotation times the body-Z thrust (:292-302)
+    const T ax = f.bz * (sph * sps + cph * cps * sth);
+    const T ay = f.bz * (cph * sps * sth - cps * sph);
+    const T netz = f.bz * (cph * cth) + kp.G;                     // :143
+    const T dphi = s[7], dthe = s[9], dpsi = s[11];
+    // Eq. 12 (:257-290) with Omega = 0 (:135); the perturbation is added twice (:263-287, :183)
+    T d1 = ax, d3 = ay, d5 = netz;
+    T d7 = dpsi * dthe * kp.gphi - kp.jx * dthe * f.om + f.u2;
+    T d9 = -(dpsi * dphi * kp.gthe + kp.jy * dphi * f.om + f.u3);
+    T d11 = dthe * dphi * kp.gpsi + f.u4;
+    if constexpr (PERT) {
+        d1 += (T)2 * p[0]; d3 += (T)2 * p[1]; d5 += (T)2 * p[2];
+        if constexpr (NP == 6) { d7 += (T)2 * p[3]; d9 += (T)2 * p[4]; d11 += (T)2 * p[5]; }
+    }
+    // forward Euler, every derivative from the old state (:187)
+    const T dt = kp.dt;
+    const T i0 = dt * s[1], i1 = dt * d1, i2 = dt * s[3], i3 = dt * d3, i4 = dt * s[5], i5 = dt * d5;
+    const T i10 = dt * dpsi, i11 = dt * d11;
+    na = i0 * ((T)2 * s[0] + i0) + i1 * ((T)2 * s[1] + i1) + i2 * ((T)2 * s[2] + i2)
+       + i3 * ((T)2 * s[3] + i3) + i4 * ((T)2 * s[4] + i4) + i5 * ((T)2 * s[5] + i5);
+    nc = i10 * ((T)2 * s[10] + i10) + i11 * ((T)2 * s[11] + i11);
+    s[0] += dt * s[1];  s[1] += dt * d1;
+    s[2] += dt * s[3];  s[3] += dt * d3;
+    s[4] += dt * s[5];  s[5] += dt * d5;
+    s[6] += dt * dphi;  s[7] += dt * d7;
+    s[8] += dt * dthe;  s[9] += dt * d9;
+    s[10] += dt * dpsi; s[11] += dt * d11;
+}
+
 template <typename T, int NP, bool DIRECT>
 __device__ __forceinline__ bool dynamics_update(const KParams<T>& kp, T (&s)[12], int& st,
                                                 const Forces<T>& f, const T (&p)[NP], T& na, T& nc) {
     na = (T)0; nc = (T)0;
     T sph, cph, sth, cth, sps, cps;
     sincos3_t(s[6], s[8], s[10], sph, cph, sth, cth, sps, cps);
-    // third column of the body->inertial rotation times the body-Z thrust (:292-302)
-    const T ax = f.bz * (sph * sps + cph * cps * sth);
-    const T ay = f.bz * (cph * sps * sth - cps * sph);
-    const T netz = f.bz * (cph * cth) + kp.G;                     // :143
 
-    if (DIRECT && st == ST_LANDED && netz < (T)0) st = ST_AIRBORNE;   // :147-149
+    if (DIRECT && st == ST_LANDED) {                               // :147-149
+        const T netz = f.bz * (cph * cth) + kp.G;                  // :143
+        if (netz < (T)0) st = ST_AIRBORNE;
+    }
 
     const bool touch = s[4] > (T)0 && s[5] > (T)0;                 // :162 (pre-step state)
     if (st == ST_AIRBORNE && !touch) {                             // :159, :180-187
-        const T dphi = s[7], dthe = s[9], dpsi = s[11];
-        // Eq. 12 (:257-290) with Omega = 0 (:135); the perturbation is added twice (:263-287, :183)
-        T d1 = ax, d3 = ay, d5 = netz;
-        T d7 = dpsi * dthe * kp.gphi - kp.jx * dthe * f.om + f.u2;
-        T d9 = -(dpsi * dphi * kp.gthe + kp.jy * dphi * f.om + f.u3);
-        T d11 = dthe * dphi * kp.gpsi + f.u4;
-        d1 += (T)2 * p[0]; d3 += (T)2 * p[1]; d5 += (T)2 * p[2];
-        if constexpr (NP == 6) { d7 += (T)2 * p[3]; d9 += (T)2 * p[4]; d11 += (T)2 * p[5]; }
-        // forward Euler, every derivative from the old state (:187)
-        const T dt = kp.dt;
-        const T i0 = dt * s[1], i1 = dt * d1, i2 = dt * s[3], i3 = dt * d3, i4 = dt * s[5], i5 = dt * d5;
-        const T i10 = dt * dpsi, i11 = dt * d11;
-        na = i0 * ((T)2 * s[0] + i0) + i1 * ((T)2 * s[1] + i1) + i2 * ((T)2 * s[2] + i2)
-           + i3 * ((T)2 * s[3] + i3) + i4 * ((T)2 * s[4] + i4) + i5 * ((T)2 * s[5] + i5);
-        nc = i10 * ((T)2 * s[10] + i10) + i11 * ((T)2 * s[11] + i11);
-        s[0] += dt * s[1];  s[1] += dt * d1;
-        s[2] += dt * s[3];  s[3] += dt * d3;
-        s[4] += dt * s[5];  s[5] += dt * d5;
-        s[6] += dt * dphi;  s[7] += dt * d7;
-        s[8] += dt * dthe;  s[9] += dt * d9;
-        s[10] += dt * dpsi; s[11] += dt * d11;
+        airborne_integrate<T, NP, true>(kp, s, f, p, sph, cph, sth, cth, sps, cps, na, nc);
         return true;
     }
     if (st == ST_LEVELING) {                                       // :152-156
@@ -379,6 +397,41 @@ __device__ __forceinline__ void env_advance(const KParams<T>& kp, T (&s)[12], in
     if (steps == kp.max_steps) { done = true; cause |= CAUSE_TIMEOUT; }          // :128
     steps = min(steps + 1, 2047);                                  // :130 (11-bit field)
     if (!done) cause = 0;
+}
+
+// The common case of env_advance as straight-line code, for the K-fused loops: an AIRBORNE env that
+// is not touching the ground, is past the first step of its episode (no reset perturbation left)
+// and -- fp32 -- has all three angles inside the polynomial range of sincos_poly.  airborne_hot()
+// is that precondition; under it airborne_substep() gives exactly what env_advance gives.
+template <typename T>
+__device__ __forceinline__ bool airborne_hot(const T (&s)[12], int st, int steps) {
+    // (bitwise on purpose: one straight run of compares, no short-circuit branches)
+    int hot = (int)(st == ST_AIRBORNE) & (int)(steps != 1) & (int)!(s[4] > (T)0 && s[5] > (T)0);
+    if constexpr (sizeof(T) == 4) hot &= (int)(!COPTER_LIBM_ONLY && fmaxf(fmaxf(fabsf(s[6]), fabsf(s[8])), fabsf(s[10])) <= 0.78539816f);
+    return hot != 0;
+}
+
+// Returns the step's ending flags: bit 0 out of bounds, bit 1 over-angle (exclusive: the reference
+// tests them with if / elif, task.py:111-118), bit 2 the env's own step limit; 0 = the episode goes
+// on.  airborne_cause() turns them into the CAUSE_* bits env_advance reports.
+enum { END_OOB = 1, END_ANGLE = 2, END_TIMEOUT = 4 };
+template <typename T, int VARIANT>
+__device__ __forceinline__ int airborne_substep(const KParams<T>& kp, T (&s)[12], int& steps, const Forces<T>& f,
+                                                T& na, T& nc) {
+    T sph, cph, sth, cth, sps, cps;
+    if constexpr (sizeof(T) == 4) { sincos_poly(s[6], sph, cph); sincos_poly(s[8], sth, cth); sincos_poly(s[10], sps, cps); }
+    else sincos3_t(s[6], s[8], s[10], sph, cph, sth, cth, sps, cps);
+    const T none[3] = {(T)0, (T)0, (T)0};
+    airborne_integrate<T, 3, false>(kp, s, f, none, sph, cph, sth, cth, sps, cps, na, nc);
+    // task.py:111-130 with the stale status AIRBORNE
+    const bool oob = abs_t(s[0]) >= kp.bounds || abs_t(s[2]) >= kp.bounds;
+    const bool ang = !oob && (abs_t(s[6]) >= kp.max_angle || abs_t(s[8]) >= kp.max_angle);
+    const bool timeout = steps == kp.max_steps;
+    steps = min(steps + 1, 2047);
+    return (oob ? END_OOB : 0) | (ang ? END_ANGLE : 0) | (timeout ? END_TIMEOUT : 0);
+}
+__device__ __forceinline__ int airborne_cause(int end) {
+    return ((end & END_OOB) ? CAUSE_OOB : 0) | ((end & END_ANGLE) ? CAUSE_ANGLE : 0) | ((end & END_TIMEOUT) ? CAUSE_TIMEOUT : 0);
 }
 
 // The reward modifiers of task.py:111-118 and lander.py:69-72 applied to a base reward.

@@ -150,10 +150,21 @@ def _worker(args):
     return run_stream(*args)
 
 
-def run_parallel(kind, seconds, procs):
-    """`procs` independent env loops, one process each. Returns aggregate env-steps/s."""
+def make_pool(procs):
+    """A pool of `procs` worker processes that can be reused across run_parallel() calls."""
     import multiprocessing as mp
-    ctx = mp.get_context('fork')
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_worker, [(kind, seconds, 1000 + i) for i in range(procs)])
+    return mp.get_context('fork').Pool(procs)
+
+
+def run_parallel(kind, seconds, procs, pool=None):
+    """`procs` independent env loops, one process each. Returns aggregate env-steps/s."""
+    own = pool is None
+    if own:
+        pool = make_pool(procs)
+    try:
+        res = pool.map(_worker, [(kind, seconds, 1000 + i) for i in range(procs)], chunksize=1)
+    finally:
+        if own:
+            pool.close()
+            pool.join()
     return sum(n / el for n, el in res)
