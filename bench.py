@@ -339,6 +339,35 @@ def main():
     del senv
     torch.cuda.empty_cache()
 
+    # ---- configs[4] side measurement: policy-in-the-loop rollout, ONE launch per horizon ---
+    policy_rollout = None
+    if not args.no_extras and k == 1 and args.variant == 'Lander3D' and args.dtype == 'f32':
+        try:
+            pn, pT = min(n, 1 << 23), 16
+            penv = g.CopterVecEnv('Lander3D', pn, seed=2026, env_offset=rank * pn, write_obs=False)
+            penv.reset()
+            pol = g.mlp_policy(10, 4, dtype=torch.float32, seed=5)
+            pro = g.FusedPolicyRollout(penv, pol.net, pT, out_scale=0.2 * 0.0166, out_offset=0.0166)
+            for _ in range(3):
+                pro.run()
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            p0.record()
+            for _ in range(reps):
+                pro.run()
+            p1.record()
+            barrier()
+            pms = max_over_ranks(p0.elapsed_time(p1))
+            policy_rollout = {'value': world * pn * pT * reps / (pms * 1e-3), 'unit': UNIT, 'ms_per_env_step': pms / (reps * pT),
+                              'workload': 'Lander3D f32, %d envs/GPU, tanh MLP 10-64-64-4 policy + env step fused in '
+                                          'copter_policy_rollout_kernel, horizon %d per launch, reward/done rows written' % (pn, pT),
+                              'bound': 'MUFU (XU) pipe: 132 tanh per env-step'}
+            del pro, penv, pol
+        except Exception as e:
+            policy_rollout = {'unavailable': repr(e)[:200]}
+        torch.cuda.empty_cache()
+
     # ---- end to end through the host-array API -------------------------------------------
     h = env.host_buffers()
     h['action'][:] = actions[0].cpu().numpy()
@@ -389,6 +418,7 @@ def main():
             'episodes': dict({kk: stats[kk] for kk in ('episodes', 'mean_length', 'landed', 'crashed', 'oob', 'angle', 'timeout')},
                              ms_per_step_with_statistics=ms_with_stats),
             'fused_substeps': extras,
+            'policy_rollout': policy_rollout,
         }
         print(json.dumps(line))
     if world > 1:

@@ -6,8 +6,8 @@ Developer tool, run on the GPU box under compute-sanitizer:
     compute-sanitizer --tool racecheck python tools/sanitize.py
 
 Exercises every kernel on ragged sizes (partial warps / partial tiles), every variant, both
-precisions, statistics, final observations, injected forces, K-fusion, the fused rollout and
-the host-array pipeline, so that out-of-bounds accesses and shared-memory hazards in the
+precisions, statistics, final observations, injected forces, K-fusion, the fused rollouts, the
+policy kernels and the host-array pipeline, so that out-of-bounds accesses and shared-memory hazards in the
 obs staging tiles would be reported.
 """
 import os
@@ -31,6 +31,15 @@ for variant in ('Lander3D', 'Lander2D', 'Lander1D', 'Hover3D', 'Hover2D', 'Hover
             env.rollout(5, source='randn', record_rewards=True, record_dones=True, record_actions=True)
             env.rollout(3, source='uniform')
             env.stats()
+for variant in ('Lander3D', 'Lander2D', 'Lander1D', 'Hover3D'):
+    for n in (1, 33, 129, 300):
+        env = g.CopterVecEnv(variant, n, seed=4, track_returns=True)
+        env.reset()
+        pol = g.mlp_policy(env.obs_size, env.action_size, dtype=torch.float32, seed=n)
+        g.FusedMLPPolicy(env, pol.net, out_scale=0.02, out_offset=0.0166)()
+        ro = g.FusedPolicyRollout(env, pol.net, 6, out_scale=0.02, out_offset=0.0166, store_obs=True, store_actions=True)
+        ro.run()
+        ro.run()
 env = g.LanderVec(1000, seed=2, track_stats=True)
 env.reset()
 for t in range(3):
