@@ -58,6 +58,9 @@ __device__ __forceinline__ float tanh_fast(float x) {
 // hidden activations.  COPTER_POLICY_TANH_BF16X2 (A/B knob) rounds the pair to bf16 first and
 // uses tanh.approx.bf16x2; it is not faster on B200 (the packed form costs two XU slots) and is
 // less accurate, so the default is two fp32 MUFU.TANH.
+#ifndef COPTER_POLICY_MT
+#define COPTER_POLICY_MT 2             // row tiles of 16 envs carried through the layers together (A/B knob: 1)
+#endif
 #ifndef COPTER_POLICY_TANH_BF16X2
 #define COPTER_POLICY_TANH_BF16X2 0      // measured on B200: 0.435 ms vs 0.412 ms for two fp32 tanh (2^23 envs)
 #endif
@@ -146,72 +149,79 @@ __device__ __forceinline__ void policy_forward_warp(const PolicySmem& sm, Policy
     xrow[1] = make_uint4(xin[4], xin[5], xin[6], xin[7]);
     __syncwarp();
 
-    // layer-1 A fragments of both row tiles: four 8x8 matrices each (rows 0-7 / 8-15 x k 0-7 / 8-15)
-    uint32_t a1[2][4];
+    // COPTER_POLICY_MT rows tiles of 16 envs are carried through the layers together (2: every weight
+    // fragment load serves both tiles and the two accumulator chains interleave; 1: half the live
+    // registers, twice the fragment loads)
+    constexpr int MT = COPTER_POLICY_MT;
+#pragma unroll 1
+    for (int m0 = 0; m0 < 2; m0 += MT) {
+        // layer-1 A fragments: four 8x8 matrices per row tile (rows 0-7 / 8-15 x k 0-7 / 8-15)
+        uint32_t a1[MT][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-        const int j = lane >> 3, r = lane & 7;
-        ldmatrix_x4(a1[mt], wt.x + (16 * mt + 8 * (j & 1) + r) * kPolXStride + 8 * (j >> 1));
-    }
-
-    // ---- layer 1: [32 x 16] x [16 x 64], activations kept as the A fragments of layer 2 ----
-    uint32_t h[2][4][4];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-        const uint2 b = sm.w1[nt][lane];
-        const float4 bias = sm.b1[nt][t];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            float c[4];
-            mma_bf16_bias(c, a1[mt], b.x, b.y, bias);
-            h[mt][nt >> 1][(nt & 1) * 2 + 0] = tanh_pack(c[0], c[1]);      // rows g
-            h[mt][nt >> 1][(nt & 1) * 2 + 1] = tanh_pack(c[2], c[3]);      // rows g + 8
+        for (int mt = 0; mt < MT; ++mt) {
+            const int j = lane >> 3, r = lane & 7;
+            ldmatrix_x4(a1[mt], wt.x + (16 * (m0 + mt) + 8 * (j & 1) + r) * kPolXStride + 8 * (j >> 1));
         }
-    }
 
-    // ---- layer 2: [32 x 64] x [64 x 64], two n-tiles at a time, each pair feeding one k-tile of
-    // ---- layer 3: [32 x 64] x [64 x 8]
-    float c3[2][4];
+        // ---- layer 1: [16 MT x 16] x [16 x 64], activations kept as the A fragments of layer 2 ----
+        uint32_t h[MT][4][4];
 #pragma unroll
-    for (int kt3 = 0; kt3 < 4; ++kt3) {
-        uint32_t a3[2][4];
+        for (int nt = 0; nt < 8; ++nt) {
+            const uint2 b = sm.w1[nt][lane];
+            const float4 bias = sm.b1[nt][t];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int nt = 2 * kt3 + half;
-            const float4 bias = sm.b2[nt][t];
-            float c[2][4];
+            for (int mt = 0; mt < MT; ++mt) {
+                float c[4];
+                mma_bf16_bias(c, a1[mt], b.x, b.y, bias);
+                h[mt][nt >> 1][(nt & 1) * 2 + 0] = tanh_pack(c[0], c[1]);      // rows g
+                h[mt][nt >> 1][(nt & 1) * 2 + 1] = tanh_pack(c[2], c[3]);      // rows g + 8
+            }
+        }
+
+        // ---- layer 2: [16 MT x 64] x [64 x 64], two n-tiles at a time, each pair feeding one k-tile of
+        // ---- layer 3: [16 MT x 64] x [64 x 8]
+        float c3[MT][4];
 #pragma unroll
-            for (int kp = 0; kp < 2; ++kp) {
-                const uint4 b = sm.w2[nt][kp][lane];
+        for (int kt3 = 0; kt3 < 4; ++kt3) {
+            uint32_t a3[MT][4];
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    if (kp == 0) mma_bf16_bias(c[mt], h[mt][0], b.x, b.y, bias);
-                    else         mma_bf16(c[mt], h[mt][2], b.x, b.y);
-                    mma_bf16(c[mt], h[mt][2 * kp + 1], b.z, b.w);
+            for (int half = 0; half < 2; ++half) {
+                const int nt = 2 * kt3 + half;
+                const float4 bias = sm.b2[nt][t];
+                float c[MT][4];
+#pragma unroll
+                for (int kp = 0; kp < 2; ++kp) {
+                    const uint4 b = sm.w2[nt][kp][lane];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        if (kp == 0) mma_bf16_bias(c[mt], h[mt][0], b.x, b.y, bias);
+                        else         mma_bf16(c[mt], h[mt][2], b.x, b.y);
+                        mma_bf16(c[mt], h[mt][2 * kp + 1], b.z, b.w);
+                    }
+                }
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    a3[mt][half * 2 + 0] = tanh_pack(c[mt][0], c[mt][1]);
+                    a3[mt][half * 2 + 1] = tanh_pack(c[mt][2], c[mt][3]);
                 }
             }
+            const uint4 b = sm.w3[kt3 >> 1][lane];
+            const uint32_t b0 = (kt3 & 1) ? b.z : b.x, b1 = (kt3 & 1) ? b.w : b.y;
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                a3[mt][half * 2 + 0] = tanh_pack(c[mt][0], c[mt][1]);
-                a3[mt][half * 2 + 1] = tanh_pack(c[mt][2], c[mt][3]);
+            for (int mt = 0; mt < MT; ++mt) {
+                if (kt3 == 0) mma_bf16_bias(c3[mt], a3[mt], b0, b1, sm.b3[t]);
+                else          mma_bf16(c3[mt], a3[mt], b0, b1);
             }
         }
-        const uint4 b = sm.w3[kt3 >> 1][lane];
-        const uint32_t b0 = (kt3 & 1) ? b.z : b.x, b1 = (kt3 & 1) ? b.w : b.y;
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            if (kt3 == 0) mma_bf16_bias(c3[mt], a3[mt], b0, b1, sm.b3[t]);
-            else          mma_bf16(c3[mt], a3[mt], b0, b1);
-        }
-    }
 
-    // lanes t < 2 hold columns 2t, 2t+1 (< 4) of rows g and g + 8 of each row tile: hand every
-    // env's pre-activation row back to its own lane, which applies the output tanh once
-    if (t < 2) {
+        // lanes t < 2 hold columns 2t, 2t+1 (< 4) of rows g and g + 8 of each row tile: hand every
+        // env's pre-activation row back to its own lane, which applies the output tanh once
+        if (t < 2) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            *reinterpret_cast<float2*>(wt.act + (16 * mt + g) * 4 + 2 * t) = make_float2(c3[mt][0], c3[mt][1]);
-            *reinterpret_cast<float2*>(wt.act + (16 * mt + g + 8) * 4 + 2 * t) = make_float2(c3[mt][2], c3[mt][3]);
+            for (int mt = 0; mt < MT; ++mt) {
+                *reinterpret_cast<float2*>(wt.act + (16 * (m0 + mt) + g) * 4 + 2 * t) = make_float2(c3[mt][0], c3[mt][1]);
+                *reinterpret_cast<float2*>(wt.act + (16 * (m0 + mt) + g + 8) * 4 + 2 * t) = make_float2(c3[mt][2], c3[mt][3]);
+            }
         }
     }
     __syncwarp();

@@ -17,12 +17,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VDIR = os.path.join(ROOT, 'tools', 'variants')
 SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
 
+def _v(mt, ctas, *extra):
+    return ['-DCOPTER_POLICY_MT=%d' % mt, '-DCOPTER_POLICY_ROLLOUT_CTAS_PER_SM=%d' % ctas, '-DCOPTER_POLICY_CTAS_PER_SM=%d' % ctas] + list(extra)
+
+
 VARIANTS = {
-    'pol_base': [],
-    'pol_r3': ['-DCOPTER_POLICY_ROLLOUT_CTAS_PER_SM=3', '-DCOPTER_POLICY_CTAS_PER_SM=3'],
-    'pol_r5': ['-DCOPTER_POLICY_ROLLOUT_CTAS_PER_SM=5', '-DCOPTER_POLICY_CTAS_PER_SM=5'],
-    'pol_r6': ['-DCOPTER_POLICY_ROLLOUT_CTAS_PER_SM=6', '-DCOPTER_POLICY_CTAS_PER_SM=6'],
-    'pol_bf16x2': ['-DCOPTER_POLICY_TANH_BF16X2=1'],
+    'pol_mt2_c4': _v(2, 4), 'pol_mt2_c5': _v(2, 5), 'pol_mt2_c6': _v(2, 6),
+    'pol_mt1_c5': _v(1, 5), 'pol_mt1_c6': _v(1, 6), 'pol_mt1_c7': _v(1, 7), 'pol_mt1_c8': _v(1, 8),
+    'pol_mt2_c5_bf16x2': _v(2, 5, '-DCOPTER_POLICY_TANH_BF16X2=1'),
 }
 VARIANTS.update(json.loads(os.environ.get('COPTER_SWEEP_EXTRA', '{}')))
 
