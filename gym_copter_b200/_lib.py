@@ -50,7 +50,7 @@ class CopterPidGains(C.Structure):
 
 class CopterMlpPolicy(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('w1', 'b1', 'w2', 'b2', 'w3', 'b3')] + [
-        ('hidden', C.c_int32), ('out_scale', C.c_float), ('out_offset', C.c_float)]
+        ('hidden', C.c_int32), ('out_scale', C.c_float), ('out_offset', C.c_float), ('action_std', C.c_void_p)]
 
 
 SOURCE_KINDS = {'const': 0, 'randn': 1, 'uniform': 2, 'pid': 3}
@@ -108,7 +108,7 @@ def load():
     lib.copter_default_pid_gains.argtypes, lib.copter_default_pid_gains.restype = [C.POINTER(CopterPidGains)], None
     lib.copter_policy_mlp_f32.argtypes = [vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp]
     lib.copter_policy_mlp_f32.restype = i32
-    lib.copter_policy_rollout_f32.argtypes = [P, B, C.POINTER(CopterMlpPolicy), i64, i64, u64, i32, i32, i32, vp, vp, vp, vp, vp]
+    lib.copter_policy_rollout_f32.argtypes = [P, B, C.POINTER(CopterMlpPolicy), i64, i64, u64, i64, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.copter_policy_rollout_f32.restype = i32
     lib.copter_pipeline_create.argtypes, lib.copter_pipeline_create.restype = [i32, C.POINTER(vp)], i32
     lib.copter_pipeline_destroy.argtypes, lib.copter_pipeline_destroy.restype = [vp], i32

@@ -313,29 +313,34 @@ struct RolloutArgs {
 __device__ __forceinline__ float  log_t(float a)  { return logf(a); }
 __device__ __forceinline__ double log_t(double a) { return log(a); }
 
-// Command vector of (env, step): offset + scale * xi, xi_j = 1 | N(0,1) | U(-1,1), from
-// Philox4x32-10 with counter (env_lo, env_hi, step, 1) -- stream tag 1, the reset forces use 0.
+// Four variates xi_j = N(0,1) | U(-1,1) of (env, step, stream tag) from Philox4x32-10 with counter
+// (env_lo, env_hi, step, tag), key = seed (low word XOR the step's high word).
+template <typename T>
+__device__ __forceinline__ void draw_variates(uint64_t seed, uint64_t env, uint64_t step, uint32_t tag, bool uniform, T (&xi)[4]) {
+    uint32_t c[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)step, tag};
+    philox4x32_10(c, (uint32_t)seed ^ (uint32_t)(step >> 32), (uint32_t)(seed >> 32));
+    if (uniform) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xi[j] = (T)fma((double)c[j], 0x1p-31, -1.0);     // exact, one rounding
+    } else {                                                                         // Box-Muller, two pairs
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const T u1 = (T)(((double)c[2 * h] + 1.0) * 0x1p-32);                   // (0, 1]
+            const T u2 = (T)((double)c[2 * h + 1] * 0x1p-32);
+            const T r = sqrt_t((T)-2 * log_t(u1));
+            T sn, cs;
+            sincos_t((T)6.283185307179586 * u2, &sn, &cs);
+            xi[2 * h] = r * cs; xi[2 * h + 1] = r * sn;
+        }
+    }
+}
+
+// Command vector of (env, step): offset + scale * xi, xi_j = 1 | N(0,1) | U(-1,1); stream tag 1
+// (the reset forces use 0, the policy rollout's exploration noise 2).
 template <typename T, int A>
 __device__ __forceinline__ void draw_action(const RolloutArgs<T>& a, uint64_t env, uint64_t step, T (&act)[A]) {
     T xi[4] = {(T)1, (T)1, (T)1, (T)1};
-    if (a.src_kind != COPTER_SRC_CONST) {
-        uint32_t c[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)step, 1u};
-        philox4x32_10(c, (uint32_t)a.seed ^ (uint32_t)(step >> 32), (uint32_t)(a.seed >> 32));
-        if (a.src_kind == COPTER_SRC_UNIFORM) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) xi[j] = (T)fma((double)c[j], 0x1p-31, -1.0);     // exact, one rounding
-        } else {                                                                         // Box-Muller, two pairs
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const T u1 = (T)(((double)c[2 * h] + 1.0) * 0x1p-32);                   // (0, 1]
-                const T u2 = (T)((double)c[2 * h + 1] * 0x1p-32);
-                const T r = sqrt_t((T)-2 * log_t(u1));
-                T sn, cs;
-                sincos_t((T)6.283185307179586 * u2, &sn, &cs);
-                xi[2 * h] = r * cs; xi[2 * h + 1] = r * sn;
-            }
-        }
-    }
+    if (a.src_kind != COPTER_SRC_CONST) draw_variates<T>(a.seed, env, step, 1u, a.src_kind == COPTER_SRC_UNIFORM, xi);
 #pragma unroll
     for (int j = 0; j < A; ++j) act[j] = a.src_offset + a.src_scale * xi[j];
 }
@@ -524,8 +529,9 @@ struct PolicyRolloutArgs {
     float* state; uint32_t* meta; float* obs; float* reward_sum; uint8_t* done_any;
     const float* init_force; float* ep_return; double* stats;
     float* reward_tn; uint8_t* done_tn; float* action_tn; float* obs_tn;
-    int64_t n, stride, env_offset; uint64_t seed; int n_steps, auto_reset;
+    int64_t n, stride, env_offset, first_step; uint64_t seed; int n_steps, auto_reset;
     PolicyWeights w;
+    const float* action_std;    // [A] or null: Gaussian exploration noise around the network's output
 };
 
 #ifndef COPTER_POLICY_ROLLOUT_CTAS_PER_SM
@@ -573,6 +579,12 @@ copter_policy_rollout_kernel(const __grid_constant__ KParams<float> kp, const __
             bool dn = false; int cause = 0, ep_len = 0; T ep_ret = (T)0;
             if (valid) {
                 T m[4];
+                if (a.action_std) {                                   // exploration: action ~ N(policy(obs), std^2)
+                    T xi[4];
+                    draw_variates<T>(a.seed, (uint64_t)(a.env_offset + i), (uint64_t)(a.first_step + t), 2u, false, xi);
+#pragma unroll
+                    for (int j = 0; j < A; ++j) act[j] = fmaf(a.action_std[j], xi[j], act[j]);
+                }
                 if (a.action_tn) {
                     T* row = a.action_tn + ((int64_t)t * a.n + i) * A;
                     if constexpr (A == 4) *reinterpret_cast<float4*>(row) = make_float4(act[0], act[1], act[2], act[3]);
@@ -1058,12 +1070,12 @@ int copter_policy_mlp_f32(const void* state, int64_t state_stride, int64_t n, in
 }
 
 int copter_policy_rollout_f32(const CopterParams* p, const CopterBuffers* b, const CopterMlpPolicy* policy, int64_t n,
-                              int64_t env_offset, uint64_t seed, int n_steps, int variant, int flags,
+                              int64_t env_offset, uint64_t seed, int64_t first_step, int n_steps, int variant, int flags,
                               float* reward_tn, uint8_t* done_tn, float* action_tn, float* obs_tn, void* stream) {
     int e = check_params(p);
     if (e) return e;
     if (!b || !b->state || !b->meta || !policy_ok(policy)) return COPTER_E_ARG;
-    if (n < 0 || env_offset < 0 || n_steps < 1 || policy->hidden != kPolH || (b->state_stride > 0 && b->state_stride < n)) return COPTER_E_RANGE;
+    if (n < 0 || env_offset < 0 || first_step < 0 || n_steps < 1 || policy->hidden != kPolH || (b->state_stride > 0 && b->state_stride < n)) return COPTER_E_RANGE;
     if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
     if (!aligned16(b->state) || (b->obs && !aligned16(b->obs)) || (action_tn && !aligned16(action_tn)) || (obs_tn && !aligned16(obs_tn))) return COPTER_E_ALIGN;
     if (n == 0) return 0;
@@ -1073,8 +1085,8 @@ int copter_policy_rollout_f32(const CopterParams* p, const CopterBuffers* b, con
     a.init_force = (const float*)b->init_force; a.ep_return = (float*)b->ep_return; a.stats = b->stats;
     a.reward_tn = reward_tn; a.done_tn = done_tn; a.action_tn = action_tn; a.obs_tn = obs_tn;
     a.n = n; a.stride = b->state_stride > 0 ? b->state_stride : n; a.env_offset = env_offset; a.seed = seed;
-    a.n_steps = n_steps; a.auto_reset = (flags & COPTER_F_AUTO_RESET) ? 1 : 0;
-    a.w = policy_weights(policy);
+    a.first_step = first_step; a.n_steps = n_steps; a.auto_reset = (flags & COPTER_F_AUTO_RESET) ? 1 : 0;
+    a.w = policy_weights(policy); a.action_std = policy->action_std;
     cudaStream_t s = (cudaStream_t)stream;
     switch (variant) {
         case COPTER_LANDER3D: return launch_policy_rollout_v<COPTER_LANDER3D>(kp, a, s);

@@ -156,9 +156,14 @@ class FusedPolicyRollout:
     horizon    T
     store_obs / store_actions   also record obs_t [T,N,O] (what the policy saw) / action_t [T,N,A]
                                 (the command before the env's clip), e.g. for a PPO update
+    action_std  None (deterministic policy), a float, or an fp32 CUDA tensor [A] (e.g. exp of a learnable
+                log-std, read in place): Gaussian exploration, action = policy(obs) + std * N(0,1), the
+                noise from Philox keyed by (seed, global env id, env.rollout_step + t) -- reproducible and
+                independent of how the rollout is cut into horizons
     """
 
-    def __init__(self, env, net, horizon, out_scale=1.0, out_offset=0.0, store_obs=False, store_actions=False):
+    def __init__(self, env, net, horizon, out_scale=1.0, out_offset=0.0, store_obs=False, store_actions=False,
+                 action_std=None):
         probe = FusedMLPPolicy(env, net, out_scale, out_offset)       # same parameter checks
         if env.k_substeps != 1:
             raise CopterError('FusedPolicyRollout steps with k_substeps == 1')
@@ -166,7 +171,14 @@ class FusedPolicyRollout:
         if self.horizon < 1:
             raise CopterError('horizon must be >= 1')
         self.params = probe.params
-        self.policy = _lib.CopterMlpPolicy(*[p.data_ptr() for p in self.params], 64, float(out_scale), float(out_offset))
+        if action_std is not None and not isinstance(action_std, torch.Tensor):
+            action_std = torch.full((env.action_size,), float(action_std), dtype=torch.float32, device=env.device)
+        if action_std is not None and (action_std.dtype != torch.float32 or action_std.device != env.device
+                                       or action_std.numel() != env.action_size or not action_std.is_contiguous()):
+            raise CopterError('action_std must be a contiguous fp32 tensor [A] on the env device')
+        self.action_std = action_std
+        self.policy = _lib.CopterMlpPolicy(*[p.data_ptr() for p in self.params], 64, float(out_scale), float(out_offset),
+                                           action_std.data_ptr() if action_std is not None else None)
         n, dev = env.num_envs, env.device
         self.rewards = torch.zeros((self.horizon, n), dtype=torch.float32, device=dev)
         self.dones = torch.zeros((self.horizon, n), dtype=torch.uint8, device=dev)
@@ -185,12 +197,13 @@ class FusedPolicyRollout:
                 b.obs = None
             _lib.check(self.lib.copter_policy_rollout_f32(
                 C.byref(env.params), C.byref(b), C.byref(self.policy), env.num_envs, env.env_offset,
-                env.seed_value & 0xFFFFFFFFFFFFFFFF, self.horizon, VARIANT_IDS[env.variant],
+                env.seed_value & 0xFFFFFFFFFFFFFFFF, env.rollout_step, self.horizon, VARIANT_IDS[env.variant],
                 _lib.F_AUTO_RESET if env.auto_reset else 0, self.rewards.data_ptr(), self.dones.data_ptr(),
                 self.actions.data_ptr() if self.actions is not None else None,
                 self.obs.data_ptr() if self.obs is not None else None,
                 C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)), 'copter_policy_rollout')
         env.launches += 1
+        env.rollout_step += self.horizon
         return self.rewards, self.dones.view(torch.bool), env.obs if env.write_obs else None
 
 

@@ -242,15 +242,24 @@ int copter_policy_mlp_f32(const void* state, int64_t state_stride, int64_t n, in
  * reward_tn float[n_steps][n], done_tn uint8[n_steps][n], action_tn float[n_steps][n][A] (the
  * commands before the env's clip), obs_tn float[n_steps][n][O] (the observation the policy
  * acted on at step t).
+ * Exploration (what an on-policy learner such as PPO rolls out): with policy->action_std set
+ * (A floats, device memory) the command is drawn around the network's output,
+ *     action_j = out_offset + out_scale * tanh(.)_j + action_std[j] * xi_j,   xi ~ N(0,1),
+ * xi from Philox4x32-10 with counter (env_lo, env_hi, first_step + t, 2) (Box-Muller as in
+ * COPTER_SRC_RANDN; stream tag 2), key = seed: reproducible, and independent of how the rollout
+ * is cut into launches when the caller advances first_step by n_steps.  action_tn then holds the
+ * sampled commands the learner needs for its log-probabilities.
  */
 typedef struct CopterMlpPolicy {
     const float *w1, *b1, *w2, *b2, *w3, *b3;   /* torch.nn.Linear layouts W[out][in], b[out]; fp32 device memory */
     int32_t hidden;                             /* must be 64 */
     float out_scale, out_offset;                /* action = out_offset + out_scale * tanh(.) */
+    const float* action_std;                    /* nullable: [A] standard deviations of the Gaussian exploration noise */
 } CopterMlpPolicy;
 int copter_policy_rollout_f32(const CopterParams* p, const CopterBuffers* b, const CopterMlpPolicy* policy,
-                              int64_t n, int64_t env_offset, uint64_t seed, int n_steps, int variant, int flags,
-                              float* reward_tn, uint8_t* done_tn, float* action_tn, float* obs_tn, void* stream);
+                              int64_t n, int64_t env_offset, uint64_t seed, int64_t first_step, int n_steps,
+                              int variant, int flags, float* reward_tn, uint8_t* done_tn, float* action_tn,
+                              float* obs_tn, void* stream);
 
 /*
  * The same step for callers that hold HOST arrays (the reference's callers pass numpy

@@ -130,14 +130,15 @@ def reset_force(seed, env_id, episode, scale, dtype=np.float64):
     return np.stack(f, axis=-1).astype(dtype)
 
 
-def source_actions(seed, env_id, step, kind, scale, offset, act_size, dtype=np.float64):
+def source_actions(seed, env_id, step, kind, scale, offset, act_size, dtype=np.float64, tag=1):
     """
     The product's on-device action sources (copter_rollout_*), restated: action_j = offset +
-    scale * xi_j with xi from Philox4x32-10, counter (env_lo, env_hi, step, 1), key = seed
+    scale * xi_j with xi from Philox4x32-10, counter (env_lo, env_hi, step, tag), key = seed
     (low word XOR step's high word).  'const' and 'uniform' are bit-exact in `dtype`;
     'randn' (Box-Muller on u1 = (c+1) 2^-32, u2 = c 2^-32, pairs (c0,c1), (c2,c3)) agrees with
     the device to the accuracy of its log / sin / cos.  lander.py:21,42 are the reference's
-    two streams: const 1.625e-2 and 1.625e-2 * randn(4).
+    two streams: const 1.625e-2 and 1.625e-2 * randn(4).  tag 1 = the action sources, tag 2 = the
+    exploration noise of copter_policy_rollout_f32 (kind 'randn').
     """
     T = np.dtype(dtype).type
     env_id = np.asarray(env_id, dtype=np.uint64)
@@ -145,7 +146,7 @@ def source_actions(seed, env_id, step, kind, scale, offset, act_size, dtype=np.f
     xi = np.ones((n, 4), dtype)
     if kind != 'const':
         c = philox4x32_10(env_id & _U32, env_id >> np.uint64(32), np.full(n, step & 0xFFFFFFFF, np.uint64),
-                          np.ones(n, np.uint64), (seed & 0xFFFFFFFF) ^ (step >> 32), (seed >> 32) & 0xFFFFFFFF)
+                          np.full(n, tag, np.uint64), (seed & 0xFFFFFFFF) ^ (step >> 32), (seed >> 32) & 0xFFFFFFFF)
         c = [x.astype(np.float64) for x in c]
         if kind == 'uniform':
             xi = np.stack([x * 2.0 ** -31 - 1.0 for x in c], -1).astype(dtype)

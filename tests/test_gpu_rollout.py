@@ -335,3 +335,43 @@ def test_fused_policy_rollout_argument_errors(pkg):
         pkg.FusedPolicyRollout(env, good, 4).run()          # not reset
     with pytest.raises(pkg.CopterError):
         pkg.FusedPolicyRollout(pkg.CopterVecEnv('Lander3D', 64, k_substeps=2), good, 4)
+
+
+def test_fused_policy_rollout_exploration_noise(pkg):
+    """action_std: the sampled command is policy(obs) + std * xi with xi the documented Philox
+    stream (counter (env, step, 2), Box-Muller) -- checked against the oracle's restatement of
+    the stream and the policy kernel's own output on the recorded observations; the trajectory
+    equals stepping the recorded commands; cutting the horizon differently changes nothing."""
+    n, T, seed, off = 1031, 24, 0xABCDEF0123, 5000
+    mk = lambda: pkg.CopterVecEnv('Lander3D', n, seed=seed, env_offset=off)          # noqa: E731
+    pol = pkg.mlp_policy(10, 4, dtype=torch.float32, seed=9)
+    std = torch.tensor([0.004, 0.002, 0.001, 0.003], device='cuda')
+    a_env, b_env, c_env = mk(), mk(), mk()
+    for e in (a_env, b_env, c_env):
+        e.reset()
+    a_env.rollout_step = b_env.rollout_step = 2 ** 32 + 7
+    ro = pkg.FusedPolicyRollout(a_env, pol.net, T, out_scale=0.01, out_offset=0.0166, store_obs=True, store_actions=True, action_std=std)
+    r, d, _ = ro.run()
+    ids = np.arange(n, dtype=np.uint64) + np.uint64(off)
+    mean_k = pkg.FusedMLPPolicy(c_env, pol.net, out_scale=0.01, out_offset=0.0166)
+    for t in range(T):
+        xi = source_actions(seed, ids, 2 ** 32 + 7 + t, 'randn', 1.0, 0.0, 4, np.float32, tag=2)
+        st = torch.zeros((n, 12), device='cuda')
+        st[:, :10] = ro.obs[t]
+        c_env.set_state(st)
+        mean = mean_k().clone()
+        got = (ro.actions[t] - mean).cpu().numpy() / std.cpu().numpy()
+        assert np.max(np.abs(got - xi)) <= 2e-4, (t, np.max(np.abs(got - xi)))       # fp32 cancellation in (action - mean) / std
+        # replay of the recorded commands through the step kernel
+        o, r2, d2, _, _ = b_env.step(ro.actions[t])
+        assert torch.equal(d2, d[t]) and merr(r[t].cpu().numpy(), r2.cpu().numpy()) <= 1e-5
+    assert torch.equal(a_env.state, b_env.state) and torch.equal(a_env.meta, b_env.meta)
+    z = ((ro.actions - 0.0166).cpu().numpy())
+    assert 0.5 * 0.001 < z[..., 2].std() < 0.02          # noise present, of the configured scale
+    # same rollout cut into horizons of 5, 7 and 12 steps
+    e2 = mk(); e2.reset(); e2.rollout_step = 2 ** 32 + 7
+    for h in (5, 7, 12):
+        pkg.FusedPolicyRollout(e2, pol.net, h, out_scale=0.01, out_offset=0.0166, action_std=std).run()
+    assert torch.equal(e2.state, a_env.state) and torch.equal(e2.meta, a_env.meta) and e2.rollout_step == a_env.rollout_step
+    with pytest.raises(pkg.CopterError):
+        pkg.FusedPolicyRollout(a_env, pol.net, 4, action_std=torch.ones(3, device='cuda'))
