@@ -1,0 +1,42 @@
+"""bench.py's CPU-checkable contract: the reference arm prints ONE JSON line with the keys the
+driver reads (a bounded sample of the workload on the host cores), and the product arm refuses
+to run without a CUDA device instead of falling back to anything."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '2', '--warmup', '1'],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'env-steps/s' and d['higher_is_better'] is True
+    assert d['metric'].startswith('env-steps/sec') and d['steps'] == 2 and d['warmup'] == 1 and d['n_gpus'] == 1
+    assert d['value'] > 1e3
+    cb = d['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and 'sample' in cb
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert d['config']['action_stream'] == 'randn' and 'workload' in d['config']
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ''
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_product_arm_needs_a_gpu():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and 'CUDA' in (r.stderr + r.stdout)
