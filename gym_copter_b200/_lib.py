@@ -9,7 +9,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 # COPTER_B200_LIB: developer knob used by tools/sweep.py to time alternative builds
 LIB_PATH = os.environ.get('COPTER_B200_LIB') or os.path.join(PKG, 'libcopter_b200.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 STATS_LEN = 16
 STATS_SLOTS = 64
 F_AUTO_RESET = 1
@@ -45,7 +45,8 @@ class CopterActionSource(C.Structure):
 class CopterPidGains(C.Structure):
     _fields_ = [(n, C.c_double) for n in ('rate_kp', 'rate_ki', 'rate_kd', 'rate_windup', 'rate_big',
                                           'pos_kp', 'pos_ki', 'pos_kd', 'pos_windup', 'pos_target',
-                                          'descent_kp', 'descent_kd')]
+                                          'descent_kp', 'descent_kd',
+                                          'alt_kp', 'alt_ki', 'alt_kd', 'alt_windup', 'alt_target')]
 
 
 class CopterMlpPolicy(C.Structure):
@@ -53,7 +54,7 @@ class CopterMlpPolicy(C.Structure):
         ('hidden', C.c_int32), ('out_scale', C.c_float), ('out_offset', C.c_float), ('action_std', C.c_void_p)]
 
 
-SOURCE_KINDS = {'const': 0, 'randn': 1, 'uniform': 2, 'pid': 3}
+SOURCE_KINDS = {'const': 0, 'randn': 1, 'uniform': 2, 'pid': 3, 'pid_hover': 4}
 
 
 class CopterError(RuntimeError):

@@ -306,8 +306,9 @@ struct RolloutArgs {
     T* reward_tn; uint8_t* done_tn; T* action_tn;
     int64_t n, stride, env_offset, first_step; uint64_t seed;
     int n_steps, auto_reset, src_kind; T src_scale, src_offset;
-    T* controller;              // [n][16] PID memories (COPTER_SRC_PID)
+    T* controller;              // [n][16] PID memories (COPTER_SRC_PID), [n][24] (COPTER_SRC_PID_HOVER)
     T rate_kp, rate_ki, rate_kd, rate_windup, rate_big, pos_kp, pos_ki, pos_kd, pos_windup, pos_target, descent_kp, descent_kd;
+    T alt_kp, alt_ki, alt_kd, alt_windup, alt_target;
 };
 
 __device__ __forceinline__ float  log_t(float a)  { return logf(a); }
@@ -401,7 +402,29 @@ __device__ __forceinline__ void pid_heuristic(const RolloutArgs<T>& a, const T (
     for (int j = 0; j < 4; ++j) act[j] = a.src_offset + a.src_scale * mix[j];
 }
 
-template <typename T, int VARIANT, bool STATS, bool PID>
+// Hover3D.heuristic (attic/mars/hover3d.py:65-92, controllers :33-38 and hover.py:23): the same
+// roll/pitch loops plus a yaw-rate PID and the altitude-hold set-point controller
+// (pidcontrollers/__init__.py:91-99: demand on (-z, -dz), position error -> climb-rate set-point ->
+// PI on the climb rate), mixed with the yaw term.  `mem` = (roll_rate, pitch_rate, x_poshold [fed y],
+// y_poshold [fed x], yaw_rate, altitude).
+template <typename T>
+__device__ __forceinline__ void pid_hover_heuristic(const RolloutArgs<T>& a, const T (&s)[12], PidMem<T> (&mem)[6], T (&act)[4]) {
+    T o[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) o[j] = (T)(float)s[j];
+    const T roll_todo = rate_demand<T>(a, o[7], mem[0]) + poshold_demand<T>(a, o[2], o[3], mem[2]);
+    const T pitch_todo = rate_demand<T>(a, -o[9], mem[1]) + poshold_demand<T>(a, o[0], o[1], mem[3]);
+    const T yaw_todo = rate_demand<T>(a, -o[11], mem[4]);
+    const T climb_target = (a.alt_target - (-o[4])) * (T)1;                                // posPid(1, 0, 0) on -z
+    const T hover_todo = pid_compute<T>(a.alt_kp, a.alt_ki, a.alt_kd, a.alt_windup, climb_target, -o[5], mem[5]);
+    const T t = (hover_todo + (T)1) / (T)2, r = roll_todo, p = pitch_todo, y = yaw_todo;
+    const T mix[4] = {t - r - p - y, t + r + p - y, t + r - p + y, t - r + p + y};         // hover3d.py:92
+#pragma unroll
+    for (int j = 0; j < 4; ++j) act[j] = a.src_offset + a.src_scale * mix[j];
+}
+
+// PID: 0 = drawn commands, 1 = landing heuristic (4 controller memories), 2 = hover heuristic (6)
+template <typename T, int VARIANT, bool STATS, int PID>
 __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (PID ? 5 : COPTER_F32_CTAS_PER_SM) : 2)
 copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant__ RolloutArgs<T> a) {
     constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A;
@@ -435,18 +458,20 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
         RewardRun<T> run;
         run_begin<T, VARIANT>(kp, run, s);
         T na = (T)0, nc = (T)0, dz_prev = s[5];
-        PidMem<T> mem[4];
-        if constexpr (PID) {
+        constexpr int NMEM = PID == 2 ? 6 : 4;
+        PidMem<T> mem[NMEM];
+        if constexpr (PID != 0) {
             if (valid) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) { const T* q = a.controller + i * 16 + 4 * c; mem[c].errI = q[0]; mem[c].last = q[1]; mem[c].d1 = q[2]; mem[c].d2 = q[3]; }
+                for (int c = 0; c < NMEM; ++c) { const T* q = a.controller + i * (4 * NMEM) + 4 * c; mem[c].errI = q[0]; mem[c].last = q[1]; mem[c].d1 = q[2]; mem[c].d2 = q[3]; }
             }
         }
         for (int t = 0; t < a.n_steps; ++t) {
             bool dn = false; int cause = 0, ep_len = 0; T ep_ret = (T)0;
             if (valid) {
                 T act[A], m[4];
-                if constexpr (PID && A == 4) pid_heuristic<T>(a, s, mem, act);
+                if constexpr (PID == 1 && A == 4) pid_heuristic<T>(a, s, mem, act);
+                else if constexpr (PID == 2 && A == 4) pid_hover_heuristic<T>(a, s, mem, act);
                 else draw_action<T, A>(a, (uint64_t)(a.env_offset + i), (uint64_t)(a.first_step + t), act);
                 if (a.action_tn) {
 #pragma unroll
@@ -507,9 +532,9 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
             if (a.reward_sum) a.reward_sum[i] = total;
             if (a.done_any) a.done_any[i] = done_any ? 1 : 0;
             if (STATS && a.ep_return) a.ep_return[i] = ret;
-            if constexpr (PID) {
+            if constexpr (PID != 0) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) { T* q = a.controller + i * 16 + 4 * c; q[0] = mem[c].errI; q[1] = mem[c].last; q[2] = mem[c].d1; q[3] = mem[c].d2; }
+                for (int c = 0; c < NMEM; ++c) { T* q = a.controller + i * (4 * NMEM) + 4 * c; q[0] = mem[c].errI; q[1] = mem[c].last; q[2] = mem[c].d1; q[3] = mem[c].d2; }
             }
         }
         if (a.obs) write_obs_rows<VARIANT, T>(a.obs, tiles[warp], lane, row0, rows, s);
@@ -771,16 +796,23 @@ int launch_step(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_
 
 template <typename T, int VARIANT>
 int launch_rollout_v(const KParams<T>& kp, const RolloutArgs<T>& a, cudaStream_t s) {
-    if (a.src_kind == COPTER_SRC_PID) {
+    if (a.src_kind == COPTER_SRC_PID || a.src_kind == COPTER_SRC_PID_HOVER) {
         if constexpr (Variant<VARIANT>::A == 4) {
-            if (a.stats) copter_rollout_kernel<T, VARIANT, true, true><<<grid_for<copter_rollout_kernel<T, VARIANT, true, true>>(a.n), kBlock, 0, s>>>(kp, a);
-            else         copter_rollout_kernel<T, VARIANT, false, true><<<grid_for<copter_rollout_kernel<T, VARIANT, false, true>>(a.n), kBlock, 0, s>>>(kp, a);
+            if (a.src_kind == COPTER_SRC_PID) {
+                if (a.stats) copter_rollout_kernel<T, VARIANT, true, 1><<<grid_for<copter_rollout_kernel<T, VARIANT, true, 1>>(a.n), kBlock, 0, s>>>(kp, a);
+                else         copter_rollout_kernel<T, VARIANT, false, 1><<<grid_for<copter_rollout_kernel<T, VARIANT, false, 1>>(a.n), kBlock, 0, s>>>(kp, a);
+            } else if constexpr (Variant<VARIANT>::O == 12) {
+                if (a.stats) copter_rollout_kernel<T, VARIANT, true, 2><<<grid_for<copter_rollout_kernel<T, VARIANT, true, 2>>(a.n), kBlock, 0, s>>>(kp, a);
+                else         copter_rollout_kernel<T, VARIANT, false, 2><<<grid_for<copter_rollout_kernel<T, VARIANT, false, 2>>(a.n), kBlock, 0, s>>>(kp, a);
+            } else {
+                return COPTER_E_VARIANT;      // the hover heuristic reads the yaw rate: full-state observation only
+            }
         } else {
-            return COPTER_E_VARIANT;          // the heuristic is defined for the four-motor envs only
+            return COPTER_E_VARIANT;          // the heuristics are defined for the four-motor envs only
         }
     } else {
-        if (a.stats) copter_rollout_kernel<T, VARIANT, true, false><<<grid_for<copter_rollout_kernel<T, VARIANT, true, false>>(a.n), kBlock, 0, s>>>(kp, a);
-        else         copter_rollout_kernel<T, VARIANT, false, false><<<grid_for<copter_rollout_kernel<T, VARIANT, false, false>>(a.n), kBlock, 0, s>>>(kp, a);
+        if (a.stats) copter_rollout_kernel<T, VARIANT, true, 0><<<grid_for<copter_rollout_kernel<T, VARIANT, true, 0>>(a.n), kBlock, 0, s>>>(kp, a);
+        else         copter_rollout_kernel<T, VARIANT, false, 0><<<grid_for<copter_rollout_kernel<T, VARIANT, false, 0>>(a.n), kBlock, 0, s>>>(kp, a);
     }
     return (int)cudaGetLastError();
 }
@@ -793,9 +825,9 @@ int launch_rollout(const CopterParams* p, const CopterBuffers* b, const CopterAc
     int e = check_params(p);
     if (e) return e;
     if (!b || !b->state || !b->meta || !src) return COPTER_E_ARG;
-    if (src->kind == COPTER_SRC_PID && (!controller || !aligned16(controller))) return COPTER_E_ARG;
+    if ((src->kind == COPTER_SRC_PID || src->kind == COPTER_SRC_PID_HOVER) && (!controller || !aligned16(controller))) return COPTER_E_ARG;
     if (n < 0 || env_offset < 0 || n_steps < 1 || first_step < 0 || (b->state_stride > 0 && b->state_stride < n)) return COPTER_E_RANGE;
-    if (src->kind < COPTER_SRC_CONST || src->kind > COPTER_SRC_PID) return COPTER_E_RANGE;
+    if (src->kind < COPTER_SRC_CONST || src->kind > COPTER_SRC_PID_HOVER) return COPTER_E_RANGE;
     if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
     if (!aligned16(b->state) || (b->obs && !aligned16(b->obs))) return COPTER_E_ALIGN;
     if (n == 0) return 0;
@@ -813,6 +845,7 @@ int launch_rollout(const CopterParams* p, const CopterBuffers* b, const CopterAc
     a.rate_kp = (T)g.rate_kp; a.rate_ki = (T)g.rate_ki; a.rate_kd = (T)g.rate_kd; a.rate_windup = (T)g.rate_windup; a.rate_big = (T)g.rate_big;
     a.pos_kp = (T)g.pos_kp; a.pos_ki = (T)g.pos_ki; a.pos_kd = (T)g.pos_kd; a.pos_windup = (T)g.pos_windup; a.pos_target = (T)g.pos_target;
     a.descent_kp = (T)g.descent_kp; a.descent_kd = (T)g.descent_kd;
+    a.alt_kp = (T)g.alt_kp; a.alt_ki = (T)g.alt_ki; a.alt_kd = (T)g.alt_kd; a.alt_windup = (T)g.alt_windup; a.alt_target = (T)g.alt_target;
     cudaStream_t s = (cudaStream_t)stream;
     switch (variant) {
         case COPTER_LANDER3D: return launch_rollout_v<T, COPTER_LANDER3D>(kp, a, s);
@@ -1030,6 +1063,7 @@ void copter_default_pid_gains(CopterPidGains* g) {
     g->rate_big = 40.0 * M_PI / 180.0;                                                    // BIG_DEGREES_PER_SECOND
     g->pos_kp = 0.00001; g->pos_ki = 0.1; g->pos_kd = 4.0; g->pos_windup = 0.2; g->pos_target = 0.0;   // PositionHoldPidController (:102-107)
     g->descent_kp = 1.15; g->descent_kd = 1.33;                                           // DescentPidController (:110-121)
+    g->alt_kp = 0.2; g->alt_ki = 3.0; g->alt_kd = 0.0; g->alt_windup = 0.2; g->alt_target = 5.0;       // AltitudeHoldPidController (:93), windup :14
 }
 
 int copter_dynamics_f32(const CopterParams* p, void* state, uint8_t* status, int32_t* ticks, void* perturb, const void* motors, int64_t n, void* stream) {

@@ -73,6 +73,63 @@ __device__ __forceinline__ uint32_t tanh_pack(float lo, float hi) {
     return pack_bf16(tanh_fast(lo), tanh_fast(hi));
 #endif
 }
+// The same pair on the FMA pipe instead of the XU: clamp to |x| <= 3.25 and evaluate the odd
+// degree-13 polynomial x P(x^2) (weighted minimax fit, tools/fit_tanh_poly.py).  |error| <= 2.0e-3
+// absolute and <= 2.3e-3 relative, i.e. inside the half-ulp (2^-9 .. 2^-8 relative) of the bf16
+// rounding that follows; MUFU.TANH is 5e-4.  The policy kernels are bound by the XU pipe while the
+// FMA pipe idles (10 % busy, profiles/r1_policy_kernel_ncu_full.txt), so the n-tiles selected by
+// COPTER_POLICY_POLY_MASK take this route (the FlashAttention-4 exp2 trick, applied to tanh).
+#ifndef COPTER_POLICY_POLY_MASK
+#define COPTER_POLICY_POLY_MASK 0x00     // bit nt set: hidden n-tile nt (8 columns) of both layers uses the polynomial
+#endif
+#ifndef COPTER_POLICY_POLY_F32X2
+#define COPTER_POLICY_POLY_F32X2 1       // packed fma.rn.f32x2 (one issue slot per pair) vs scalar FFMA with immediates
+#endif
+constexpr float kTanhClamp = 3.25f;
+__host__ __device__ constexpr float tanh_poly_coef(int k) {    // coefficient of x^(2k+1)
+    constexpr float c[7] = {9.977270291e-01f, -3.117916466e-01f, 9.229137325e-02f, -1.838625564e-02f,
+                            2.184749761e-03f, -1.380842544e-04f, 3.552717362e-06f};
+    return c[k];
+}
+__device__ __forceinline__ uint64_t f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t tanh_pack_poly(float lo, float hi) {
+    lo = fminf(fmaxf(lo, -kTanhClamp), kTanhClamp);
+    hi = fminf(fmaxf(hi, -kTanhClamp), kTanhClamp);
+#if COPTER_POLICY_POLY_F32X2
+    const uint64_t x = f32x2(lo, hi), u = mul_f32x2(x, x);
+    uint64_t p = f32x2(tanh_poly_coef(6), tanh_poly_coef(6));
+#pragma unroll
+    for (int k = 5; k >= 0; --k) p = fma_f32x2(p, u, f32x2(tanh_poly_coef(k), tanh_poly_coef(k)));
+    const uint64_t r = mul_f32x2(p, x);
+    float rl, rh;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(rl), "=f"(rh) : "l"(r));
+    return pack_bf16(rl, rh);
+#else
+    const float ul = lo * lo, uh = hi * hi;
+    float pl = tanh_poly_coef(6), ph = tanh_poly_coef(6);
+#pragma unroll
+    for (int k = 5; k >= 0; --k) { pl = fmaf(pl, ul, tanh_poly_coef(k)); ph = fmaf(ph, uh, tanh_poly_coef(k)); }
+    return pack_bf16(pl * lo, ph * hi);
+#endif
+}
+// hidden n-tile nt: XU or FMA-pipe tanh (nt is a constant once the layer loops are unrolled)
+__device__ __forceinline__ uint32_t tanh_pack_nt(int nt, float lo, float hi) {
+    return ((COPTER_POLICY_POLY_MASK >> nt) & 1) ? tanh_pack_poly(lo, hi) : tanh_pack(lo, hi);
+}
 // D = A B + D
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -173,8 +230,8 @@ __device__ __forceinline__ void policy_forward_warp(const PolicySmem& sm, Policy
             for (int mt = 0; mt < MT; ++mt) {
                 float c[4];
                 mma_bf16_bias(c, a1[mt], b.x, b.y, bias);
-                h[mt][nt >> 1][(nt & 1) * 2 + 0] = tanh_pack(c[0], c[1]);      // rows g
-                h[mt][nt >> 1][(nt & 1) * 2 + 1] = tanh_pack(c[2], c[3]);      // rows g + 8
+                h[mt][nt >> 1][(nt & 1) * 2 + 0] = tanh_pack_nt(nt, c[0], c[1]);      // rows g
+                h[mt][nt >> 1][(nt & 1) * 2 + 1] = tanh_pack_nt(nt, c[2], c[3]);      // rows g + 8
             }
         }
 
@@ -201,8 +258,8 @@ __device__ __forceinline__ void policy_forward_warp(const PolicySmem& sm, Policy
                 }
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                    a3[mt][half * 2 + 0] = tanh_pack(c[mt][0], c[mt][1]);
-                    a3[mt][half * 2 + 1] = tanh_pack(c[mt][2], c[mt][3]);
+                    a3[mt][half * 2 + 0] = tanh_pack_nt(nt, c[mt][0], c[mt][1]);
+                    a3[mt][half * 2 + 1] = tanh_pack_nt(nt, c[mt][2], c[mt][3]);
                 }
             }
             const uint4 b = sm.w3[kt3 >> 1][lane];

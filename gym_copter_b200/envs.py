@@ -249,6 +249,10 @@ class CopterVecEnv:
           source='pid'      action = offset + scale*mixer(PID heuristic of attic/mars/lander3d.py:64-87
                             on the previous observation); `pid_gains` = dict of CopterPidGains
                             overrides; controller memories live in `self.controller` [N,16]
+          source='pid_hover' the hover demo's heuristic (attic/mars/hover3d.py:65-92: roll/pitch/yaw
+                            rate PIDs, position hold, altitude hold at `alt_target` = 5 m), Hover3D
+                            only; `self.controller` is [N,24].  scale=0.03312 (twice the hover
+                            command) holds the live vehicle at the target with the reference's gains
         Step for step identical to `n_steps` calls of step() with k_substeps=1 on the same
         commands.  Returns a dict: 'obs' (after the last step), 'reward_sum' [N], 'done_any'
         [N] bool, plus 'rewards' [T,N], 'dones' [T,N] bool, 'actions' [T,N,A] when recorded.
@@ -258,13 +262,16 @@ class CopterVecEnv:
         if source not in SOURCE_KINDS:
             raise ValueError('source must be one of %s' % sorted(SOURCE_KINDS))
         d_scale, d_off = {'const': (0.0, 1.625e-2), 'randn': (1.625e-2, 0.0), 'uniform': (1.0, 0.0),
-                          'pid': (1.0, 0.0)}[source]
+                          'pid': (1.0, 0.0), 'pid_hover': (1.0, 0.0)}[source]
         gains = None
-        if source == 'pid':
+        if source in ('pid', 'pid_hover'):
             if self.action_size != 4:
-                raise CopterError('the PID heuristic drives the four-motor variants only')
-            if self.controller is None:
-                self.controller = torch.zeros((self.num_envs, 16), dtype=self.dtype, device=self.device)
+                raise CopterError('the PID heuristics drive the four-motor variants only')
+            if source == 'pid_hover' and self.obs_size != 12:
+                raise CopterError('the hover heuristic reads the yaw rate: Hover3D (12-component observation) only')
+            width = 24 if source == 'pid_hover' else 16
+            if self.controller is None or self.controller.shape[1] != width:
+                self.controller = torch.zeros((self.num_envs, width), dtype=self.dtype, device=self.device)
             gains = _lib.default_pid_gains(**(pid_gains or {}))
         src = CopterActionSource(SOURCE_KINDS[source], 0, d_scale if scale is None else float(scale),
                                  d_off if offset is None else float(offset))

@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define COPTER_ABI_VERSION 1
+#define COPTER_ABI_VERSION 2
 
 /* dynamics/__init__.py:65-68 */
 enum { COPTER_STATUS_CRASHED = 0, COPTER_STATUS_LANDED = 1, COPTER_STATUS_LEVELING = 2, COPTER_STATUS_AIRBORNE = 3 };
@@ -170,7 +170,7 @@ int copter_step_f64(const CopterParams* p, const CopterBuffers* b, int64_t n, in
  * Optional per-step outputs: reward_tn T[n_steps][n], done_tn uint8[n_steps][n] (GAE-ready
  * layout), action_tn T[n_steps][n][A] (the commands used, before clipping).
  */
-enum { COPTER_SRC_CONST = 0, COPTER_SRC_RANDN = 1, COPTER_SRC_UNIFORM = 2, COPTER_SRC_PID = 3 };
+enum { COPTER_SRC_CONST = 0, COPTER_SRC_RANDN = 1, COPTER_SRC_UNIFORM = 2, COPTER_SRC_PID = 3, COPTER_SRC_PID_HOVER = 4 };
 typedef struct CopterActionSource { int32_t kind; int32_t reserved; double scale; double offset; } CopterActionSource;
 
 /*
@@ -183,11 +183,21 @@ typedef struct CopterActionSource { int32_t kind; int32_t reserved; double scale
  * phi-rate, theta-rate, x_poshold, y_poshold); it persists across episodes exactly as the
  * reference's controller objects do (they live in the env, not in an episode); zero it to start.
  * `gains` NULL selects the reference's constants (copter_default_pid_gains).
+ *
+ * COPTER_SRC_PID_HOVER: the hover demo's heuristic -- attic/mars/hover3d.py:65-92 (controller set
+ * :33-38 plus the altitude-hold controller of attic/mars/hover.py:23, pidcontrollers/__init__.py:
+ * 70-99): the same roll/pitch loops, a yaw-rate PID on -dpsi and the altitude-hold set-point
+ * controller on (-z, -dz), mixer [t-r-p-y, t+r+p-y, t+r-p+y, t-r+p+y] with t = (hover+1)/2.  It
+ * reads the yaw rate, so it needs the 12-component observation (COPTER_HOVER3D).  `controller`
+ * is T[n][24] here: the four memories above, then yaw-rate and altitude-hold.  With
+ * scale = 2 x the hover command (0.03312, so that t = 1/2 hovers) the reference's own gains
+ * hold the live vehicle at 5 m for whole 1000-step episodes.
  */
 typedef struct CopterPidGains {
     double rate_kp, rate_ki, rate_kd, rate_windup, rate_big;      /* AngularVelocityPidController */
     double pos_kp, pos_ki, pos_kd, pos_windup, pos_target;        /* PositionHoldPidController */
     double descent_kp, descent_kd;                                /* DescentPidController */
+    double alt_kp, alt_ki, alt_kd, alt_windup, alt_target;        /* AltitudeHoldPidController (COPTER_SRC_PID_HOVER) */
 } CopterPidGains;
 void copter_default_pid_gains(CopterPidGains* g);
 

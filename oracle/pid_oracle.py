@@ -3,7 +3,9 @@ TEST INFRASTRUCTURE ONLY -- numpy restatement, batched over envs, of the referen
 landing heuristic: attic/mars/pidcontrollers/__init__.py:12-146 (controllers) and
 attic/mars/lander3d.py:64-87 (Lander3D.heuristic + quad-X mixer).  Pinned by executing the
 reference's controller classes themselves (the module is numpy-only and loads by file path)
-in tests/test_pid_oracle.py.
+in tests/test_pid_oracle.py.  HoverHeuristicBatch is the hover demo's controller set:
+attic/mars/hover3d.py:33-38,65-92 with the altitude-hold controller of attic/mars/hover.py:23
+(pidcontrollers/__init__.py:70-99).
 """
 import numpy as np
 
@@ -61,4 +63,38 @@ class LanderHeuristicBatch:
         descent_todo = o[:, 4] * self.descent_kp + o[:, 5] * self.descent_kd
         t, r, p = (descent_todo + T(1)) / T(2), phi_todo, theta_todo
         mix = np.stack([t - r - p, t + r + p, t + r - p, t - r + p], -1)          # lander3d.py:87
+        return self.offset + self.scale * mix
+
+
+class HoverHeuristicBatch:
+    """Hover3D.heuristic (attic/mars/hover3d.py:33-38, 65-92; altpid from hover.py:23) for N envs."""
+
+    def __init__(self, n, dtype=np.float64, scale=1.0, offset=0.0, alt_target=5.0, alt_kp=0.2, alt_ki=3.0, alt_kd=0.0,
+                 alt_windup=0.2):
+        T = np.dtype(dtype).type
+        self.T, self.scale, self.offset = T, T(scale), T(offset)
+        self.roll_rate = PidBatch(n, T(1.0), T(0), T(1.0), T(6), dtype)         # AngularVelocityPidController (:124-135)
+        self.pitch_rate = PidBatch(n, T(1.0), T(0), T(1.0), T(6), dtype)
+        self.yaw_rate = PidBatch(n, T(1.0), T(0), T(1.0), T(6), dtype)
+        self.x_poshold = PidBatch(n, T(0.00001), T(0.1), T(4.0), T(0.2), dtype)  # PositionHoldPidController (:102-107)
+        self.y_poshold = PidBatch(n, T(0.00001), T(0.1), T(4.0), T(0.2), dtype)
+        self.alt = PidBatch(n, T(alt_kp), T(alt_ki), T(alt_kd), T(alt_windup), dtype)   # AltitudeHoldPidController (:91-99)
+        self.alt_target = T(alt_target)
+        self.big = T(np.radians(40))
+
+    def _rate(self, pid, rate):
+        pid.reset_where(np.abs(rate) > self.big)                                  # :141-143
+        return pid.compute(self.T(0), rate)
+
+    def act(self, obs):
+        """obs: [N,12] float32 observation of the previous step. Returns motors [N,4]."""
+        T = self.T
+        o = obs.astype(np.float32).astype(self.alt.err_i.dtype)
+        roll_todo = self._rate(self.roll_rate, o[:, 7]) + self.x_poshold.compute((T(0) - o[:, 2]) * T(1), o[:, 3])
+        pitch_todo = self._rate(self.pitch_rate, -o[:, 9]) + self.y_poshold.compute((T(0) - o[:, 0]) * T(1), o[:, 1])
+        yaw_todo = self._rate(self.yaw_rate, -o[:, 11])
+        # AltitudeHoldPidController.getDemand(z, dz): set-point controller on (-z, -dz)  (:96-99, 80-88)
+        hover_todo = self.alt.compute((self.alt_target - (-o[:, 4])) * T(1), -o[:, 5])
+        t, r, p, y = (hover_todo + T(1)) / T(2), roll_todo, pitch_todo, yaw_todo
+        mix = np.stack([t - r - p - y, t + r + p - y, t + r - p + y, t - r + p + y], -1)   # hover3d.py:92
         return self.offset + self.scale * mix

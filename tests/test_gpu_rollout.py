@@ -252,6 +252,50 @@ def test_pid_heuristic_rollout_vs_oracle(pkg, dtype, tol):
         pkg.CopterVecEnv('Lander2D', 8).rollout(1, source='pid')
 
 
+@pytest.mark.parametrize('dtype,tol', [(torch.float64, 5e-6), (torch.float32, 1e-4)])
+def test_pid_hover_heuristic_rollout_vs_oracle(pkg, dtype, tol):
+    """The hover demo's heuristic (attic/mars/hover3d.py:65-92: altitude hold + position hold +
+    roll/pitch/yaw rate loops) closed around Hover3D on the device, against the closed loop of the
+    two oracles.  The reference's own gains, with the mixer output scaled by twice the hover
+    command so that t = 1/2 hovers the live vehicle: every copter climbs from the reset altitude to
+    the 5 m set-point, holds it, and the episode ends by the 1000-step limit.
+    Tolerance of the fp64 loop: the controllers read the float32 observation, and this loop
+    regulates z to the set-point THROUGH that quantiser (ulp32(5 m) = 4.8e-7): a last-bit
+    difference of the fp64 state that flips one float32 rounding moves the closed-loop state by
+    about one such ulp (measured 8e-7 over 1200 steps), so the bound is a few float32 ulps of the
+    regulated altitude instead of the open-loop 1e-9.  Commands agree to 1e-5 relative throughout."""
+    from oracle.pid_oracle import HoverHeuristicBatch
+    n, T, seed = 512, 1200, 5
+    scale = 2 * 0.016560178212092172
+    env = pkg.CopterVecEnv('Hover3D', n, dtype=dtype, seed=seed, track_stats=True)
+    orc = EnvBatch('Hover3D', n, seed=seed)
+    pid = HoverHeuristicBatch(n, scale=scale)
+    env.reset()
+    o_obs = orc.reset()
+    sync = np.ones(n, bool)
+    worst_a = worst_s = 0.0
+    for chunk in range(T // 50):
+        out = env.rollout(50, source='pid_hover', scale=scale, record_actions=True, record_dones=True)
+        acts, dones = out['actions'].cpu().numpy(), out['dones'].cpu().numpy()
+        for t in range(50):
+            a = pid.act(o_obs)
+            worst_a = max(worst_a, float((np.abs(acts[t] - a) / np.maximum(np.abs(a), 1e-2))[sync].max()))
+            o_obs, o_r, o_done, _ = orc.step(a)
+            sync &= dones[t] == o_done
+        sync &= env.status.cpu().numpy() == orc.dyn.status
+        worst_s = max(worst_s, merr(env.state.cpu().numpy()[sync], orc.dyn.x[sync]))
+        if chunk == 15:              # step 800 of the first episode: holding the set-point
+            z = env.state.cpu().numpy()[:, 4]
+            assert np.abs(z + 5.0).max() < 0.1, (z.min(), z.max())
+    assert env.controller.shape == (n, 24)
+    assert sync.sum() >= (n if dtype == torch.float64 else 0.97 * n), sync.sum()
+    assert worst_s <= tol and worst_a <= (1e-5 if dtype == torch.float64 else 2e-3), (worst_s, worst_a)
+    s = env.stats()
+    assert s['episodes'] == n and s['timeout'] == n          # every first episode ran to the step limit
+    with pytest.raises(pkg.CopterError):
+        pkg.CopterVecEnv('Lander3D', 8).rollout(1, source='pid_hover')      # no yaw rate in that observation
+
+
 @pytest.mark.parametrize('variant', ['Lander3D', 'Lander2D', 'Hover3D', 'Lander1D'])
 def test_fused_mlp_policy_vs_torch_fp32(pkg, variant):
     """The hand-written policy kernel (bf16 tensor-core MMAs, fp32 accumulation, MUFU tanh)

@@ -26,6 +26,15 @@ VARIANTS = {
     'pol_mt1_c5': _v(1, 5), 'pol_mt1_c6': _v(1, 6), 'pol_mt1_c7': _v(1, 7), 'pol_mt1_c8': _v(1, 8),
     'pol_mt2_c5_bf16x2': _v(2, 5, '-DCOPTER_POLICY_TANH_BF16X2=1'),
 }
+# FMA-pipe polynomial tanh for the hidden n-tiles in the mask (bit nt), packed f32x2 or scalar
+for _m in (0x00, 0x80, 0x88, 0xa8, 0xaa, 0xff):
+    VARIANTS['poly_%02x' % _m] = _v(2, 5, '-DCOPTER_POLICY_POLY_MASK=0x%02x' % _m)
+VARIANTS['poly_88_scalar'] = _v(2, 5, '-DCOPTER_POLICY_POLY_MASK=0x88', '-DCOPTER_POLICY_POLY_F32X2=0')
+VARIANTS['poly_aa_scalar'] = _v(2, 5, '-DCOPTER_POLICY_POLY_MASK=0xaa', '-DCOPTER_POLICY_POLY_F32X2=0')
+VARIANTS['poly_88_c4'] = _v(2, 4, '-DCOPTER_POLICY_POLY_MASK=0x88')
+VARIANTS['poly_aa_c4'] = _v(2, 4, '-DCOPTER_POLICY_POLY_MASK=0xaa')
+if os.environ.get('COPTER_SWEEP_ONLY'):
+    VARIANTS = {k: v for k, v in VARIANTS.items() if k.startswith(os.environ['COPTER_SWEEP_ONLY'])}
 VARIANTS.update(json.loads(os.environ.get('COPTER_SWEEP_EXTRA', '{}')))
 
 
@@ -61,9 +70,21 @@ def time_one():
         return e0.elapsed_time(e1) / reps
     fused = g.FusedMLPPolicy(env, pol.net, out_scale=0.2 * 0.0166, out_offset=0.0166)
     ms_pol = timed(fused, 30)
+    # accuracy against the PyTorch fp32 evaluation, activations pushed into the curved part of tanh
+    small = g.LanderVec(1 << 16, seed=3)
+    small.reset()
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    for _ in range(30):
+        small.step(0.0166 * (1 + 0.3 * torch.randn((small.num_envs, 4), device='cuda', generator=gen)))
+    pol3 = g.mlp_policy(10, 4, dtype=torch.float32, seed=5)
+    for p in pol3.net.parameters():
+        p.data.mul_(3.0)
+    with torch.no_grad():
+        err = (g.FusedMLPPolicy(small, pol3.net)() - pol3.net(small.obs)).abs()
     ro = g.FusedPolicyRollout(env, pol.net, T, out_scale=0.2 * 0.0166, out_offset=0.0166)
     ms = timed(ro.run, 8) / T
-    print(json.dumps({'policy_kernel_ms': ms_pol, 'rollout_ms_per_env_step': ms, 'rollout_steps_per_s': n / ms * 1e3}))
+    print(json.dumps({'policy_kernel_ms': ms_pol, 'rollout_ms_per_env_step': ms, 'rollout_steps_per_s': n / ms * 1e3,
+                      'err_max': err.max().item(), 'err_mean': err.mean().item()}))
 
 
 def run():
