@@ -192,6 +192,12 @@ def main():
     args = parse()
     if args.impl == 'reference':
         return run_reference_arm(args)
+    # stdout carries the one JSON line and nothing else: from here on file descriptor 1 is stderr
+    # (NCCL's version banner and any other library chatter written to fd 1 end up there), and the
+    # line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -208,9 +214,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # keep stdout to the one JSON line: the image exports NCCL_DEBUG, whose version banner
-        # goes to stdout unless it is sent elsewhere
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
@@ -420,7 +423,8 @@ def main():
             'fused_substeps': extras,
             'policy_rollout': policy_rollout,
         }
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + '\n')
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 
