@@ -423,7 +423,27 @@ __device__ __forceinline__ void pid_hover_heuristic(const RolloutArgs<T>& a, con
     for (int j = 0; j < 4; ++j) act[j] = a.src_offset + a.src_scale * mix[j];
 }
 
-// PID: 0 = drawn commands, 1 = landing heuristic (4 controller memories), 2 = hover heuristic (6)
+// The 2-D / 1-D demos (attic/heuristic/lander2d.py:14-24, lander1d.py:14-20, hover2d.py:17-31,
+// hover1d.py:14-20): the demand is the command itself (no (t+1)/2), 2-D adds -/+ the roll
+// correction for the two motor pairs.  Controller memories keep their 3-D slots (0 = roll rate,
+// 2 = position hold fed y, 5 = altitude hold), so one layout serves every variant.
+template <typename T, int A, int NMEM, bool HOVER>
+__device__ __forceinline__ void pid_planar_heuristic(const RolloutArgs<T>& a, const T (&s)[12], PidMem<T> (&mem)[NMEM], T (&act)[A]) {
+    const T y = (T)(float)s[2], dy = (T)(float)s[3], z = (T)(float)s[4], dz = (T)(float)s[5], dphi = (T)(float)s[7];
+    T demand;
+    if constexpr (HOVER) demand = pid_compute<T>(a.alt_kp, a.alt_ki, a.alt_kd, a.alt_windup, (a.alt_target - (-z)) * (T)1, -dz, mem[NMEM - 1]);
+    else                 demand = z * a.descent_kp + dz * a.descent_kd;
+    if constexpr (A == 1) {
+        act[0] = a.src_offset + a.src_scale * demand;
+    } else {
+        T todo = poshold_demand<T>(a, y, dy, mem[2]);
+        if constexpr (HOVER) todo = rate_demand<T>(a, dphi, mem[0]) + todo;            // hover2d.py:23-26
+        act[0] = a.src_offset + a.src_scale * (demand - todo);
+        act[1] = a.src_offset + a.src_scale * (demand + todo);
+    }
+}
+
+// PID: 0 = drawn commands, 1 = landing heuristics (4 controller memories), 2 = hover heuristics (6)
 template <typename T, int VARIANT, bool STATS, int PID>
 __global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? (PID ? 5 : COPTER_F32_CTAS_PER_SM) : 2)
 copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant__ RolloutArgs<T> a) {
@@ -472,6 +492,7 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
                 T act[A], m[4];
                 if constexpr (PID == 1 && A == 4) pid_heuristic<T>(a, s, mem, act);
                 else if constexpr (PID == 2 && A == 4) pid_hover_heuristic<T>(a, s, mem, act);
+                else if constexpr (PID != 0) pid_planar_heuristic<T, A, NMEM, PID == 2>(a, s, mem, act);
                 else draw_action<T, A>(a, (uint64_t)(a.env_offset + i), (uint64_t)(a.first_step + t), act);
                 if (a.action_tn) {
 #pragma unroll
@@ -796,19 +817,15 @@ int launch_step(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_
 
 template <typename T, int VARIANT>
 int launch_rollout_v(const KParams<T>& kp, const RolloutArgs<T>& a, cudaStream_t s) {
-    if (a.src_kind == COPTER_SRC_PID || a.src_kind == COPTER_SRC_PID_HOVER) {
-        if constexpr (Variant<VARIANT>::A == 4) {
-            if (a.src_kind == COPTER_SRC_PID) {
-                if (a.stats) copter_rollout_kernel<T, VARIANT, true, 1><<<grid_for<copter_rollout_kernel<T, VARIANT, true, 1>>(a.n), kBlock, 0, s>>>(kp, a);
-                else         copter_rollout_kernel<T, VARIANT, false, 1><<<grid_for<copter_rollout_kernel<T, VARIANT, false, 1>>(a.n), kBlock, 0, s>>>(kp, a);
-            } else if constexpr (Variant<VARIANT>::O == 12) {
-                if (a.stats) copter_rollout_kernel<T, VARIANT, true, 2><<<grid_for<copter_rollout_kernel<T, VARIANT, true, 2>>(a.n), kBlock, 0, s>>>(kp, a);
-                else         copter_rollout_kernel<T, VARIANT, false, 2><<<grid_for<copter_rollout_kernel<T, VARIANT, false, 2>>(a.n), kBlock, 0, s>>>(kp, a);
-            } else {
-                return COPTER_E_VARIANT;      // the hover heuristic reads the yaw rate: full-state observation only
-            }
+    if (a.src_kind == COPTER_SRC_PID) {
+        if (a.stats) copter_rollout_kernel<T, VARIANT, true, 1><<<grid_for<copter_rollout_kernel<T, VARIANT, true, 1>>(a.n), kBlock, 0, s>>>(kp, a);
+        else         copter_rollout_kernel<T, VARIANT, false, 1><<<grid_for<copter_rollout_kernel<T, VARIANT, false, 1>>(a.n), kBlock, 0, s>>>(kp, a);
+    } else if (a.src_kind == COPTER_SRC_PID_HOVER) {
+        if constexpr (Variant<VARIANT>::A == 4 && Variant<VARIANT>::O != 12) {
+            return COPTER_E_VARIANT;          // the 3-D hover heuristic reads the yaw rate: full-state observation only
         } else {
-            return COPTER_E_VARIANT;          // the heuristics are defined for the four-motor envs only
+            if (a.stats) copter_rollout_kernel<T, VARIANT, true, 2><<<grid_for<copter_rollout_kernel<T, VARIANT, true, 2>>(a.n), kBlock, 0, s>>>(kp, a);
+            else         copter_rollout_kernel<T, VARIANT, false, 2><<<grid_for<copter_rollout_kernel<T, VARIANT, false, 2>>(a.n), kBlock, 0, s>>>(kp, a);
         }
     } else {
         if (a.stats) copter_rollout_kernel<T, VARIANT, true, 0><<<grid_for<copter_rollout_kernel<T, VARIANT, true, 0>>(a.n), kBlock, 0, s>>>(kp, a);

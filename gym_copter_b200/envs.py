@@ -138,7 +138,7 @@ class CopterVecEnv:
         self._pipeline = None
         self._host = None
         self.rollout_step = 0       # global step index of the on-device action streams
-        self.controller = None      # [N,16] PID memories, allocated by rollout(source='pid')
+        self.controller = None      # PID memories, allocated by rollout(source='pid' [N,16] | 'pid_hover' [N,24])
 
     # ---- plumbing -----------------------------------------------------------------------
 
@@ -249,9 +249,11 @@ class CopterVecEnv:
           source='pid'      action = offset + scale*mixer(PID heuristic of attic/mars/lander3d.py:64-87
                             on the previous observation); `pid_gains` = dict of CopterPidGains
                             overrides; controller memories live in `self.controller` [N,16]
+                            (2-D / 1-D variants: attic/heuristic/lander2d.py, lander1d.py)
           source='pid_hover' the hover demo's heuristic (attic/mars/hover3d.py:65-92: roll/pitch/yaw
-                            rate PIDs, position hold, altitude hold at `alt_target` = 5 m), Hover3D
-                            only; `self.controller` is [N,24].  scale=0.03312 (twice the hover
+                            rate PIDs, position hold, altitude hold at `alt_target` = 5 m; 2-D / 1-D:
+                            attic/heuristic/hover2d.py, hover1d.py); of the four-motor variants
+                            Hover3D only; `self.controller` is [N,24].  scale=0.03312 (twice the hover
                             command) holds the live vehicle at the target with the reference's gains
         Step for step identical to `n_steps` calls of step() with k_substeps=1 on the same
         commands.  Returns a dict: 'obs' (after the last step), 'reward_sum' [N], 'done_any'
@@ -265,10 +267,8 @@ class CopterVecEnv:
                           'pid': (1.0, 0.0), 'pid_hover': (1.0, 0.0)}[source]
         gains = None
         if source in ('pid', 'pid_hover'):
-            if self.action_size != 4:
-                raise CopterError('the PID heuristics drive the four-motor variants only')
-            if source == 'pid_hover' and self.obs_size != 12:
-                raise CopterError('the hover heuristic reads the yaw rate: Hover3D (12-component observation) only')
+            if source == 'pid_hover' and self.action_size == 4 and self.obs_size != 12:
+                raise CopterError('the 3-D hover heuristic reads the yaw rate: Hover3D (12-component observation) only')
             width = 24 if source == 'pid_hover' else 16
             if self.controller is None or self.controller.shape[1] != width:
                 self.controller = torch.zeros((self.num_envs, width), dtype=self.dtype, device=self.device)

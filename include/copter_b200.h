@@ -178,7 +178,10 @@ typedef struct CopterActionSource { int32_t kind; int32_t reserved; double scale
  * lander3d.py:64-87 (roll/pitch rate PIDs + position-hold PIDs + descent PD, quad-X mixer
  * [t-r-p, t+r+p, t+r-p, t-r+p]) over attic/mars/pidcontrollers/__init__.py:12-146 -- fed, like
  * the reference's caller loop (attic/mars/task.py:134-160), with the float32 observation of the
- * previous step; action_j = offset + scale * mixer_j.  Four-motor variants only.  `controller`
+ * previous step; action_j = offset + scale * mixer_j.  On the 2-D / 1-D variants the same source
+ * is the reference's planar demo (attic/heuristic/lander2d.py:14-24: [d - p, d + p] with d the
+ * descent demand and p the position-hold demand on (y, dy); lander1d.py:14-20: d alone -- no
+ * (t+1)/2 there), using the same memory slots.  `controller`
  * T[n][16] holds the four controllers' memories (errorI, lastError, deltaError1, deltaError2 for
  * phi-rate, theta-rate, x_poshold, y_poshold); it persists across episodes exactly as the
  * reference's controller objects do (they live in the env, not in an episode); zero it to start.
@@ -188,7 +191,10 @@ typedef struct CopterActionSource { int32_t kind; int32_t reserved; double scale
  * :33-38 plus the altitude-hold controller of attic/mars/hover.py:23, pidcontrollers/__init__.py:
  * 70-99): the same roll/pitch loops, a yaw-rate PID on -dpsi and the altitude-hold set-point
  * controller on (-z, -dz), mixer [t-r-p-y, t+r+p-y, t+r-p+y, t-r+p+y] with t = (hover+1)/2.  It
- * reads the yaw rate, so it needs the 12-component observation (COPTER_HOVER3D).  `controller`
+ * reads the yaw rate, so among the four-motor variants it needs the 12-component observation
+ * (COPTER_HOVER3D); on the 2-D / 1-D variants it is attic/heuristic/hover2d.py:17-31
+ * ([h - r, h + r], h = altitude-hold demand, r = roll-rate PID + position hold on (y, dy)) and
+ * hover1d.py:14-20 (h alone).  `controller`
  * is T[n][24] here: the four memories above, then yaw-rate and altitude-hold.  With
  * scale = 2 x the hover command (0.03312, so that t = 1/2 hovers) the reference's own gains
  * hold the live vehicle at 5 m for whole 1000-step episodes.

@@ -98,3 +98,37 @@ class HoverHeuristicBatch:
         t, r, p, y = (hover_todo + T(1)) / T(2), roll_todo, pitch_todo, yaw_todo
         mix = np.stack([t - r - p - y, t + r + p - y, t + r - p + y, t - r + p + y], -1)   # hover3d.py:92
         return self.offset + self.scale * mix
+
+
+class PlanarHeuristicBatch:
+    """The 2-D and 1-D heuristic demos (attic/heuristic/lander2d.py:14-24, lander1d.py:14-20,
+    hover2d.py:17-31, hover1d.py:14-20) for N envs.  `kind` = 'lander' | 'hover', `dims` = 2 | 1.
+    Observation: (y, dy, z, dz, phi, dphi) for 2-D, (z, dz) for 1-D.  No (t+1)/2 and no mixer here:
+    the demand itself is the command (2-D: demand -/+ roll correction for the two motor pairs)."""
+
+    def __init__(self, n, kind, dims, dtype=np.float64, scale=1.0, offset=0.0, descent_kp=1.15, descent_kd=1.33,
+                 alt_target=5.0):
+        T = np.dtype(dtype).type
+        self.T, self.kind, self.dims, self.scale, self.offset = T, kind, dims, T(scale), T(offset)
+        self.descent_kp, self.descent_kd = T(descent_kp), T(descent_kd)
+        self.rate = PidBatch(n, T(1.0), T(0), T(1.0), T(6), dtype)
+        self.poshold = PidBatch(n, T(0.00001), T(0.1), T(4.0), T(0.2), dtype)
+        self.alt = PidBatch(n, T(0.2), T(3.0), T(0.0), T(0.2), dtype)
+        self.alt_target = T(alt_target)
+        self.big = T(np.radians(40))
+
+    def act(self, obs):
+        T = self.T
+        o = obs.astype(np.float32).astype(self.alt.err_i.dtype)
+        z, dz = (o[:, 2], o[:, 3]) if self.dims == 2 else (o[:, 0], o[:, 1])
+        if self.kind == 'lander':
+            demand = z * self.descent_kp + dz * self.descent_kd
+        else:
+            demand = self.alt.compute((self.alt_target - (-z)) * T(1), -dz)
+        if self.dims == 1:
+            return self.offset + self.scale * demand[:, None]
+        todo = self.poshold.compute((T(0) - o[:, 0]) * T(1), o[:, 1])
+        if self.kind == 'hover':
+            self.rate.reset_where(np.abs(o[:, 5]) > self.big)
+            todo = self.rate.compute(T(0), o[:, 5]) + todo
+        return self.offset + self.scale * np.stack([demand - todo, demand + todo], -1)

@@ -99,3 +99,82 @@ def test_hover_heuristic_matches_reference_controllers():
             worst = max(worst, np.max(np.abs(r - a[i]) / np.maximum(np.abs(r), 1)))
     assert worst <= 1e-13, worst
     assert np.abs(mine.alt.err_i).max() == 0.2 and unclamped > n * steps // 4
+
+
+def _load_attic_heuristic(name):
+    """Executes /root/reference/attic/heuristic/<name>.py unmodified and returns its `heuristic`
+    function.  The scripts import `main.demo` (absent from the reference tree: the demo runner) and
+    run it at import time, so `main` is a stub whose demo() does nothing; `pidcontrollers` is the
+    reference's own attic/mars module."""
+    import sys
+    import types
+    spec = importlib.util.spec_from_file_location('pidcontrollers', PID_PATH)
+    pidmod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pidmod)
+    stub = types.ModuleType('main')
+    stub.demo = lambda *a, **k: None
+    stub.demo3d = lambda *a, **k: None
+    saved = {k: sys.modules.get(k) for k in ('main', 'pidcontrollers')}
+    sys.modules['main'], sys.modules['pidcontrollers'] = stub, pidmod
+    try:
+        path = os.path.join(refshim.REFERENCE_ROOT, 'attic', 'heuristic', name + '.py')
+        s = importlib.util.spec_from_file_location('ref_heuristic_' + name, path)
+        mod = importlib.util.module_from_spec(s)
+        s.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod.heuristic, pidmod
+
+
+@pytest.mark.parametrize('name,kind,dims', [('lander2d', 'lander', 2), ('lander1d', 'lander', 1),
+                                            ('hover2d', 'hover', 2), ('hover1d', 'hover', 1)])
+def test_planar_heuristics_match_reference_scripts(name, kind, dims):
+    from oracle.pid_oracle import PlanarHeuristicBatch
+    heuristic, pm = _load_attic_heuristic(name)
+    make = {'lander2d': lambda: (pm.PositionHoldPidController(), pm.DescentPidController()),
+            'lander1d': lambda: (pm.DescentPidController(),),
+            'hover2d': lambda: (pm.AngularVelocityPidController(), pm.PositionHoldPidController(), pm.AltitudeHoldPidController()),
+            'hover1d': lambda: (pm.AltitudeHoldPidController(),)}[name]
+    rng = np.random.default_rng(2)
+    n, steps = 8, 300
+    refs = [make() for _ in range(n)]
+    mine = PlanarHeuristicBatch(n, kind, dims)
+    worst = 0.0
+    for t in range(steps):
+        obs = rng.normal(0, 1, (n, 6)) * np.array([3, 1, 5, 2, .3, 1.0])
+        if t % 3:
+            obs[:, 2:4] = np.array([-5.0, 0.0]) + 0.02 * rng.normal(0, 1, (n, 2))
+        obs = (obs if dims == 2 else obs[:, 2:4]).astype(np.float32)
+        a = mine.act(obs)
+        for i in range(n):
+            r = np.array(heuristic(tuple(obs[i].astype(np.float64)), refs[i]))
+            worst = max(worst, np.max(np.abs(r - a[i]) / np.maximum(np.abs(r), 1)))
+    assert worst <= 1e-13, worst
+
+
+def test_hover3d_heuristic_script_equals_the_env_method():
+    """attic/heuristic/hover.py:19-48 is the same controller as attic/mars/hover3d.py:65-92."""
+    import sys
+    import types
+    saved = {k: sys.modules.get(k) for k in ('gym_copter', 'gym_copter.rendering', 'gym_copter.rendering.threed')}
+    for k in saved:
+        sys.modules[k] = types.ModuleType(k)
+    sys.modules['gym_copter.rendering.threed'].ThreeDHoverRenderer = None
+    try:
+        heuristic, pm = _load_attic_heuristic('hover')
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    H = reference_hover_heuristic()
+    a, b = H(), tuple(c() for c in (pm.AngularVelocityPidController,) * 3 + (pm.PositionHoldPidController,) * 2 + (pm.AltitudeHoldPidController,))
+    rng = np.random.default_rng(3)
+    for t in range(100):
+        s = rng.normal(0, 1, 12) * np.array([3, 1, 3, 1, 5, 2, .3, 1.0, .3, 1.0, .3, 1.0])
+        assert np.allclose(a(s), heuristic(s, b), rtol=0, atol=0)
