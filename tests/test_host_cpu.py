@@ -27,7 +27,9 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 16
     for n in sorted(names):
         assert hasattr(lib, n), n
-    assert lib.copter_abi_version() == 1
+    m = re.search(r'#define\s+COPTER_ABI_VERSION\s+(\d+)', hdr)
+    from gym_copter_b200 import _lib as binding
+    assert m and lib.copter_abi_version() == int(m.group(1)) == binding.ABI_VERSION
 
 
 def test_params_struct_matches_header_and_reference_constants(lib):
