@@ -538,6 +538,46 @@ def test_full_size_sampled_parity_and_conservation(pkg):
     assert torch.equal(half.state, env.state[N // 2:]) and torch.equal(half.meta, env.meta[N // 2:])
 
 
+def test_quarter_billion_envs_64bit_indexing(pkg):
+    """2^28 + 77 Lander3D envs on one GPU (31 GB of the 180 GB; the observation tensor alone has
+    2.7e9 elements, past 2^31): 24 fused rollout steps on the U(-1,1) source (bit-exact commands
+    in the oracle, ~7-step episodes, so resets are exercised) and one step() launch, checked for
+    env ids sampled at the head, around the 2^31-element boundaries of the obs / state / action
+    indexing, and in the ragged tail, against the oracle run alone on those global ids."""
+    from oracle.copter_oracle import source_actions
+    n, T, seed = (1 << 28) + 77, 24, 4242
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip('needs 40 GB of free device memory')
+    edges = [0, (1 << 31) // 12, (1 << 31) // 10, (1 << 31) // 4, 1 << 27, 1 << 28]
+    idx = np.unique(np.concatenate([np.arange(max(e - 40, 0), min(e + 40, n)) for e in edges] + [np.arange(n - 100, n)]))
+    idx_t = torch.as_tensor(idx, device='cuda')
+    env = pkg.CopterVecEnv('Lander3D', n, dtype=torch.float32, seed=seed)
+    orc = EnvBatch('Lander3D', len(idx), seed=seed, env_ids=idx)
+    env.reset(); orc.reset()
+    assert np.array_equal(env.obs[idx_t].cpu().numpy(), orc.observe())
+    out = env.rollout(T, source='uniform', record_dones=True)
+    dones = out['dones'][:, idx_t].cpu().numpy()
+    sync = np.ones(len(idx), bool)
+    for t in range(T):
+        a = source_actions(seed, idx, t, 'uniform', 1.0, 0.0, 4, np.float32).astype(np.float64)
+        _, _, o_done, _ = orc.step(a)
+        sync &= dones[t] == o_done
+    a = torch.full((n, 4), 0.0166, device='cuda')
+    obs, r, term, _, _ = env.step(a)
+    o_obs, o_r, o_done, _ = orc.step(np.full((len(idx), 4), np.float64(np.float32(0.0166))))
+    mw = env.meta[idx_t].to(torch.int64).cpu().numpy() & 0xFFFFFFFF                # sampled rows only: no full-size temporaries
+    sync &= (term[idx_t].cpu().numpy() == o_done) & ((mw & 3) == orc.dyn.status)
+    x = env.state_planes[:, idx_t, :].permute(1, 0, 2).reshape(len(idx), 12).cpu().numpy()
+    scale = np.maximum(np.abs(orc.dyn.x).max(1, keepdims=True), 1.0)              # saturating commands
+    worst = float((np.abs(x - orc.dyn.x) / scale)[sync].max())
+    worst_o = float((np.abs(obs[idx_t].cpu().numpy() - o_obs) / scale)[sync].max())
+    assert sync.sum() >= 0.97 * len(idx) and worst <= 1e-4 and worst_o <= 1e-4, (sync.sum(), len(idx), worst, worst_o)
+    assert (((mw >> 2) & 2047)[sync] == orc.steps[sync]).all()
+    del env, a, out
+    torch.cuda.empty_cache()
+
+
 # ---------------------------------------------------------------------------------------
 # randomised shapes (hypothesis): any n / k / shard offset / variant / seed
 # ---------------------------------------------------------------------------------------
