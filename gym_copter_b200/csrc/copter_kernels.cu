@@ -130,12 +130,11 @@ __device__ __forceinline__ void debit_idle_steps(double* stats, int lane, int id
 // instructions per env-step on the HBM-bound path).
 template <typename T, int VARIANT, bool STATS, bool SINGLE, bool PRELOADED>
 __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T>& a,
-                                          const RawEnv<T, Variant<VARIANT>::A>& preloaded, float* tiles, int64_t tile_id) {
+                                          const RawEnv<T, Variant<VARIANT>::A>& preloaded, float* tiles, int64_t row0) {
     constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A;
     // (recomputed here rather than passed in: cheaper than keeping five values live across the body)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row0 = tile_id * kBlock + warp * 32;           // first env of this warp
-    const int64_t i = row0 + lane;
+    const int64_t i = row0 + lane;                               // row0 = first env of this warp
     const bool valid = i < a.n;
     const int rows = (int)max((int64_t)0, min((int64_t)32, a.n - row0));
     float* tile = tiles + warp * (32 * O);
@@ -286,12 +285,187 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
             const int64_t inext = (tile_id + gridDim.x) * kBlock + threadIdx.x;
             if (inext < a.n) load_raw<T, A>(a, inext, nxt);
         }
-        if (COPTER_K1_SPECIALIZE && a.k == 1) step_tile<T, VARIANT, STATS, true, kPrefetch>(kp, a, cur, &tiles[0][0], tile_id);
-        else                                  step_tile<T, VARIANT, STATS, false, kPrefetch>(kp, a, cur, &tiles[0][0], tile_id);
+        const int64_t row0 = tile_id * kBlock + (threadIdx.x >> 5) * 32;
+        if (COPTER_K1_SPECIALIZE && a.k == 1) step_tile<T, VARIANT, STATS, true, kPrefetch>(kp, a, cur, &tiles[0][0], row0);
+        else                                  step_tile<T, VARIANT, STATS, false, kPrefetch>(kp, a, cur, &tiles[0][0], row0);
         if (kPrefetch) cur = nxt;
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// A/B shape (compiled in with -DCOPTER_TMA_MIN_K=1|2, off by default): persistent CTAs that fetch
+// their NEXT tile's inputs with the TMA engine (cp.async.bulk 1-D: three 2 KB state planes, the
+// action rows and the meta words of 128 envs per stage, two stages, one full/empty mbarrier pair
+// per stage) while their warps compute the current tile, and that get their tiles from cluster
+// launch control: the grid still holds one CTA per tile, a running CTA cancels a not-yet-launched
+// CTA and takes over its block index (hardware work stealing, no counter in memory).
+// Measured on B200 (Lander3D fp32, 2^24 envs; profiles/r1_sweep_tma_clc.txt):
+//   * static grid-stride tiles lose 17 % at K = 1 (0.486 vs 0.414 ms) however the loads are issued
+//     (plain, register-prefetched or TMA-prefetched; staggering the CTAs' start changes nothing):
+//     SMs do not all see the same memory bandwidth, and a static split waits for the slowest;
+//   * with cluster launch control the persistent kernel is level with the one-tile-per-CTA kernel
+//     at K = 1 (0.4140 vs 0.4134 ms) -- the hardware CTA scheduler was doing that balancing;
+//   * the prefetch itself buys nothing at any K (K = 4: 0.604 vs 0.584 ms, K = 16: 1.627 vs 1.614):
+//     launches with K >= 3 are bound by instruction issue (t = 0.24 ms + K x 0.086 ms), not by
+//     exposed load latency, and K <= 2 by HBM.
+// So the shipped step kernel stays the simple one; this one documents the alternative.
+// ------------------------------------------------------------------------------------------
+#ifndef COPTER_TMA_MIN_K
+#define COPTER_TMA_MIN_K 0        // k_substeps >= this use copter_step_tma_kernel (0: never)
+#endif
+#ifndef COPTER_TMA_CTAS_PER_SM
+#define COPTER_TMA_CTAS_PER_SM COPTER_F32_CTAS_PER_SM     // fp32 occupancy target of that kernel (A/B knob)
+#endif
+
+template <typename T, int A> struct alignas(128) TileStage {     // one tile (kBlock envs) of inputs, laid out as in HBM
+    typename Vec<T>::type plane[12 / Vec<T>::V][kBlock];
+    T act[kBlock * A];
+    uint32_t meta[kBlock];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_global, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_global), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Cluster launch control (sm_100): a running CTA cancels a CTA of the grid that has not been launched
+// yet and takes over its block index -- dynamic tile scheduling done by the hardware, no counter in
+// memory.  The 16-byte response lands in shared memory through an mbarrier like a TMA copy.
+__device__ __forceinline__ void clc_try_cancel(void* resp16, uint64_t* bar) {
+    mbar_expect_tx(bar, 16);
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+                 :: "r"(smem_u32(resp16)), "r"(smem_u32(bar)) : "memory");
+}
+// returns the cancelled CTA's blockIdx.x, or 0xFFFFFFFF when nothing was left to cancel
+__device__ __forceinline__ uint32_t clc_response(const void* resp16) {
+    uint32_t ok, x;
+    asm volatile("{\n\t.reg .b128 r;\n\t.reg .pred p;\n\t.reg .b64 lo, hi;\n\t.reg .b32 y, z, w;\n\t"
+                 "ld.shared.v2.b64 {lo, hi}, [%2];\n\t"
+                 "mov.b128 r, {lo, hi};\n\t"
+                 "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p, r;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t"
+                 "mov.u32 %1, 0;\n\t"
+                 "@p clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%1, y, z, w}, r;\n\t}"
+                 : "=r"(ok), "=r"(x) : "r"(smem_u32(resp16)) : "memory");
+    return ok ? x : 0xFFFFFFFFu;
+}
+
+#ifndef COPTER_TMA_CLC
+#define COPTER_TMA_CLC 1          // 1: one CTA per tile in the grid, running CTAs steal the pending ones (cluster launch
+#endif                            //    control); 0 (A/B knob): one resident wave, tiles assigned by a grid stride
+
+template <typename T, int VARIANT, bool STATS, bool SINGLE>
+__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? COPTER_TMA_CTAS_PER_SM : 2)
+copter_step_tma_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant__ StepArgs<T> a) {
+    constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A, V = Vec<T>::V, NP = 12 / V;
+    using V4 = typename Vec<T>::type;
+    __shared__ __align__(16) float tiles[kWarpsPerBlock][32 * O];
+    __shared__ TileStage<T, A> stage[2];
+    __shared__ __align__(16) uint4 clc_resp;
+    __shared__ __align__(8) uint64_t full[2], empty[2], clc_bar;
+    __shared__ uint32_t sh_next[2];
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);                       // the producer's expect_tx arrival
+        mbar_init(&empty[0], kWarpsPerBlock); mbar_init(&empty[1], kWarpsPerBlock);   // one arrival per consumer warp
+        mbar_init(&clc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");    // visible to the async proxy
+    }
+    __syncthreads();
+    if (STATS) credit_env_steps(a.stats, a.n, a.k);
+
+    constexpr uint32_t kPlaneBytes = kBlock * sizeof(V4), kActBytes = kBlock * A * sizeof(T), kMetaBytes = kBlock * 4;
+    // thread 0: arm the stage's barrier with the tile's byte count and hand the copies to the TMA engine
+    auto fetch = [&](uint32_t tile, int st) {
+        TileStage<T, A>& dst = stage[st];
+        const int64_t row0 = (int64_t)tile * kBlock;
+        const V4* planes = reinterpret_cast<const V4*>(a.state);
+        mbar_expect_tx(&full[st], NP * kPlaneBytes + kActBytes + kMetaBytes);
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) bulk_load(dst.plane[pl], planes + (int64_t)pl * a.stride + row0, kPlaneBytes, &full[st]);
+        bulk_load(dst.act, a.action + row0 * A, kActBytes, &full[st]);
+        bulk_load(dst.meta, a.meta + row0, kMetaBytes, &full[st]);
+    };
+    // Tiles below n_full are complete and go through the staging; a ragged last tile takes direct loads.
+    // Loop state is one word.  All threads: bit 0 = stage, bits 1-2 = next phase of full[0..1].
+    // Thread 0 only: bits 3-4 = next phase of empty[0..1], bits 5-6 = stage 0/1 has been filled before,
+    // bit 7 = a try_cancel is in flight, bit 8 = next phase of clc_bar.
+    constexpr uint32_t kNone = 0xFFFFFFFFu;
+    const uint32_t n_tiles = (uint32_t)((a.n + kBlock - 1) / kBlock), n_full = (uint32_t)(a.n / kBlock);
+    uint32_t tile = blockIdx.x, ring = 0;
+    if (tile >= n_tiles) return;
+    if (threadIdx.x == 0) {
+        if (tile < n_full) { fetch(tile, 0); ring |= 1u << 5; }
+        if (COPTER_TMA_CLC) { clc_try_cancel(&clc_resp, &clc_bar); ring |= 1u << 7; }
+    }
+    for (;; ring ^= 1u) {
+        const int st = ring & 1u;
+        if (threadIdx.x == 0) {
+            uint32_t nxt = kNone;
+            if (COPTER_TMA_CLC) {
+                if (ring & (1u << 7)) {
+                    mbar_wait(&clc_bar, (ring >> 8) & 1u);
+                    ring ^= 1u << 8;
+                    nxt = clc_response(&clc_resp);
+                    if (nxt != kNone) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // response read before the buffer is rewritten
+                        clc_try_cancel(&clc_resp, &clc_bar);
+                    } else {
+                        ring &= ~(1u << 7);                         // a failed try_cancel is the last one
+                    }
+                }
+            } else if (tile + gridDim.x < n_tiles) {
+                nxt = tile + gridDim.x;
+            }
+            if (nxt < n_full) {
+                const int o = st ^ 1;
+                if (ring & (1u << (5 + o))) {                       // filled before: wait until all four warps have read it
+                    mbar_wait(&empty[o], (ring >> (3 + o)) & 1u);
+                    ring ^= 8u << o;
+                }
+                fetch(nxt, o);
+                ring |= 1u << (5 + o);
+            }
+            sh_next[st] = nxt;
+        }
+        __syncthreads();
+        const uint32_t nxt = sh_next[st];
+        RawEnv<T, A> cur;
+        const int64_t row0 = (int64_t)tile * kBlock + (threadIdx.x >> 5) * 32;
+        if (tile < n_full) {                                        // CTA-uniform
+            mbar_wait(&full[st], (ring >> (1 + st)) & 1u);
+            ring ^= 2u << st;
+            const TileStage<T, A>& src = stage[st];
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) cur.plane[pl] = src.plane[pl][threadIdx.x];
+#pragma unroll
+            for (int j = 0; j < A; ++j) cur.act[j] = src.act[threadIdx.x * A + j];
+            cur.meta = src.meta[threadIdx.x];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        } else if (row0 + lane < a.n) {
+            load_raw<T, A>(a, row0 + lane, cur);
+        }
+        step_tile<T, VARIANT, STATS, SINGLE, true>(kp, a, cur, &tiles[0][0], row0);
+        if (nxt == kNone) break;
+        tile = nxt;
+    }
+}
 
 // ------------------------------------------------------------------------------------------
 // Multi-step rollout with on-device action sources: n_steps reference steps per launch, the
@@ -753,12 +927,11 @@ int sm_count() {
 
 // Grid: one CTA per tile of kBlock envs, scheduled by the hardware as CTAs retire.  Measured on
 // B200 (Lander3D fp32, 2^24 envs, K = 1): 6.7 TB/s, against 5.6 TB/s for a persistent grid of
-// SMs x resident CTAs walking the tiles with a grid stride -- persistent CTAs start together,
-// do identical work and stay phase-locked (everyone loads, then everyone computes, then
-// everyone stores), so DRAM sees bursts; CTAs that start whenever a slot frees up spread the
-// three phases evenly in time.  (COPTER_PERSISTENT=1 / COPTER_PREFETCH=1 keep the old shape for
-// A/B runs; profiles/README.md has the sweep.)  The kernels keep their tile loop, so a grid
-// capped at 2^31-1 CTAs still covers any n.
+// SMs x resident CTAs walking the tiles with a grid stride.  The loss is the static split (the SMs
+// do not all see the same memory bandwidth; a persistent grid fed by cluster launch control is
+// level with this shape -- see copter_step_tma_kernel), so the hardware scheduler does the balancing.
+// (COPTER_PERSISTENT=1 / COPTER_PREFETCH=1 keep the old shape for A/B runs; profiles/README.md has
+// the sweep.)  The kernels keep their tile loop, so a grid capped at 2^31-1 CTAs still covers any n.
 template <auto Kernel>
 int grid_for(int64_t n) {
     static int per_sm = 0;
@@ -781,8 +954,38 @@ int check_params(const CopterParams* p) {
     return 0;
 }
 
+// resident-wave grid for the persistent-warp kernels
+template <auto Kernel>
+int resident_grid_for(int64_t n) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int q = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, Kernel, kBlock, 0) != cudaSuccess || q <= 0) q = 4;
+        per_sm = q;
+    }
+    const int64_t tiles = (n + kBlock - 1) / kBlock, cap = (int64_t)sm_count() * per_sm;
+    return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
+}
+
 template <typename T, int VARIANT>
 int launch_step_v(const KParams<T>& kp, const StepArgs<T>& a, cudaStream_t s) {
+    // K-fused launches: TMA-prefetched inputs (every bulk copy needs 16-byte aligned sources; the
+    // state planes and the action rows are checked by the caller, the meta words here)
+    if (COPTER_TMA_MIN_K > 0 && a.k >= COPTER_TMA_MIN_K && aligned16(a.meta) && a.n <= (int64_t)0x7fffffff * kBlock) {
+        constexpr bool kSingle = COPTER_TMA_MIN_K == 1 && COPTER_K1_SPECIALIZE;      // only an A/B build sends K = 1 here
+        // cluster launch control: the grid holds one CTA per tile and the resident CTAs steal the rest
+        const int64_t n_tiles = (a.n + kBlock - 1) / kBlock;
+#define COPTER_TMA_GRID(K) (COPTER_TMA_CLC ? (int)n_tiles : resident_grid_for<K>(a.n))
+        if (kSingle && a.k == 1) {
+            if (a.stats) copter_step_tma_kernel<T, VARIANT, true, kSingle><<<COPTER_TMA_GRID((copter_step_tma_kernel<T, VARIANT, true, kSingle>)), kBlock, 0, s>>>(kp, a);
+            else         copter_step_tma_kernel<T, VARIANT, false, kSingle><<<COPTER_TMA_GRID((copter_step_tma_kernel<T, VARIANT, false, kSingle>)), kBlock, 0, s>>>(kp, a);
+        } else {
+            if (a.stats) copter_step_tma_kernel<T, VARIANT, true, false><<<COPTER_TMA_GRID((copter_step_tma_kernel<T, VARIANT, true, false>)), kBlock, 0, s>>>(kp, a);
+            else         copter_step_tma_kernel<T, VARIANT, false, false><<<COPTER_TMA_GRID((copter_step_tma_kernel<T, VARIANT, false, false>)), kBlock, 0, s>>>(kp, a);
+        }
+#undef COPTER_TMA_GRID
+        return (int)cudaGetLastError();
+    }
     if (a.stats) copter_step_kernel<T, VARIANT, true><<<grid_for<copter_step_kernel<T, VARIANT, true>>(a.n), kBlock, 0, s>>>(kp, a);
     else         copter_step_kernel<T, VARIANT, false><<<grid_for<copter_step_kernel<T, VARIANT, false>>(a.n), kBlock, 0, s>>>(kp, a);
     return (int)cudaGetLastError();

@@ -19,6 +19,14 @@ SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
 VARIANTS = {}
 VARIANTS['current'] = []
 VARIANTS['nofast'] = ['-DCOPTER_FAST_SUBSTEP=0']      # K-fused loop without the straight-line substep
+VARIANTS['tma_k2'] = ['-DCOPTER_TMA_MIN_K=2']         # K-fused launches through the TMA-prefetch + cluster-launch-control kernel
+VARIANTS['tma_k2_c7'] = ['-DCOPTER_TMA_MIN_K=2', '-DCOPTER_TMA_CTAS_PER_SM=7']
+VARIANTS['tma_k1'] = ['-DCOPTER_TMA_MIN_K=1']         # K = 1 through the TMA kernel too
+VARIANTS['tma_k1_c6'] = ['-DCOPTER_TMA_MIN_K=1', '-DCOPTER_TMA_CTAS_PER_SM=6']
+VARIANTS['tma_k2_noclc'] = ['-DCOPTER_TMA_MIN_K=2', '-DCOPTER_TMA_CLC=0']         # static grid-stride tiles instead of cluster launch control
+VARIANTS['tma_k1_noclc'] = ['-DCOPTER_TMA_MIN_K=1', '-DCOPTER_TMA_CLC=0']
+if os.environ.get('COPTER_SWEEP_ONLY'):
+    VARIANTS = {k: v for k, v in VARIANTS.items() if k.startswith(tuple(os.environ['COPTER_SWEEP_ONLY'].split(',')))}
 
 
 def build():
