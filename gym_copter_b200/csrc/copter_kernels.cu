@@ -490,22 +490,48 @@ __device__ __forceinline__ double log_t(double a) { return log(a); }
 
 // Four variates xi_j = N(0,1) | U(-1,1) of (env, step, stream tag) from Philox4x32-10 with counter
 // (env_lo, env_hi, step, tag), key = seed (low word XOR the step's high word).
+//   U(-1,1): RN(c 2^-31 - 1), one rounding of the exact value.
+//   N(0,1):  Box-Muller on u1 = RN((c + 1) 2^-32) in (0, 1], u2 = RN(c' 2^-32), pairs (c0,c1), (c2,c3).
 template <typename T>
 __device__ __forceinline__ void draw_variates(uint64_t seed, uint64_t env, uint64_t step, uint32_t tag, bool uniform, T (&xi)[4]) {
     uint32_t c[4] = {(uint32_t)env, (uint32_t)(env >> 32), (uint32_t)step, tag};
     philox4x32_10(c, (uint32_t)seed ^ (uint32_t)(step >> 32), (uint32_t)(seed >> 32));
-    if (uniform) {
+    if constexpr (sizeof(T) == 4) {
+        // fp32: the same roundings without the FP64 pipe -- an integer converted with round-to-nearest
+        // and scaled by a power of two is the single rounding of the exact value (c 2^-31 - 1 =
+        // (c - 2^31) 2^-31 with c - 2^31 an int32).  The Gaussian transform uses the MUFU forms of sqrt
+        // and sin/cos (on an angle folded into [-pi, pi)): absolute error 5e-7 on the direction, i.e.
+        // <= 4e-6 on a variate at the 6.7-sigma end of the range; the fp64 path below keeps the library
+        // functions throughout.
+        if (uniform) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) xi[j] = (T)fma((double)c[j], 0x1p-31, -1.0);     // exact, one rounding
-    } else {                                                                         // Box-Muller, two pairs
+            for (int j = 0; j < 4; ++j) xi[j] = __int2float_rn((int)(c[j] ^ 0x80000000u)) * 0x1p-31f;
+        } else {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const T u1 = (T)(((double)c[2 * h] + 1.0) * 0x1p-32);                   // (0, 1]
-            const T u2 = (T)((double)c[2 * h + 1] * 0x1p-32);
-            const T r = sqrt_t((T)-2 * log_t(u1));
-            T sn, cs;
-            sincos_t((T)6.283185307179586 * u2, &sn, &cs);
-            xi[2 * h] = r * cs; xi[2 * h + 1] = r * sn;
+            for (int h = 0; h < 2; ++h) {
+                const float u1 = __ull2float_rn((unsigned long long)c[2 * h] + 1ull) * 0x1p-32f;      // (0, 1]
+                const float u2 = __uint2float_rn(c[2 * h + 1]) * 0x1p-32f;                            // [0, 1]
+                float r;
+                asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * logf(u1)));    // library logf: lg2.approx loses the small radii (u1 -> 1)
+                // cos / sin(2 pi u2) = -cos / -sin(2 pi (u2 - 1/2)): the folded angle stays where sin.approx is accurate
+                const float ang = 6.283185307179586f * (u2 - 0.5f);
+                xi[2 * h] = -r * __cosf(ang); xi[2 * h + 1] = -r * __sinf(ang);
+            }
+        }
+    } else {
+        if (uniform) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xi[j] = (T)fma((double)c[j], 0x1p-31, -1.0);     // exact, one rounding
+        } else {                                                                         // Box-Muller, two pairs
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const T u1 = (T)(((double)c[2 * h] + 1.0) * 0x1p-32);                   // (0, 1]
+                const T u2 = (T)((double)c[2 * h + 1] * 0x1p-32);
+                const T r = sqrt_t((T)-2 * log_t(u1));
+                T sn, cs;
+                sincos_t((T)6.283185307179586 * u2, &sn, &cs);
+                xi[2 * h] = r * cs; xi[2 * h + 1] = r * sn;
+            }
         }
     }
 }
