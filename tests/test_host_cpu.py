@@ -52,6 +52,28 @@ def test_params_struct_matches_header_and_reference_constants(lib):
         default_params(not_a_field=1)
 
 
+def test_pid_gains_struct_matches_header_and_reference_constants(lib):
+    """CopterPidGains: the ctypes mirror has the header's fields in the header's order, and the
+    defaults are the reference's controller constants (attic/mars/pidcontrollers/__init__.py:
+    AngularVelocityPidController :124-135, PositionHoldPidController :102-107,
+    DescentPidController :110-121, AltitudeHoldPidController :91-99, windup default :14)."""
+    from gym_copter_b200 import _lib as binding
+    hdr = open(os.path.join(ROOT, 'include', 'copter_b200.h')).read()
+    body = re.search(r'typedef struct CopterPidGains \{(.*?)\} CopterPidGains;', hdr, flags=re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    names = [n.strip() for decl in re.findall(r'double\s+([^;]+);', body) for n in decl.split(',')]
+    assert names == [f[0] for f in binding.CopterPidGains._fields_] and len(names) == 17
+    g = binding.default_pid_gains()
+    assert (g.rate_kp, g.rate_ki, g.rate_kd, g.rate_windup, g.rate_big) == (1.0, 0.0, 1.0, 6.0, np.radians(40))
+    assert (g.pos_kp, g.pos_ki, g.pos_kd, g.pos_windup, g.pos_target) == (0.00001, 0.1, 4.0, 0.2, 0.0)
+    assert (g.descent_kp, g.descent_kd) == (1.15, 1.33)
+    assert (g.alt_kp, g.alt_ki, g.alt_kd, g.alt_windup, g.alt_target) == (0.2, 3.0, 0.0, 0.2, 5.0)
+    assert binding.SOURCE_KINDS == {'const': 0, 'randn': 1, 'uniform': 2, 'pid': 3, 'pid_hover': 4}
+    assert all(re.search(r'COPTER_SRC_%s\s*=\s*%d\b' % (k.upper(), v), hdr) for k, v in binding.SOURCE_KINDS.items())
+    with pytest.raises(TypeError):
+        binding.default_pid_gains(not_a_gain=1)
+
+
 def test_argument_validation_without_a_gpu(lib):
     from gym_copter_b200 import default_params
     from gym_copter_b200._lib import CopterBuffers

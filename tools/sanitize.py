@@ -6,7 +6,8 @@ Developer tool, run on the GPU box under compute-sanitizer:
     compute-sanitizer --tool racecheck python tools/sanitize.py
 
 Exercises every kernel on ragged sizes (partial warps / partial tiles), every variant, both
-precisions, statistics, final observations, injected forces, K-fusion, the fused rollouts, the
+precisions, statistics, final observations, injected forces, K-fusion, the fused rollouts with
+every action source (drawn and PID heuristics), the
 policy kernels and the host-array pipeline, so that out-of-bounds accesses and shared-memory hazards in the
 obs staging tiles would be reported.
 """
@@ -30,6 +31,9 @@ for variant in ('Lander3D', 'Lander2D', 'Lander1D', 'Hover3D', 'Hover2D', 'Hover
                 env.step(a)
             env.rollout(5, source='randn', record_rewards=True, record_dones=True, record_actions=True)
             env.rollout(3, source='uniform')
+            env.rollout(4, source='pid', scale=2e-3, offset=0.0149, record_actions=True)            # 3-D / planar landing heuristics
+            if variant != 'Lander3D':                                                              # hover heuristics ([N,24] controller memories)
+                env.rollout(4, source='pid_hover', scale=0.0331, record_actions=True)
             env.stats()
 for variant in ('Lander3D', 'Lander2D', 'Lander1D', 'Hover3D'):
     for n in (1, 33, 129, 300):
