@@ -32,6 +32,15 @@ template <typename T, int A> struct RawEnv {
     uint32_t meta;
 };
 
+__device__ __forceinline__ uint32_t low_word(float v)  { return __float_as_uint(v); }
+__device__ __forceinline__ uint32_t low_word(double v) { return (uint32_t)__double2loint(v); }
+__device__ __forceinline__ float  or_words(float v, uint32_t m)  { return __uint_as_float(__float_as_uint(v) | m); }
+__device__ __forceinline__ double or_words(double v, uint32_t m) { return __hiloint2double(__double2hiint(v) | (int)m, __double2loint(v) | (int)m); }
+
+#ifndef COPTER_TIE_LOADS
+#define COPTER_TIE_LOADS 1        // 0 (A/B knob): leave the placement of the action row's first use to ptxas
+#endif
+
 template <typename T, int A>
 __device__ __forceinline__ void load_raw(const StepArgs<T>& a, int64_t i, RawEnv<T, A>& r) {
     using V4 = typename Vec<T>::type;
@@ -56,6 +65,24 @@ __device__ __forceinline__ void load_raw(const StepArgs<T>& a, int64_t i, RawEnv
         r.act[0] = v.x; r.act[1] = v.y;
     } else {
         r.act[0] = a.action[i];
+    }
+    // ptxas is free to place the first use of the action row (its clip) anywhere after the action
+    // loads -- and has placed it BEFORE the state loads (fp64 Hover3D: 58 instructions and one full
+    // memory round trip between the two groups, 0.221 instead of 0.190 ms per launch; which
+    // instantiation is hit changes with unrelated edits).  The tie below makes every word of the
+    // action row depend on the meta word and one word of every state plane through a value the compiler cannot know
+    // is zero (the sign bit of n), so that no use of the action can be scheduled
+    // before all of this env's loads have been issued.  Measured (B200): the tie costs 1 % where ptxas
+    // had the good order anyway (0.1908 vs 0.1887 ms fp64; fp32 K = 1 0.4191 vs 0.4176, K = 4 0.593 vs
+    // 0.585) and saves 14 % where it had not, so it is applied to the fp64 kernels, where the bad
+    // order has been seen; the fp32 kernels keep ptxas' own schedule, pinned by tests/test_sass_guards.py.
+    if (COPTER_TIE_LOADS && sizeof(T) == 8) {
+        uint32_t mix = r.meta;
+#pragma unroll
+        for (int pl = 0; pl < 12 / V; ++pl) mix |= low_word(r.plane[pl].x);
+        mix &= (uint32_t)((uint64_t)a.n >> 63);
+#pragma unroll
+        for (int j = 0; j < A; ++j) r.act[j] = or_words(r.act[j], mix);
     }
 }
 
@@ -130,11 +157,12 @@ __device__ __forceinline__ void debit_idle_steps(double* stats, int lane, int id
 // instructions per env-step on the HBM-bound path).
 template <typename T, int VARIANT, bool STATS, bool SINGLE, bool PRELOADED>
 __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T>& a,
-                                          const RawEnv<T, Variant<VARIANT>::A>& preloaded, float* tiles, int64_t row0) {
+                                          const RawEnv<T, Variant<VARIANT>::A>& preloaded, float* tiles, int64_t tile_id) {
     constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A;
     // (recomputed here rather than passed in: cheaper than keeping five values live across the body)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t i = row0 + lane;                               // row0 = first env of this warp
+    const int64_t row0 = tile_id * kBlock + warp * 32;           // first env of this warp
+    const int64_t i = row0 + lane;
     const bool valid = i < a.n;
     const int rows = (int)max((int64_t)0, min((int64_t)32, a.n - row0));
     float* tile = tiles + warp * (32 * O);
@@ -285,9 +313,8 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
             const int64_t inext = (tile_id + gridDim.x) * kBlock + threadIdx.x;
             if (inext < a.n) load_raw<T, A>(a, inext, nxt);
         }
-        const int64_t row0 = tile_id * kBlock + (threadIdx.x >> 5) * 32;
-        if (COPTER_K1_SPECIALIZE && a.k == 1) step_tile<T, VARIANT, STATS, true, kPrefetch>(kp, a, cur, &tiles[0][0], row0);
-        else                                  step_tile<T, VARIANT, STATS, false, kPrefetch>(kp, a, cur, &tiles[0][0], row0);
+        if (COPTER_K1_SPECIALIZE && a.k == 1) step_tile<T, VARIANT, STATS, true, kPrefetch>(kp, a, cur, &tiles[0][0], tile_id);
+        else                                  step_tile<T, VARIANT, STATS, false, kPrefetch>(kp, a, cur, &tiles[0][0], tile_id);
         if (kPrefetch) cur = nxt;
     }
 }
@@ -461,7 +488,7 @@ copter_step_tma_kernel(const __grid_constant__ KParams<T> kp, const __grid_const
         } else if (row0 + lane < a.n) {
             load_raw<T, A>(a, row0 + lane, cur);
         }
-        step_tile<T, VARIANT, STATS, SINGLE, true>(kp, a, cur, &tiles[0][0], row0);
+        step_tile<T, VARIANT, STATS, SINGLE, true>(kp, a, cur, &tiles[0][0], (int64_t)tile);
         if (nxt == kNone) break;
         tile = nxt;
     }
