@@ -509,28 +509,34 @@ class SingleEnv:
             setattr(self, k, getattr(self.vec, 'single_' + k))
         self.STATE_NAMES, self.TARGET_RADIUS = self.vec.STATE_NAMES, self.vec.TARGET_RADIUS
         self.FRAMES_PER_SECOND, self.metadata = self.vec.FRAMES_PER_SECOND, self.vec.metadata
-        self.viewer, self.pose, self.done = None, None, False
+        self.viewer, self.done = None, False
+        self._host = self.vec.host_buffers()        # page-locked action / obs / reward / done of the one env
 
     @property
     def unwrapped(self):
         return self
 
+    @property
+    def pose(self):
+        """(x, y, z, phi, theta, psi) as envs/task.py:102 sets it for the renderer thread; read from
+        the device on demand (psi is not part of the Lander observation), so a plain step() loop does
+        not pay for it."""
+        s = self.vec.state_planes.reshape(12).cpu().numpy()         # one env: plane-major order is component order
+        return (s[0], s[2], s[4], s[6], s[8], s[10])
+
     def reset(self, seed=None, options=None, force=None):
         obs, info = self.vec.reset(seed, options, None if force is None else np.asarray(force).reshape(1, 3))
         self.done = False
-        self._update_pose()
         return obs[0].cpu().numpy(), info
 
     def step(self, action):
-        a = np.asarray(action, dtype=np.float64).reshape(1, -1)
-        obs, r, term, trunc, info = self.vec.step(a)
-        self.done = bool(term[0].item())
-        self._update_pose()
-        return obs[0].cpu().numpy(), float(r[0].item()), self.done, False, {}
-
-    def _update_pose(self):
-        s = self.vec.state[0].cpu().numpy()
-        self.pose = (s[0], s[2], s[4], s[6], s[8], s[10])          # task.py:102
+        # one library call per step: the command goes in and observation / reward / done come back
+        # through the page-locked buffers of copter_step_host_* (H2D + kernel + D2H + one stream sync)
+        h = self._host
+        h['action'][0, :] = np.asarray(action, dtype=h['action'].dtype).reshape(-1)
+        obs, r, term, _, _ = self.vec.step_host(None, n_streams=1)
+        self.done = bool(term[0])
+        return obs[0].copy(), float(r[0]), self.done, False, {}
 
     def set_altitude(self, altitude):
         self.vec.set_altitude(altitude)

@@ -147,7 +147,31 @@ def fp64():
     print(json.dumps({'bench': 'config4 Hover3D fp64 2^22 envs', 'ms_per_step': ms, 'steps_per_s': n / ms * 1e3, 'gbs': 289 * n / ms / 1e6}), flush=True)
 
 
+def single():
+    """config 1: the single-env facade (`make('gym_copter:Lander-v0')`) in lander.py's loop --
+    latency per step() call (one env cannot use the GPU's width; this is the drop-in call shape)."""
+    import time
+    import numpy as np
+    for dt in (torch.float64, torch.float32):
+        env = g.make('gym_copter:Lander-v0', dtype=dt)
+        env.reset()
+        a = 1.625e-2 * np.ones(4)
+        n, steps = 0, 0
+        for _ in range(200):
+            env.step(a)
+        t0 = time.perf_counter()
+        while steps < 5000:
+            obs, r, done, _, _ = env.step(a)
+            steps += 1
+            if done:
+                env.reset(); n += 1
+        el = time.perf_counter() - t0
+        print(json.dumps({'bench': 'config1 single-env facade Lander-v0 %s, constant thrust, reset on done' % str(dt).split('.')[-1],
+                          'us_per_step': el / steps * 1e6, 'steps_per_s': steps / el, 'episodes': n}), flush=True)
+        env.close()
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['config2', 'rollout', 'policy', 'fp64', 'zerocopy']
+    which = sys.argv[1:] or ['config2', 'rollout', 'policy', 'fp64', 'zerocopy', 'single']
     for w in which:
         globals()[w]()
