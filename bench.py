@@ -338,6 +338,19 @@ def main():
             extras['k%d' % kk] = {'value': world * done_steps / (ms_kk * 1e-3), 'unit': UNIT,
                                   'ms_per_launch': ms_kk / steps_kk,
                                   'note': 'executed env-steps only (envs idle after done within a launch)'}
+            # the same K through the host-array API: one action row in, one observation row out per K env-steps
+            hb = senv.host_buffers()
+            hb['action'][:] = actions[0].cpu().numpy()
+            senv.step_host(None)
+            barrier()
+            before = senv.stats()['env_steps']
+            t0 = time.perf_counter()
+            for _ in range(max(3, args.e2e_steps // 4)):
+                senv.step_host(None)
+            torch.cuda.synchronize()
+            el = max_over_ranks(time.perf_counter() - t0)
+            extras['k%d' % kk]['e2e'] = {'value': world * (senv.stats()['env_steps'] - before) / el, 'unit': UNIT,
+                                         'api': 'CopterVecEnv.step_host, k_substeps=%d' % kk}
         senv.k_substeps = 1
     del senv
     torch.cuda.empty_cache()
