@@ -236,7 +236,50 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
             // machine, no perturbation, one predicated region.  Anything else takes the general step.
             const bool hot = airborne_hot<T>(s, st, steps);
             const bool fast = COPTER_FAST_SUBSTEP && __all_sync(0xffffffffu, (int)!live | (int)hot);
-            if (live) {
+            if (COPTER_CALM_STREAK && fast) {                           // warp-uniform
+                // Streak of straight-line substeps: as long as every live lane stays calm (airborne_calm:
+                // nothing ended, still in the common case) the next substep needs neither the ending flags
+                // nor the hot test -- one compare chain and one vote per substep.  The loop is executed by
+                // the whole warp (k stays uniform); lanes whose env already finished in this launch idle in it.
+                bool calm = true, tmo = false;
+                int streak = 0;
+                do {
+                    if (live) {
+                        dz_prev = s[5];
+                        tmo = steps == kp.max_steps;
+                        airborne_arith<T>(kp, s, forces, na, nc);
+                        ++steps;
+                        calm = airborne_calm<T>(kp, s, tmo);
+                        if (calm) { run.na += na; run.nc += nc; }
+                    }
+                    ++streak; ++k;
+                } while (k < a.k && __all_sync(0xffffffffu, calm));
+                --k;                                                   // the for statement counts the last one
+                if (live) {
+                    run.steps += streak;
+                    steps = min(steps, 2047);
+                    int end = 0;
+                    if (!calm) {                                       // back to the exact tests for this lane's last step
+                        end = airborne_flags<T>(kp, s, tmo);
+                        if (!(end & END_ANGLE)) { run.na += na; run.nc += nc; }
+                    }
+                    if (end != 0) {
+                        cause = airborne_cause(end);
+                        live = false;
+                        ep_cause = cause;
+                        total = run_reward<T, VARIANT>(kp, run, s, cause, na, nc, dz_prev);
+                        if (STATS) ep_len = steps - 1;                 // `steps` is 1 right after reset (task.py:191,197)
+                        if (a.final_obs) {   // terminal observation; rows of unfinished envs stay untouched
+#pragma unroll
+                            for (int j = 0; j < O; ++j) a.final_obs[i * O + j] = (float)s[Variant<VARIANT>::first + j];
+                        }
+                        if (a.auto_reset) {
+                            reset_state<T>(kp, s, st, steps);
+                            episode = (episode + 1) & 0x7FFFFu;
+                        }
+                    }
+                }
+            } else if (live) {
                 dz_prev = s[5];
                 bool dn;
                 if (fast) {

@@ -52,6 +52,9 @@ namespace copter {
 #ifndef COPTER_FAST_SUBSTEP
 #define COPTER_FAST_SUBSTEP 1     // 0 (A/B knob): every substep of a K-fused launch takes the general env_advance
 #endif
+#ifndef COPTER_CALM_STREAK
+#define COPTER_CALM_STREAK 1     // 0 (A/B knob): every straight-line substep re-derives the ending flags and the hot test
+#endif
 #ifndef COPTER_STREAMING
 #define COPTER_STREAMING 0      // 1: evict-first (ld/st .cs) hints on the state planes
 #endif
@@ -85,6 +88,7 @@ struct KParams {
     T lvx, lvy, lang, invM;
     T jx, jy;                     // Jr/Ix, Jr/Iy
     T oob_penalty, max_angle, bounds, z0, target_radius;
+    T calm_angle;            // min(max_angle, polynomial sin/cos range): below it a step neither ends over-angle nor leaves the fast path
     T yaw_pf, xyz_pf, dz_max, dz_penalty, bonus;
     int max_steps;
     int status0;                  // status right after reset (dynamics/__init__.py:215-217)
@@ -116,6 +120,7 @@ KParams<T> make_kparams(const CopterParams& p) {
     k.invM = (T)(1.0 / p.M);
     k.oob_penalty = (T)p.out_of_bounds_penalty;
     k.max_angle = (T)(p.max_angle_deg * M_PI / 180.0);
+    k.calm_angle = (sizeof(T) == 4 && k.max_angle > (T)0.78539816f) ? (T)0.78539816f : k.max_angle;
     k.bounds = (T)p.bounds;
     k.z0 = (T)(-p.initial_altitude);
     k.target_radius = (T)p.target_radius;
@@ -415,20 +420,40 @@ __device__ __forceinline__ bool airborne_hot(const T (&s)[12], int st, int steps
 // tests them with if / elif, task.py:111-118), bit 2 the env's own step limit; 0 = the episode goes
 // on.  airborne_cause() turns them into the CAUSE_* bits env_advance reports.
 enum { END_OOB = 1, END_ANGLE = 2, END_TIMEOUT = 4 };
-template <typename T, int VARIANT>
-__device__ __forceinline__ int airborne_substep(const KParams<T>& kp, T (&s)[12], int& steps, const Forces<T>& f,
-                                                T& na, T& nc) {
+// the arithmetic of one such step (no flags, no step counter)
+template <typename T>
+__device__ __forceinline__ void airborne_arith(const KParams<T>& kp, T (&s)[12], const Forces<T>& f, T& na, T& nc) {
     T sph, cph, sth, cth, sps, cps;
     if constexpr (sizeof(T) == 4) { sincos_poly(s[6], sph, cph); sincos_poly(s[8], sth, cth); sincos_poly(s[10], sps, cps); }
     else sincos3_t(s[6], s[8], s[10], sph, cph, sth, cth, sps, cps);
     const T none[3] = {(T)0, (T)0, (T)0};
     airborne_integrate<T, 3, false>(kp, s, f, none, sph, cph, sth, cth, sps, cps, na, nc);
-    // task.py:111-130 with the stale status AIRBORNE
+}
+// task.py:111-130 with the stale status AIRBORNE, on the state after the step
+template <typename T>
+__device__ __forceinline__ int airborne_flags(const KParams<T>& kp, const T (&s)[12], bool timeout) {
     const bool oob = abs_t(s[0]) >= kp.bounds || abs_t(s[2]) >= kp.bounds;
     const bool ang = !oob && (abs_t(s[6]) >= kp.max_angle || abs_t(s[8]) >= kp.max_angle);
+    return (oob ? END_OOB : 0) | (ang ? END_ANGLE : 0) | (timeout ? END_TIMEOUT : 0);
+}
+template <typename T, int VARIANT>
+__device__ __forceinline__ int airborne_substep(const KParams<T>& kp, T (&s)[12], int& steps, const Forces<T>& f,
+                                                T& na, T& nc) {
+    airborne_arith<T>(kp, s, f, na, nc);
     const bool timeout = steps == kp.max_steps;
     steps = min(steps + 1, 2047);
-    return (oob ? END_OOB : 0) | (ang ? END_ANGLE : 0) | (timeout ? END_TIMEOUT : 0);
+    return airborne_flags<T>(kp, s, timeout);
+}
+// "Calm" after a straight-line step: the step ended nothing (in bounds, under the angle limit, not
+// the step limit) AND the env is still in airborne_hot()'s common case, so the next substep can be
+// straight-line too.  Deliberately a little stricter than the two conditions it implies (psi is held
+// to the angle limit as well, `<` instead of `<=` at the polynomial range): a lane that is not calm
+// just goes back to the exact tests.  Five compares instead of the flags + hot + two warp votes.
+template <typename T>
+__device__ __forceinline__ bool airborne_calm(const KParams<T>& kp, const T (&s)[12], bool timeout) {
+    const T m_xy = fmax(abs_t(s[0]), abs_t(s[2]));
+    const T m_ang = fmax(fmax(abs_t(s[6]), abs_t(s[8])), abs_t(s[10]));
+    return (int)!timeout & (int)(m_xy < kp.bounds) & (int)(m_ang < kp.calm_angle) & (int)!(s[4] > (T)0 && s[5] > (T)0);
 }
 __device__ __forceinline__ int airborne_cause(int end) {
     return ((end & END_OOB) ? CAUSE_OOB : 0) | ((end & END_ANGLE) ? CAUSE_ANGLE : 0) | ((end & END_TIMEOUT) ? CAUSE_TIMEOUT : 0);

@@ -19,6 +19,7 @@ SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
 VARIANTS = {}
 VARIANTS['current'] = []
 VARIANTS['nofast'] = ['-DCOPTER_FAST_SUBSTEP=0']      # K-fused loop without the straight-line substep
+VARIANTS['nostreak'] = ['-DCOPTER_CALM_STREAK=0']     # K-fused loop: flags + hot test + two votes on every substep
 VARIANTS['tma_k2'] = ['-DCOPTER_TMA_MIN_K=2']         # K-fused launches through the TMA-prefetch + cluster-launch-control kernel
 VARIANTS['tma_k2_c7'] = ['-DCOPTER_TMA_MIN_K=2', '-DCOPTER_TMA_CTAS_PER_SM=7']
 VARIANTS['tma_k1'] = ['-DCOPTER_TMA_MIN_K=1']         # K = 1 through the TMA kernel too
