@@ -164,7 +164,8 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
     const int64_t row0 = tile_id * kBlock + warp * 32;           // first env of this warp
     const int64_t i = row0 + lane;
     const bool valid = i < a.n;
-    const int rows = (int)max((int64_t)0, min((int64_t)32, a.n - row0));
+    const int64_t left = a.n - row0;                             // envs from row0 on (may be <= 0 in the last tile)
+    const int rows = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
     float* tile = tiles + warp * (32 * O);
     T s[12];
     T m[4] = {(T)0, (T)0, (T)0, (T)0};
@@ -345,6 +346,14 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
     // COPTER_PREFETCH (A/B knob, persistent grids): the raw vectors of this thread's env in the
     // NEXT tile are requested before the current tile's arithmetic starts.
     constexpr bool kPrefetch = COPTER_PREFETCH && sizeof(T) == 4;
+    if constexpr (!COPTER_PERSISTENT && !kPrefetch) {
+        // the shipped shape: the grid holds exactly one CTA per tile (launch_step_v), so there is no
+        // tile loop and no tile count to derive
+        RawEnv<T, A> none;
+        if (COPTER_K1_SPECIALIZE && a.k == 1) step_tile<T, VARIANT, STATS, true, false>(kp, a, none, &tiles[0][0], (int64_t)blockIdx.x);
+        else                                  step_tile<T, VARIANT, STATS, false, false>(kp, a, none, &tiles[0][0], (int64_t)blockIdx.x);
+        return;
+    }
     const int64_t n_tiles = (a.n + kBlock - 1) / kBlock;
     RawEnv<T, A> cur, nxt;
     if (kPrefetch) {
@@ -1040,6 +1049,8 @@ int grid_for(int64_t n) {
     const int64_t cap = COPTER_PERSISTENT ? (int64_t)sm_count() * per_sm : (int64_t)0x7fffffff;
     return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
+// the step kernel's shipped shape has no tile loop: every tile needs its own CTA
+constexpr int64_t kMaxEnvsPerLaunch = COPTER_PERSISTENT ? INT64_MAX : (int64_t)0x7fffffff * kBlock;
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -1093,7 +1104,7 @@ int launch_step(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_
     int e = check_params(p);
     if (e) return e;
     if (!b || !b->state || !b->meta || !b->action || !b->reward || !b->done) return COPTER_E_ARG;
-    if (n < 0 || env_offset < 0 || k < 1 || (b->state_stride > 0 && b->state_stride < n)) return COPTER_E_RANGE;
+    if (n < 0 || n > kMaxEnvsPerLaunch || env_offset < 0 || k < 1 || (b->state_stride > 0 && b->state_stride < n)) return COPTER_E_RANGE;
     if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
     if (!aligned16(b->state) || !aligned16(b->action) || (b->obs && !aligned16(b->obs))) return COPTER_E_ALIGN;
     if (n == 0) return 0;
