@@ -208,3 +208,21 @@ def test_gymnasium_shell_is_guarded_and_registers():
             del sys.modules[k]
         if had is not None:
             sys.modules['gymnasium'] = had
+
+
+def test_integration_md_stub_matches_the_binding():
+    """The ctypes stub printed in INTEGRATION.md (what a maintainer of the reference would paste)
+    declares the same struct fields, in the same order, as the shipped binding and the header."""
+    from gym_copter_b200 import _lib as binding
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    code = re.search(r'```python\n# gym_copter/envs/_b200.py.*?```', doc, flags=re.S).group(0)
+    ns = {}
+    structs = re.search(r'(class CopterParams\(C\.Structure\):.*?)\nLANDER3D', code, flags=re.S).group(1)
+    exec('import ctypes as C\n' + structs, ns)
+    for name in ('CopterParams', 'CopterBuffers'):
+        mine, theirs = getattr(binding, name), ns[name]
+        assert [f[0] for f in theirs._fields_] == [f[0] for f in mine._fields_], name
+        assert C.sizeof(theirs) == C.sizeof(mine), name
+    # every library call the stub makes exists with that name
+    for fn in set(re.findall(r'lib\.(copter_[a-z0-9_]+)\(', code)):
+        assert hasattr(binding.load(), fn), fn
