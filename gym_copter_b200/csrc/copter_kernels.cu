@@ -564,7 +564,6 @@ struct RolloutArgs {
     T alt_kp, alt_ki, alt_kd, alt_windup, alt_target;
 };
 
-__device__ __forceinline__ float  log_t(float a)  { return logf(a); }
 __device__ __forceinline__ double log_t(double a) { return log(a); }
 
 // Four variates xi_j = N(0,1) | U(-1,1) of (env, step, stream tag) from Philox4x32-10 with counter
