@@ -1,0 +1,47 @@
+#!/usr/bin/env python3
+"""
+Developer tool: cross-compiles the library once per A/B knob combination (no GPU needed) so that
+the alternative shapes kept for measurements -- persistent grids, register / TMA prefetch, cluster
+launch control, the untied loads, the plain K loop, the library-only math, the policy variants --
+do not rot.  Runs the builds in parallel; prints one line per combination.
+
+    python tools/check_knobs.py
+"""
+import os
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
+COMBOS = [
+    ['-DCOPTER_PERSISTENT=1'],
+    ['-DCOPTER_PERSISTENT=1', '-DCOPTER_PREFETCH=1'],
+    ['-DCOPTER_TMA_MIN_K=1'],
+    ['-DCOPTER_TMA_MIN_K=2', '-DCOPTER_TMA_CLC=0', '-DCOPTER_TMA_CTAS_PER_SM=7'],
+    ['-DCOPTER_TIE_LOADS=0', '-DCOPTER_CALM_STREAK=0'],
+    ['-DCOPTER_FAST_SUBSTEP=0', '-DCOPTER_LIBM_ONLY=1'],
+    ['-DCOPTER_STREAMING=1', '-DCOPTER_K1_SPECIALIZE=0', '-DCOPTER_K_UNROLL=4'],
+    ['-DCOPTER_POLICY_POLY_MASK=0x88', '-DCOPTER_POLICY_MT=1'],
+    ['-DCOPTER_POLICY_POLY_MASK=0xff', '-DCOPTER_POLICY_POLY_F32X2=0', '-DCOPTER_POLICY_TANH_BF16X2=1'],
+]
+
+
+def main():
+    with tempfile.TemporaryDirectory() as tmp:
+        procs = []
+        for i, flags in enumerate(COMBOS):
+            cmd = ['nvcc', '-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fPIC', '-shared'] \
+                  + flags + ['-o', os.path.join(tmp, 'lib_%d.so' % i), SRC]
+            procs.append((flags, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        bad = 0
+        for flags, p in procs:
+            out, _ = p.communicate()
+            errors = [line for line in out.splitlines() if 'error' in line.lower()]
+            print('%-90s %s' % (' '.join(flags), 'ok' if p.returncode == 0 else 'FAILED: ' + ' | '.join(errors[:3])))
+            bad += p.returncode != 0
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == '__main__':
+    main()
