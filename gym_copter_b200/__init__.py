@@ -8,8 +8,8 @@ build it with `python -m gym_copter_b200.build`.  There is no CPU fallback.
 
 from ._lib import CopterError, CopterParams, default_params, load as load_library   # noqa: F401
 from .envs import (CopterVecEnv, LanderVec, Lander3DVec, Lander2DVec, Lander1DVec,     # noqa: F401
-                   Hover3DVec, Hover2DVec, Hover1DVec, Lander, Lander3D, Lander2D,
-                   Lander1D, Hover3D, Hover2D, Hover1D, SingleEnv, make)
+                   Hover3DVec, Hover2DVec, Hover1DVec, TakeoffVec, Lander, Lander3D, Lander2D,
+                   Lander1D, Hover3D, Hover2D, Hover1D, Takeoff, SingleEnv, make)
 from .dynamics import Dynamics                                                         # noqa: F401
 from .sharding import shard_range, make_sharded_env, all_reduce_stats                  # noqa: F401
 from .rollout import FusedMLPPolicy, FusedPolicyRollout, PolicyRollout, PlanarLinear, mlp_policy                                         # noqa: F401

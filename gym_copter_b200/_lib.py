@@ -9,14 +9,15 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 # COPTER_B200_LIB: developer knob used by tools/sweep.py to time alternative builds
 LIB_PATH = os.environ.get('COPTER_B200_LIB') or os.path.join(PKG, 'libcopter_b200.so')
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 STATS_LEN = 16
 STATS_SLOTS = 64
-F_AUTO_RESET = 1
+F_AUTO_RESET, F_KEEP_EPISODE = 1, 2
+MAX_STEPS_LIMIT, MAX_STEPS_LIMIT_WIDE = 2046, 0x3FFFFFFE
 MODEL_LIFT, MODEL_GYRO = 1, 2
 CAUSE_LANDED, CAUSE_BONUS, CAUSE_OOB, CAUSE_ANGLE, CAUSE_CRASHED, CAUSE_TIMEOUT = 1, 2, 4, 8, 16, 32
 STATUS_CRASHED, STATUS_LANDED, STATUS_LEVELING, STATUS_AIRBORNE = 0, 1, 2, 3
-VARIANT_IDS = {'Lander3D': 0, 'Lander2D': 1, 'Lander1D': 2, 'Hover3D': 3, 'Hover2D': 4, 'Hover1D': 5}
+VARIANT_IDS = {'Lander3D': 0, 'Lander2D': 1, 'Lander1D': 2, 'Hover3D': 3, 'Hover2D': 4, 'Hover1D': 5, 'Takeoff': 6}
 STAT_NAMES = ('episodes', 'return_sum', 'length_sum', 'landed', 'bonus', 'crashed', 'oob',
               'angle', 'timeout', 'env_steps')
 
@@ -28,14 +29,16 @@ class CopterParams(C.Structure):
         'fps', 'initial_random_force', 'out_of_bounds_penalty', 'max_angle_deg', 'bounds',
         'initial_altitude',
         'target_radius', 'yaw_penalty_factor', 'xyz_penalty_factor', 'dz_max', 'dz_penalty',
-        'inside_radius_bonus', 'rho', 'lift_coefficient')] + [('max_steps', C.c_int32), ('dynamics_model', C.c_int32)]
+        'inside_radius_bonus', 'rho', 'lift_coefficient', 'takeoff_target_altitude')] + [
+        ('max_steps', C.c_int32), ('dynamics_model', C.c_int32)]
 
 
 class CopterBuffers(C.Structure):
     _fields_ = [('state', C.c_void_p), ('meta', C.c_void_p), ('action', C.c_void_p),
                 ('obs', C.c_void_p), ('reward', C.c_void_p), ('done', C.c_void_p),
                 ('init_force', C.c_void_p), ('ep_return', C.c_void_p), ('stats', C.c_void_p),
-                ('final_obs', C.c_void_p), ('cause', C.c_void_p), ('state_stride', C.c_int64)]
+                ('final_obs', C.c_void_p), ('cause', C.c_void_p), ('state_stride', C.c_int64),
+                ('meta_hi', C.c_void_p)]
 
 
 class CopterActionSource(C.Structure):
@@ -96,7 +99,7 @@ def load():
     for f in (lib.copter_obs_size, lib.copter_action_size):
         f.argtypes, f.restype = [i32], i32
     for f in (lib.copter_reset_f32, lib.copter_reset_f64):
-        f.argtypes, f.restype = [P, B, i64, i32, vp], i32
+        f.argtypes, f.restype = [P, B, i64, i32, i32, vp], i32
     for f in (lib.copter_step_f32, lib.copter_step_f64):
         f.argtypes, f.restype = [P, B, i64, i64, u64, i32, i32, i32, vp], i32
     for f in (lib.copter_dynamics_f32, lib.copter_dynamics_f64):
@@ -114,7 +117,7 @@ def load():
     lib.copter_pipeline_create.argtypes, lib.copter_pipeline_create.restype = [i32, C.POINTER(vp)], i32
     lib.copter_pipeline_destroy.argtypes, lib.copter_pipeline_destroy.restype = [vp], i32
     for f in (lib.copter_step_host_f32, lib.copter_step_host_f64):
-        f.argtypes, f.restype = [vp, P, B, vp, vp, vp, vp, i64, i64, u64, i32, i32, i32, i64, vp], i32
+        f.argtypes, f.restype = [vp, P, B, vp, vp, vp, vp, vp, vp, i64, i64, u64, i32, i32, i32, i64, vp], i32
     if lib.copter_abi_version() != ABI_VERSION:
         raise CopterError('libcopter_b200.so ABI %d != binding ABI %d: rebuild'
                           % (lib.copter_abi_version(), ABI_VERSION))

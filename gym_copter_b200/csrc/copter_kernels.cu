@@ -19,7 +19,7 @@ using namespace copter;
 
 template <typename T>
 struct StepArgs {
-    T* state; uint32_t* meta; const T* action; float* obs; T* reward; uint8_t* done;
+    T* state; uint32_t* meta; uint32_t* meta_hi; const T* action; float* obs; T* reward; uint8_t* done;
     const T* init_force; T* ep_return; double* stats; float* final_obs; uint8_t* cause;
     int64_t n, stride, env_offset; uint64_t seed; int k; int auto_reset;
 };
@@ -29,7 +29,7 @@ struct StepArgs {
 template <typename T, int A> struct RawEnv {
     typename Vec<T>::type plane[12 / Vec<T>::V];
     T act[A];
-    uint32_t meta;
+    uint32_t meta, meta_hi;
 };
 
 __device__ __forceinline__ uint32_t low_word(float v)  { return __float_as_uint(v); }
@@ -50,6 +50,7 @@ __device__ __forceinline__ void load_raw(const StepArgs<T>& a, int64_t i, RawEnv
     for (int pl = 0; pl < 12 / V; ++pl)
         r.plane[pl] = COPTER_STREAMING ? __ldcs(&planes[(int64_t)pl * a.stride + i]) : planes[(int64_t)pl * a.stride + i];
     r.meta = a.meta[i];
+    r.meta_hi = a.meta_hi ? a.meta_hi[i] : 0u;
     if constexpr (A == 4 && sizeof(T) == 4) {
         const float4 v = reinterpret_cast<const float4*>(a.action)[i];
         r.act[0] = v.x; r.act[1] = v.y; r.act[2] = v.z; r.act[3] = v.w;
@@ -86,8 +87,8 @@ __device__ __forceinline__ void load_raw(const StepArgs<T>& a, int64_t i, RawEnv
     }
 }
 
-template <typename T, int A>
-__device__ __forceinline__ void decode_raw(const RawEnv<T, A>& r, T (&s)[12], T (&m)[4], int& st, int& steps, uint32_t& episode) {
+template <typename T, int VARIANT>
+__device__ __forceinline__ void decode_raw(const RawEnv<T, Variant<VARIANT>::A>& r, bool wide, T (&s)[12], T (&m)[4], int& st, int& steps, uint32_t& episode) {
     constexpr int V = Vec<T>::V;
 #pragma unroll
     for (int pl = 0; pl < 12 / V; ++pl) {
@@ -95,14 +96,11 @@ __device__ __forceinline__ void decode_raw(const RawEnv<T, A>& r, T (&s)[12], T 
 #pragma unroll
         for (int j = 0; j < V; ++j) s[pl * V + j] = e[j];
     }
-    st = (int)(r.meta & 3u); steps = (int)((r.meta >> 2) & 2047u); episode = r.meta >> 13;
-    // action row, clipped to [0,1] (task.py:91) and fanned out (_get_motors)
-    T act[A];
-#pragma unroll
-    for (int j = 0; j < A; ++j) act[j] = fmin(fmax(r.act[j], (T)0), (T)1);
-    if constexpr (A == 4) { m[0] = act[0]; m[1] = act[1]; m[2] = act[2]; m[3] = act[3]; }
-    else if constexpr (A == 2) { m[0] = act[0]; m[1] = act[1]; m[2] = act[1]; m[3] = act[0]; }   // attic lander2d.py:49-51
-    else { m[0] = m[1] = m[2] = m[3] = act[0]; }                                                // attic lander1d.py:47-49
+    st = (int)(r.meta & 3u);
+    if (wide) { steps = (int)(r.meta >> 2); episode = r.meta_hi; }
+    else      { steps = (int)((r.meta >> 2) & 2047u); episode = r.meta >> 13; }
+    // action row, clipped to [0,1] (task.py:91; not for the Takeoff variant) and fanned out (_get_motors)
+    motors_from_action<T, VARIANT>(r.act, m);
 }
 
 // Folds the episodes that ended in this warp (flag `ended_lane`) into the statistics: ballot /
@@ -175,11 +173,11 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
 
     if (valid) {
         if constexpr (PRELOADED) {
-            decode_raw<T, A>(preloaded, s, m, st, steps, episode);
+            decode_raw<T, VARIANT>(preloaded, a.meta_hi != nullptr, s, m, st, steps, episode);
         } else {
             RawEnv<T, A> cur;
             load_raw<T, A>(a, i, cur);
-            decode_raw<T, A>(cur, s, m, st, steps, episode);
+            decode_raw<T, VARIANT>(cur, a.meta_hi != nullptr, s, m, st, steps, episode);
         }
         if (STATS && a.ep_return) ret = a.ep_return[i];
     } else {
@@ -218,12 +216,12 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
                 }
                 if (a.auto_reset) {
                     reset_state<T>(kp, s, st, steps);
-                    episode = (episode + 1) & 0x7FFFFu;
+                    episode = (episode + 1) & kp.ep_mask;
                 }
             }
         }
     } else {
-        // K substeps under one action: the summed reward telescopes (RewardRun, copter_physics.cuh)
+        // K substeps under one action: the summed reward telescopes (RewardRun, copter_core.h)
         RewardRun<T> run;
         run_begin<T, VARIANT>(kp, run, s);
         T na = (T)0, nc = (T)0, dz_prev = s[5]; int cause = 0;
@@ -237,6 +235,7 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
             // machine, no perturbation, one predicated region.  Anything else takes the general step.
             const bool hot = airborne_hot<T>(s, st, steps);
             const bool fast = COPTER_FAST_SUBSTEP && __all_sync(0xffffffffu, (int)!live | (int)hot);
+            bool dn = false;
             if (COPTER_CALM_STREAK && fast) {                           // warp-uniform
                 // Streak of straight-line substeps: as long as every live lane stays calm (airborne_calm:
                 // nothing ended, still in the common case) the next substep needs neither the ending flags
@@ -248,9 +247,9 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
                     if (live) {
                         dz_prev = s[5];
                         tmo = steps == kp.max_steps;
-                        airborne_arith<T>(kp, s, forces, na, nc);
+                        airborne_arith<T, T>(kp, s, forces, na, nc);
                         ++steps;
-                        calm = airborne_calm<T>(kp, s, tmo);
+                        calm = airborne_calm<T>(kp, s[0], s[2], s[4], s[5], s[6], s[8], s[10], tmo);
                         if (calm) { run.na += na; run.nc += nc; }
                     }
                     ++streak; ++k;
@@ -258,33 +257,22 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
                 --k;                                                   // the for statement counts the last one
                 if (live) {
                     run.steps += streak;
-                    steps = min(steps, 2047);
+                    steps = min(steps, kp.steps_cap);
                     int end = 0;
                     if (!calm) {                                       // back to the exact tests for this lane's last step
-                        end = airborne_flags<T>(kp, s, tmo);
+                        end = airborne_flags<T, VARIANT>(kp, s[0], s[2], s[6], s[8], tmo);
                         if (!(end & END_ANGLE)) { run.na += na; run.nc += nc; }
                     }
-                    if (end != 0) {
-                        cause = airborne_cause(end);
-                        live = false;
-                        ep_cause = cause;
-                        total = run_reward<T, VARIANT>(kp, run, s, cause, na, nc, dz_prev);
-                        if (STATS) ep_len = steps - 1;                 // `steps` is 1 right after reset (task.py:191,197)
-                        if (a.final_obs) {   // terminal observation; rows of unfinished envs stay untouched
-#pragma unroll
-                            for (int j = 0; j < O; ++j) a.final_obs[i * O + j] = (float)s[Variant<VARIANT>::first + j];
-                        }
-                        if (a.auto_reset) {
-                            reset_state<T>(kp, s, st, steps);
-                            episode = (episode + 1) & 0x7FFFFu;
-                        }
-                    }
+                    dn = end != 0;
+                    if (dn) cause = airborne_cause(end);
                 }
             } else if (live) {
                 dz_prev = s[5];
-                bool dn;
                 if (fast) {
-                    const int end = airborne_substep<T, VARIANT>(kp, s, steps, forces, na, nc);
+                    const bool tmo = steps == kp.max_steps;
+                    airborne_arith<T, T>(kp, s, forces, na, nc);
+                    steps = min(steps + 1, kp.steps_cap);
+                    const int end = airborne_flags<T, VARIANT>(kp, s[0], s[2], s[6], s[8], tmo);
                     ++run.steps;
                     if (!(end & END_ANGLE)) { run.na += na; run.nc += nc; }
                     dn = end != 0;
@@ -294,19 +282,19 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
                     pert[0] = (T)0; pert[1] = (T)0; pert[2] = (T)0;
                     run_step<T>(run, na, nc, cause);
                 }
-                if (dn) {
-                    live = false;
-                    ep_cause = cause;
-                    total = run_reward<T, VARIANT>(kp, run, s, cause, na, nc, dz_prev);
-                    if (STATS) ep_len = steps - 1;                     // `steps` is 1 right after reset (task.py:191,197)
-                    if (a.final_obs) {   // terminal observation; rows of unfinished envs stay untouched
+            }
+            if (dn) {                                                  // only a live lane can have ended
+                live = false;
+                ep_cause = cause;
+                total = run_reward<T, VARIANT>(kp, run, s, cause, na, nc, dz_prev);
+                if (STATS) ep_len = steps - 1;                         // `steps` is 1 right after reset (task.py:191,197)
+                if (a.final_obs) {   // terminal observation; rows of unfinished envs stay untouched
 #pragma unroll
-                        for (int j = 0; j < O; ++j) a.final_obs[i * O + j] = (float)s[Variant<VARIANT>::first + j];
-                    }
-                    if (a.auto_reset) {
-                        reset_state<T>(kp, s, st, steps);
-                        episode = (episode + 1) & 0x7FFFFu;
-                    }
+                    for (int j = 0; j < O; ++j) a.final_obs[i * O + j] = (float)s[Variant<VARIANT>::first + j];
+                }
+                if (a.auto_reset) {
+                    reset_state<T>(kp, s, st, steps);
+                    episode = (episode + 1) & kp.ep_mask;
                 }
             }
         }
@@ -322,7 +310,7 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
 
     if (valid) {
         store_state<T>(a.state, a.stride, i, s);
-        a.meta[i] = (uint32_t)st | ((uint32_t)steps << 2) | (episode << 13);
+        store_meta(a.meta, a.meta_hi, i, st, steps, episode);
         a.reward[i] = total;
         a.done[i] = done_any ? 1 : 0;
         if (a.cause) a.cause[i] = (uint8_t)ep_cause;
@@ -372,6 +360,210 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
+// K-fused launches on the fp32 path: TWO envs per thread, stepped together by the packed FP32 forms
+// of sm_100 (fma.rn.f32x2 / mul / add: SASS FFMA2, FMUL2, FADD2 -- two independent IEEE operations
+// per issue slot).  Launches with K >= 3 are bound by instruction issue, not by HBM (profiles/
+// r1_step_kernel_k16_*), and ~85 of the ~146 instructions of a straight-line substep are FP32
+// arithmetic: packing two envs halves their issue slots.  A lane holds env (base + lane) in the .x
+// halves and env (base + 32 + lane) in the .y halves of every quantity, so loads and stores stay
+// fully coalesced (a warp covers 64 consecutive envs).
+//   * While every live env of the warp is "calm" the substep is airborne_arith<F2>: the same
+//     airborne_integrate as the scalar kernels, instantiated on the packed lane -- bit-identical.
+//   * Anything else (first step of an episode, ground contact, large angles, an episode ending)
+//     drops to the scalar env_advance for the env concerned, exactly as copter_step_kernel does.
+//   * An env that finishes inside the launch idles afterwards.  Its half of the
+//     packed registers keeps being computed on (results unused); its final state waits in a
+//     per-thread shared-memory stash and is stored with everything else, coalesced, at the end.
+// ------------------------------------------------------------------------------------------
+#ifndef COPTER_PAIR_CTAS_PER_SM
+#define COPTER_PAIR_CTAS_PER_SM 4         // x 128 threads x 2 envs = 1024 resident envs per SM at <= 128 registers
+#endif
+
+__device__ __forceinline__ float lane_get(const F2& v, int e) { return e ? v.v.y : v.v.x; }
+__device__ __forceinline__ void lane_set(F2& v, int e, float x) { if (e) v.v.y = x; else v.v.x = x; }
+
+template <int VARIANT, bool STATS>
+__global__ void __launch_bounds__(kBlock, COPTER_PAIR_CTAS_PER_SM)
+copter_step_pair_kernel(const __grid_constant__ KParams<float> kp, const __grid_constant__ StepArgs<float> a) {
+    using T = float;
+    constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A, FIRST = Variant<VARIANT>::first;
+    __shared__ __align__(16) float tiles[kWarpsPerBlock][32 * O];
+    __shared__ float stash[2][12][kBlock];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (STATS) credit_env_steps(a.stats, a.n, a.k);
+    const int64_t base = (int64_t)blockIdx.x * (2 * kBlock) + warp * 64;     // first env of this warp
+    const bool wide = a.meta_hi != nullptr;
+
+    // Per-env registers are indexed by the half E in {0, 1}; every loop over E is fully unrolled, so E is a
+    // compile-time constant wherever it is used and nothing below lives in local memory.
+    F2 S[12];
+    Forces<T> fe[2];
+    T pert[2][3];
+    int st[2], steps[2], rsteps[2] = {0, 0}, ep_cause[2] = {0, 0}, ep_len[2] = {0, 0};
+    uint32_t episode[2];
+    bool valid[2], live[2], ended[2] = {false, false};
+    T total[2] = {(T)0, (T)0}, ret[2] = {(T)0, (T)0}, ep_ret[2] = {(T)0, (T)0};
+    Shaping<T> start[2];
+
+    RawEnv<T, A> raw[2];
+#pragma unroll
+    for (int E = 0; E < 2; ++E) {
+        const int64_t i = base + 32 * E + lane;
+        valid[E] = i < a.n;
+        if (valid[E]) load_raw<T, A>(a, i, raw[E]);
+    }
+#pragma unroll
+    for (int E = 0; E < 2; ++E) {
+        const int64_t i = base + 32 * E + lane;
+        T se[12], m[4] = {(T)0, (T)0, (T)0, (T)0};
+        st[E] = ST_LANDED; steps[E] = 1; episode[E] = 0;
+        if (valid[E]) {
+            decode_raw<T, VARIANT>(raw[E], wide, se, m, st[E], steps[E], episode[E]);
+            if (STATS && a.ep_return) ret[E] = a.ep_return[i];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) se[j] = (T)0;
+        }
+#pragma unroll
+        for (int j = 0; j < 12; ++j) lane_set(S[j], E, se[j]);
+        fe[E] = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);       // Eq. 6 once per launch (fp64 stage)
+        pert[E][0] = (T)0; pert[E][1] = (T)0; pert[E][2] = (T)0;
+        if (valid[E] && steps[E] == 1) {                            // the reset perturbation of a fresh episode
+            T f[3];
+            if (a.init_force) { f[0] = a.init_force[3 * i]; f[1] = a.init_force[3 * i + 1]; f[2] = a.init_force[3 * i + 2]; }
+            else reset_force<T>(kp, a.seed, (uint64_t)(a.env_offset + i), episode[E], f);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) pert[E][j] = f[j] * kp.invM;
+        }
+        RewardRun<T> r0;
+        run_begin<T, VARIANT>(kp, r0, se);
+        start[E] = r0.start;
+        live[E] = valid[E];
+    }
+    Forces<F2> F;
+    F.bz = F2(fe[0].bz, fe[1].bz); F.u2 = F2(fe[0].u2, fe[1].u2); F.u3 = F2(fe[0].u3, fe[1].u3);
+    F.u4 = F2(fe[0].u4, fe[1].u4); F.om = F2(fe[0].om, fe[1].om);
+
+    F2 RNA(0.0f), RNC(0.0f), NA(0.0f), NC(0.0f), DZP = S[5];
+    for (int k = 0; k < a.k; ++k) {
+        if (__all_sync(full, !(live[0] | live[1]))) break;             // every env of the warp has finished: idle
+        bool hot[2], dn[2] = {false, false};
+        int cause[2] = {0, 0};
+#pragma unroll
+        for (int E = 0; E < 2; ++E)
+            hot[E] = airborne_hot_c<T>(lane_get(S[4], E), lane_get(S[5], E), lane_get(S[6], E), lane_get(S[8], E), lane_get(S[10], E), st[E], steps[E]);
+        const bool fast = __all_sync(full, ((int)!live[0] | (int)hot[0]) & ((int)!live[1] | (int)hot[1]));
+        if (fast) {                                                     // warp-uniform
+            // calm streak (see step_tile): packed straight-line substeps until some live env of the warp
+            // needs the exact tests again
+            bool calm[2] = {true, true}, tmo[2] = {false, false};
+            int streak = 0;
+            F2 PNA, PNC;
+            do {
+                DZP = S[5];
+                tmo[0] = steps[0] == kp.max_steps; tmo[1] = steps[1] == kp.max_steps;
+                airborne_arith<F2, T>(kp, S, F, NA, NC);
+                steps[0] += (int)live[0]; steps[1] += (int)live[1];
+#pragma unroll
+                for (int E = 0; E < 2; ++E)
+                    calm[E] = (int)!live[E] | (int)airborne_calm<T>(kp, lane_get(S[0], E), lane_get(S[2], E), lane_get(S[4], E), lane_get(S[5], E),
+                                                                    lane_get(S[6], E), lane_get(S[8], E), lane_get(S[10], E), tmo[E]);
+                PNA = RNA; PNC = RNC;                                   // an over-angle ending takes its own numerators back
+                RNA = RNA + NA; RNC = RNC + NC;
+                ++streak; ++k;
+            } while (k < a.k && __all_sync(full, (int)calm[0] & (int)calm[1]));
+            --k;                                                        // the for statement counts the last one
+#pragma unroll
+            for (int E = 0; E < 2; ++E) {
+                if (live[E]) {
+                    rsteps[E] += streak;
+                    steps[E] = min(steps[E], kp.steps_cap);
+                    int end = 0;
+                    if (!calm[E]) {                                     // back to the exact tests for this env's last step
+                        end = airborne_flags<T, VARIANT>(kp, lane_get(S[0], E), lane_get(S[2], E), lane_get(S[6], E), lane_get(S[8], E), tmo[E]);
+                        if (end & END_ANGLE) { lane_set(RNA, E, lane_get(PNA, E)); lane_set(RNC, E, lane_get(PNC, E)); }
+                    }
+                    dn[E] = end != 0;
+                    if (dn[E]) cause[E] = airborne_cause(end);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int E = 0; E < 2; ++E) {
+                if (live[E]) {
+                    T se[12], na, nc;
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) se[j] = lane_get(S[j], E);
+                    lane_set(DZP, E, se[5]);
+                    env_advance<T, VARIANT>(kp, se, st[E], steps[E], fe[E], pert[E], na, nc, dn[E], cause[E]);
+                    pert[E][0] = (T)0; pert[E][1] = (T)0; pert[E][2] = (T)0;
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) lane_set(S[j], E, se[j]);
+                    lane_set(NA, E, na); lane_set(NC, E, nc);
+                    ++rsteps[E];
+                    if (!(cause[E] & CAUSE_ANGLE)) { lane_set(RNA, E, lane_get(RNA, E) + na); lane_set(RNC, E, lane_get(RNC, E) + nc); }
+                }
+            }
+        }
+#pragma unroll
+        for (int E = 0; E < 2; ++E) {
+            if (dn[E]) {                                                // only a live env can have ended
+                T se[12];
+#pragma unroll
+                for (int j = 0; j < 12; ++j) se[j] = lane_get(S[j], E);
+                live[E] = false; ended[E] = true; ep_cause[E] = cause[E];
+                RewardRun<T> run;
+                run.start = start[E]; run.na = lane_get(RNA, E); run.nc = lane_get(RNC, E); run.steps = rsteps[E];
+                total[E] = run_reward<T, VARIANT>(kp, run, se, cause[E], lane_get(NA, E), lane_get(NC, E), lane_get(DZP, E));
+                if (STATS) ep_len[E] = steps[E] - 1;                    // `steps` is 1 right after reset (task.py:191,197)
+                if (a.final_obs) {   // terminal observation; rows of unfinished envs stay untouched
+                    const int64_t i = base + 32 * E + lane;
+#pragma unroll
+                    for (int j = 0; j < O; ++j) a.final_obs[i * O + j] = (float)se[FIRST + j];
+                }
+                if (a.auto_reset) {
+                    reset_state<T>(kp, se, st[E], steps[E]);
+                    episode[E] = (episode[E] + 1) & kp.ep_mask;
+                }
+#pragma unroll
+                for (int j = 0; j < 12; ++j) stash[E][j][threadIdx.x] = se[j];
+            }
+        }
+    }
+
+#pragma unroll
+    for (int E = 0; E < 2; ++E) {
+        const int64_t row0 = base + 32 * E, i = row0 + lane;
+        const int64_t left = a.n - row0;
+        const int rows = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+        T se[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) se[j] = ended[E] ? stash[E][j][threadIdx.x] : lane_get(S[j], E);
+        if (valid[E]) {
+            if (!ended[E]) {
+                RewardRun<T> run;
+                run.start = start[E]; run.na = lane_get(RNA, E); run.nc = lane_get(RNC, E); run.steps = rsteps[E];
+                total[E] = run_reward<T, VARIANT>(kp, run, se, 0, lane_get(NA, E), lane_get(NC, E), lane_get(DZP, E));
+            }
+            if (STATS) {
+                ret[E] += total[E];
+                if (ended[E]) { ep_ret[E] = ret[E]; ret[E] = (T)0; }
+            }
+            store_state<T>(a.state, a.stride, i, se);
+            store_meta(a.meta, a.meta_hi, i, st[E], steps[E], episode[E]);
+            a.reward[i] = total[E];
+            a.done[i] = ended[E] ? 1 : 0;
+            if (a.cause) a.cause[i] = (uint8_t)ep_cause[E];
+            if (STATS && a.ep_return) a.ep_return[i] = ret[E];
+        }
+        if (a.obs) write_obs_rows<VARIANT, T>(a.obs, tiles[warp], lane, row0, rows, se);
+        if (STATS) flush_episode_stats<T>(a.stats, lane, ended[E], ep_cause[E], ep_len[E], ep_ret[E], a.ep_return != nullptr);
+    }
+    if (STATS) debit_idle_steps(a.stats, lane, (valid[0] ? a.k - rsteps[0] : 0) + (valid[1] ? a.k - rsteps[1] : 0));
+}
+
+// ------------------------------------------------------------------------------------------
 // A/B shape (compiled in with -DCOPTER_TMA_MIN_K=1|2, off by default): persistent CTAs that fetch
 // their NEXT tile's inputs with the TMA engine (cp.async.bulk 1-D: three 2 KB state planes, the
 // action rows and the meta words of 128 envs per stage, two stages, one full/empty mbarrier pair
@@ -396,6 +588,7 @@ copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant_
 #define COPTER_TMA_CTAS_PER_SM COPTER_F32_CTAS_PER_SM     // fp32 occupancy target of that kernel (A/B knob)
 #endif
 
+#if COPTER_TMA_MIN_K > 0
 template <typename T, int A> struct alignas(128) TileStage {     // one tile (kBlock envs) of inputs, laid out as in HBM
     typename Vec<T>::type plane[12 / Vec<T>::V][kBlock];
     T act[kBlock * A];
@@ -535,6 +728,7 @@ copter_step_tma_kernel(const __grid_constant__ KParams<T> kp, const __grid_const
 #pragma unroll
             for (int j = 0; j < A; ++j) cur.act[j] = src.act[threadIdx.x * A + j];
             cur.meta = src.meta[threadIdx.x];
+            cur.meta_hi = a.meta_hi ? a.meta_hi[(int64_t)tile * kBlock + threadIdx.x] : 0u;
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[st]);
         } else if (row0 + lane < a.n) {
@@ -546,6 +740,8 @@ copter_step_tma_kernel(const __grid_constant__ KParams<T> kp, const __grid_const
     }
 }
 
+#endif  // COPTER_TMA_MIN_K > 0
+
 // ------------------------------------------------------------------------------------------
 // Multi-step rollout with on-device action sources: n_steps reference steps per launch, the
 // env state in registers throughout, the motor commands drawn on the device (no action tensor
@@ -554,7 +750,7 @@ copter_step_tma_kernel(const __grid_constant__ KParams<T> kp, const __grid_const
 // ------------------------------------------------------------------------------------------
 template <typename T>
 struct RolloutArgs {
-    T* state; uint32_t* meta; float* obs; T* reward_sum; uint8_t* done_any;
+    T* state; uint32_t* meta; uint32_t* meta_hi; float* obs; T* reward_sum; uint8_t* done_any;
     const T* init_force; T* ep_return; double* stats;
     T* reward_tn; uint8_t* done_tn; T* action_tn;
     int64_t n, stride, env_offset, first_step; uint64_t seed;
@@ -607,7 +803,7 @@ __device__ __forceinline__ void draw_variates(uint64_t seed, uint64_t env, uint6
                 const T u2 = (T)((double)c[2 * h + 1] * 0x1p-32);
                 const T r = sqrt_t((T)-2 * log_t(u1));
                 T sn, cs;
-                sincos_t((T)6.283185307179586 * u2, &sn, &cs);
+                sincos_t((T)6.283185307179586 * u2, sn, cs);
                 xi[2 * h] = r * cs; xi[2 * h + 1] = r * sn;
             }
         }
@@ -739,8 +935,7 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
         T total = (T)0, ret = (T)0; bool done_any = false;
         if (valid) {
             load_state<T>(a.state, a.stride, i, s);
-            const uint32_t mw = a.meta[i];
-            st = (int)(mw & 3u); steps = (int)((mw >> 2) & 2047u); episode = mw >> 13;
+            decode_meta(a.meta[i], a.meta_hi, i, st, steps, episode);
             if (STATS && a.ep_return) ret = a.ep_return[i];
         } else {
 #pragma unroll
@@ -776,11 +971,7 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < A; ++j) a.action_tn[((int64_t)t * a.n + i) * A + j] = act[j];
                 }
-#pragma unroll
-                for (int j = 0; j < A; ++j) act[j] = fmin(fmax(act[j], (T)0), (T)1);         // task.py:91
-                if constexpr (A == 4) { m[0] = act[0]; m[1] = act[1]; m[2] = act[2]; m[3] = act[3]; }
-                else if constexpr (A == 2) { m[0] = act[0]; m[1] = act[1]; m[2] = act[1]; m[3] = act[0]; }
-                else { m[0] = m[1] = m[2] = m[3] = act[0]; }
+                motors_from_action<T, VARIANT>(act, m);                                     // task.py:91 + _get_motors
                 const Forces<T> forces = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
                 T pert[3] = {(T)0, (T)0, (T)0};
                 if (steps == 1) {
@@ -812,7 +1003,7 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
                     if (STATS) { ep_len = steps - 1; ep_ret = ret; ret = (T)0; }
                     if (a.auto_reset) {
                         reset_state<T>(kp, s, st, steps);
-                        episode = (episode + 1) & 0x7FFFFu;
+                        episode = (episode + 1) & kp.ep_mask;
                         pre_sh = lander_shaping<T>(kp, s);
                     }
                     run_begin<T, VARIANT>(kp, run, s);
@@ -827,7 +1018,7 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
         }
         if (valid) {
             store_state<T>(a.state, a.stride, i, s);
-            a.meta[i] = (uint32_t)st | ((uint32_t)steps << 2) | (episode << 13);
+            store_meta(a.meta, a.meta_hi, i, st, steps, episode);
             if (a.reward_sum) a.reward_sum[i] = total;
             if (a.done_any) a.done_any[i] = done_any ? 1 : 0;
             if (STATS && a.ep_return) a.ep_return[i] = ret;
@@ -850,7 +1041,7 @@ copter_rollout_kernel(const __grid_constant__ KParams<T> kp, const __grid_consta
 // copter_policy_mlp_f32 followed by copter_step_f32 (k = 1), n_steps times.
 // ------------------------------------------------------------------------------------------
 struct PolicyRolloutArgs {
-    float* state; uint32_t* meta; float* obs; float* reward_sum; uint8_t* done_any;
+    float* state; uint32_t* meta; uint32_t* meta_hi; float* obs; float* reward_sum; uint8_t* done_any;
     const float* init_force; float* ep_return; double* stats;
     float* reward_tn; uint8_t* done_tn; float* action_tn; float* obs_tn;
     int64_t n, stride, env_offset, first_step; uint64_t seed; int n_steps, auto_reset;
@@ -887,8 +1078,7 @@ copter_policy_rollout_kernel(const __grid_constant__ KParams<float> kp, const __
         T total = (T)0, ret = (T)0; bool done_any = false;
         if (valid) {
             load_state<T>(a.state, a.stride, i, s);
-            const uint32_t mw = a.meta[i];
-            st = (int)(mw & 3u); steps = (int)((mw >> 2) & 2047u); episode = mw >> 13;
+            decode_meta(a.meta[i], a.meta_hi, i, st, steps, episode);
             if (STATS && a.ep_return) ret = a.ep_return[i];
         } else {
 #pragma unroll
@@ -915,11 +1105,7 @@ copter_policy_rollout_kernel(const __grid_constant__ KParams<float> kp, const __
                     else if constexpr (A == 2) *reinterpret_cast<float2*>(row) = make_float2(act[0], act[1]);
                     else row[0] = act[0];
                 }
-#pragma unroll
-                for (int j = 0; j < A; ++j) act[j] = fmin(fmax(act[j], (T)0), (T)1);         // task.py:91
-                if constexpr (A == 4) { m[0] = act[0]; m[1] = act[1]; m[2] = act[2]; m[3] = act[3]; }
-                else if constexpr (A == 2) { m[0] = act[0]; m[1] = act[1]; m[2] = act[1]; m[3] = act[0]; }
-                else { m[0] = m[1] = m[2] = m[3] = act[0]; }
+                motors_from_action<T, VARIANT>(act, m);                                     // task.py:91 + _get_motors
                 const Forces<T> forces = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
                 T pert[3] = {(T)0, (T)0, (T)0};
                 if (steps == 1) {
@@ -940,7 +1126,7 @@ copter_policy_rollout_kernel(const __grid_constant__ KParams<float> kp, const __
                     if (STATS) { ep_len = steps - 1; ep_ret = ret; ret = (T)0; }
                     if (a.auto_reset) {
                         reset_state<T>(kp, s, st, steps);
-                        episode = (episode + 1) & 0x7FFFFu;
+                        episode = (episode + 1) & kp.ep_mask;
                         pre_sh = lander_shaping<T>(kp, s);
                     }
                 }
@@ -949,7 +1135,7 @@ copter_policy_rollout_kernel(const __grid_constant__ KParams<float> kp, const __
         }
         if (valid) {
             store_state<T>(a.state, a.stride, i, s);
-            a.meta[i] = (uint32_t)st | ((uint32_t)steps << 2) | (episode << 13);
+            store_meta(a.meta, a.meta_hi, i, st, steps, episode);
             if (a.reward_sum) a.reward_sum[i] = total;
             if (a.done_any) a.done_any[i] = done_any ? 1 : 0;
             if (STATS && a.ep_return) a.ep_return[i] = ret;
@@ -960,7 +1146,8 @@ copter_policy_rollout_kernel(const __grid_constant__ KParams<float> kp, const __
 
 template <typename T, int VARIANT>
 __global__ void __launch_bounds__(kBlock)
-copter_reset_kernel(const __grid_constant__ KParams<T> kp, T* state, uint32_t* meta, float* obs, T* ep_return, int64_t n, int64_t stride) {
+copter_reset_kernel(const __grid_constant__ KParams<T> kp, T* state, uint32_t* meta, uint32_t* meta_hi, float* obs, T* ep_return,
+                    int64_t n, int64_t stride, int keep_episode) {
     constexpr int O = Variant<VARIANT>::O;
     __shared__ __align__(16) float tiles[kWarpsPerBlock][32 * O];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -972,7 +1159,15 @@ copter_reset_kernel(const __grid_constant__ KParams<T> kp, T* state, uint32_t* m
         reset_state<T>(kp, s, st, steps);
         if (i < n) {
             store_state<T>(state, stride, i, s);
-            meta[i] = (uint32_t)st | ((uint32_t)steps << 2);
+            // COPTER_F_KEEP_EPISODE: the env's next episode index, so that a reset() per episode draws a new
+            // reset force every time (the reference draws fresh np.random.uniform forces, task.py:175-184)
+            uint32_t episode = 0;
+            if (keep_episode) {
+                int st_old, steps_old;
+                decode_meta(meta[i], meta_hi, i, st_old, steps_old, episode);
+                episode = (episode + 1) & kp.ep_mask;
+            }
+            store_meta(meta, meta_hi, i, st, steps, episode);
             if (ep_return) ep_return[i] = (T)0;
         }
         if (obs) write_obs_rows<VARIANT, T>(obs, tiles[warp], lane, row0, rows, s);
@@ -1019,14 +1214,34 @@ copter_reset_force_kernel(const __grid_constant__ KParams<T> kp, T* out, const u
 // ------------------------------------------------------------------------------------------
 // host-side launch helpers
 // ------------------------------------------------------------------------------------------
+// Per-device caches (the library is re-entrant and the caller selects the device: nothing here may be
+// remembered across devices).  Benign races: every thread that fills a slot writes the same value.
+constexpr int kMaxDevices = 64;
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return dev;
+}
 int sm_count() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-            sms = 148;
+    static int sms[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (sms[dev] == 0) {
+        int q = 0;
+        if (cudaDeviceGetAttribute(&q, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || q <= 0) q = 148;
+        sms[dev] = q;
     }
-    return sms;
+    return sms[dev];
+}
+template <auto Kernel>
+int ctas_per_sm(int block) {
+    static int per_sm[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (per_sm[dev] == 0) {
+        int q = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, Kernel, block, 0) != cudaSuccess || q <= 0) q = 4;
+        per_sm[dev] = q;
+    }
+    return per_sm[dev];
 }
 
 // Grid: one CTA per tile of kBlock envs, scheduled by the hardware as CTAs retire.  Measured on
@@ -1038,14 +1253,8 @@ int sm_count() {
 // the sweep.)  The kernels keep their tile loop, so a grid capped at 2^31-1 CTAs still covers any n.
 template <auto Kernel>
 int grid_for(int64_t n) {
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        int q = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, Kernel, kBlock, 0) != cudaSuccess || q <= 0) q = 4;
-        per_sm = q;
-    }
     const int64_t tiles = (n + kBlock - 1) / kBlock;
-    const int64_t cap = COPTER_PERSISTENT ? (int64_t)sm_count() * per_sm : (int64_t)0x7fffffff;
+    const int64_t cap = COPTER_PERSISTENT ? (int64_t)sm_count() * ctas_per_sm<Kernel>(kBlock) : (int64_t)0x7fffffff;
     return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 // the step kernel's shipped shape has no tile loop: every tile needs its own CTA
@@ -1053,9 +1262,9 @@ constexpr int64_t kMaxEnvsPerLaunch = COPTER_PERSISTENT ? INT64_MAX : (int64_t)0
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-int check_params(const CopterParams* p) {
+int check_params(const CopterParams* p, bool wide = false) {
     if (!p) return COPTER_E_ARG;
-    if (p->max_steps < 1 || p->max_steps > COPTER_MAX_STEPS_LIMIT) return COPTER_E_RANGE;
+    if (p->max_steps < 1 || p->max_steps > (wide ? COPTER_MAX_STEPS_LIMIT_WIDE : COPTER_MAX_STEPS_LIMIT)) return COPTER_E_RANGE;
     if (!(p->M > 0) || !(p->Ix > 0) || !(p->Iy > 0) || !(p->Iz > 0) || !(p->fps > 0)) return COPTER_E_RANGE;
     return 0;
 }
@@ -1063,13 +1272,7 @@ int check_params(const CopterParams* p) {
 // resident-wave grid for the persistent-warp kernels
 template <auto Kernel>
 int resident_grid_for(int64_t n) {
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        int q = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, Kernel, kBlock, 0) != cudaSuccess || q <= 0) q = 4;
-        per_sm = q;
-    }
-    const int64_t tiles = (n + kBlock - 1) / kBlock, cap = (int64_t)sm_count() * per_sm;
+    const int64_t tiles = (n + kBlock - 1) / kBlock, cap = (int64_t)sm_count() * ctas_per_sm<Kernel>(kBlock);
     return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 
@@ -1077,7 +1280,8 @@ template <typename T, int VARIANT>
 int launch_step_v(const KParams<T>& kp, const StepArgs<T>& a, cudaStream_t s) {
     // K-fused launches: TMA-prefetched inputs (every bulk copy needs 16-byte aligned sources; the
     // state planes and the action rows are checked by the caller, the meta words here)
-    if (COPTER_TMA_MIN_K > 0 && a.k >= COPTER_TMA_MIN_K && aligned16(a.meta) && a.n <= (int64_t)0x7fffffff * kBlock) {
+#if COPTER_TMA_MIN_K > 0
+    if (a.k >= COPTER_TMA_MIN_K && aligned16(a.meta) && a.n <= (int64_t)0x7fffffff * kBlock) {
         constexpr bool kSingle = COPTER_TMA_MIN_K == 1 && COPTER_K1_SPECIALIZE;      // only an A/B build sends K = 1 here
         // cluster launch control: the grid holds one CTA per tile and the resident CTAs steal the rest
         const int64_t n_tiles = (a.n + kBlock - 1) / kBlock;
@@ -1092,6 +1296,14 @@ int launch_step_v(const KParams<T>& kp, const StepArgs<T>& a, cudaStream_t s) {
 #undef COPTER_TMA_GRID
         return (int)cudaGetLastError();
     }
+#endif
+    // issue-bound K-fused fp32 launches: two envs per thread on packed fma.rn.f32x2 (copter_step_pair_kernel)
+    if constexpr (COPTER_PAIR_MIN_K > 0 && sizeof(T) == 4) if (a.k >= COPTER_PAIR_MIN_K) {
+        const int grid = (int)((a.n + 2 * kBlock - 1) / (2 * kBlock));
+        if (a.stats) copter_step_pair_kernel<VARIANT, true><<<grid, kBlock, 0, s>>>(kp, a);
+        else         copter_step_pair_kernel<VARIANT, false><<<grid, kBlock, 0, s>>>(kp, a);
+        return (int)cudaGetLastError();
+    }
     if (a.stats) copter_step_kernel<T, VARIANT, true><<<grid_for<copter_step_kernel<T, VARIANT, true>>(a.n), kBlock, 0, s>>>(kp, a);
     else         copter_step_kernel<T, VARIANT, false><<<grid_for<copter_step_kernel<T, VARIANT, false>>(a.n), kBlock, 0, s>>>(kp, a);
     return (int)cudaGetLastError();
@@ -1100,16 +1312,17 @@ int launch_step_v(const KParams<T>& kp, const StepArgs<T>& a, cudaStream_t s) {
 template <typename T>
 int launch_step(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_t env_offset, uint64_t seed,
                 int k, int variant, int flags, void* stream) {
-    int e = check_params(p);
+    if (!b) return COPTER_E_ARG;
+    int e = check_params(p, b->meta_hi != nullptr);
     if (e) return e;
-    if (!b || !b->state || !b->meta || !b->action || !b->reward || !b->done) return COPTER_E_ARG;
+    if (!b->state || !b->meta || !b->action || !b->reward || !b->done) return COPTER_E_ARG;
     if (n < 0 || n > kMaxEnvsPerLaunch || env_offset < 0 || k < 1 || (b->state_stride > 0 && b->state_stride < n)) return COPTER_E_RANGE;
     if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
     if (!aligned16(b->state) || !aligned16(b->action) || (b->obs && !aligned16(b->obs))) return COPTER_E_ALIGN;
     if (n == 0) return 0;
-    const KParams<T> kp = make_kparams<T>(*p);
+    const KParams<T> kp = make_kparams<T>(*p, b->meta_hi != nullptr);
     StepArgs<T> a;
-    a.state = (T*)b->state; a.meta = b->meta; a.action = (const T*)b->action; a.obs = b->obs;
+    a.state = (T*)b->state; a.meta = b->meta; a.meta_hi = b->meta_hi; a.action = (const T*)b->action; a.obs = b->obs;
     a.reward = (T*)b->reward; a.done = b->done; a.init_force = (const T*)b->init_force;
     a.ep_return = (T*)b->ep_return; a.stats = b->stats; a.final_obs = b->final_obs; a.cause = b->cause;
     a.n = n; a.stride = b->state_stride > 0 ? b->state_stride : n; a.env_offset = env_offset; a.seed = seed; a.k = k; a.auto_reset = (flags & COPTER_F_AUTO_RESET) ? 1 : 0;
@@ -1120,7 +1333,8 @@ int launch_step(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_
         case COPTER_LANDER1D: return launch_step_v<T, COPTER_LANDER1D>(kp, a, s);
         case COPTER_HOVER3D:  return launch_step_v<T, COPTER_HOVER3D>(kp, a, s);
         case COPTER_HOVER2D:  return launch_step_v<T, COPTER_HOVER2D>(kp, a, s);
-        default:              return launch_step_v<T, COPTER_HOVER1D>(kp, a, s);
+        case COPTER_HOVER1D:  return launch_step_v<T, COPTER_HOVER1D>(kp, a, s);
+        default:              return launch_step_v<T, COPTER_TAKEOFF>(kp, a, s);
     }
 }
 
@@ -1148,18 +1362,19 @@ int launch_rollout(const CopterParams* p, const CopterBuffers* b, const CopterAc
                    int64_t env_offset, uint64_t seed, int64_t first_step, int n_steps, int variant, int flags,
                    void* reward_tn, uint8_t* done_tn, void* action_tn, const CopterPidGains* gains, void* controller,
                    void* stream) {
-    int e = check_params(p);
+    if (!b) return COPTER_E_ARG;
+    int e = check_params(p, b->meta_hi != nullptr);
     if (e) return e;
-    if (!b || !b->state || !b->meta || !src) return COPTER_E_ARG;
+    if (!b->state || !b->meta || !src) return COPTER_E_ARG;
     if ((src->kind == COPTER_SRC_PID || src->kind == COPTER_SRC_PID_HOVER) && (!controller || !aligned16(controller))) return COPTER_E_ARG;
     if (n < 0 || env_offset < 0 || n_steps < 1 || first_step < 0 || (b->state_stride > 0 && b->state_stride < n)) return COPTER_E_RANGE;
     if (src->kind < COPTER_SRC_CONST || src->kind > COPTER_SRC_PID_HOVER) return COPTER_E_RANGE;
     if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
     if (!aligned16(b->state) || (b->obs && !aligned16(b->obs))) return COPTER_E_ALIGN;
     if (n == 0) return 0;
-    const KParams<T> kp = make_kparams<T>(*p);
+    const KParams<T> kp = make_kparams<T>(*p, b->meta_hi != nullptr);
     RolloutArgs<T> a;
-    a.state = (T*)b->state; a.meta = b->meta; a.obs = b->obs; a.reward_sum = (T*)b->reward; a.done_any = b->done;
+    a.state = (T*)b->state; a.meta = b->meta; a.meta_hi = b->meta_hi; a.obs = b->obs; a.reward_sum = (T*)b->reward; a.done_any = b->done;
     a.init_force = (const T*)b->init_force; a.ep_return = (T*)b->ep_return; a.stats = b->stats;
     a.reward_tn = (T*)reward_tn; a.done_tn = done_tn; a.action_tn = (T*)action_tn;
     a.n = n; a.stride = b->state_stride > 0 ? b->state_stride : n; a.env_offset = env_offset; a.first_step = first_step;
@@ -1179,34 +1394,38 @@ int launch_rollout(const CopterParams* p, const CopterBuffers* b, const CopterAc
         case COPTER_LANDER1D: return launch_rollout_v<T, COPTER_LANDER1D>(kp, a, s);
         case COPTER_HOVER3D:  return launch_rollout_v<T, COPTER_HOVER3D>(kp, a, s);
         case COPTER_HOVER2D:  return launch_rollout_v<T, COPTER_HOVER2D>(kp, a, s);
-        default:              return launch_rollout_v<T, COPTER_HOVER1D>(kp, a, s);
+        case COPTER_HOVER1D:  return launch_rollout_v<T, COPTER_HOVER1D>(kp, a, s);
+        default:              return launch_rollout_v<T, COPTER_TAKEOFF>(kp, a, s);
     }
 }
 
 template <typename T, int VARIANT>
-int launch_reset_v(const KParams<T>& kp, const CopterBuffers* b, int64_t n, cudaStream_t s) {
-    copter_reset_kernel<T, VARIANT><<<grid_for<copter_reset_kernel<T, VARIANT>>(n), kBlock, 0, s>>>(kp, (T*)b->state, b->meta, b->obs, (T*)b->ep_return, n, b->state_stride > 0 ? b->state_stride : n);
+int launch_reset_v(const KParams<T>& kp, const CopterBuffers* b, int64_t n, int keep_episode, cudaStream_t s) {
+    copter_reset_kernel<T, VARIANT><<<grid_for<copter_reset_kernel<T, VARIANT>>(n), kBlock, 0, s>>>(kp, (T*)b->state, b->meta, b->meta_hi, b->obs, (T*)b->ep_return, n, b->state_stride > 0 ? b->state_stride : n, keep_episode);
     return (int)cudaGetLastError();
 }
 
 template <typename T>
-int launch_reset(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, void* stream) {
-    int e = check_params(p);
+int launch_reset(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, int flags, void* stream) {
+    if (!b) return COPTER_E_ARG;
+    int e = check_params(p, b->meta_hi != nullptr);
     if (e) return e;
-    if (!b || !b->state || !b->meta) return COPTER_E_ARG;
+    if (!b->state || !b->meta) return COPTER_E_ARG;
     if (n < 0 || (b->state_stride > 0 && b->state_stride < n)) return COPTER_E_RANGE;
     if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
     if (!aligned16(b->state) || (b->obs && !aligned16(b->obs))) return COPTER_E_ALIGN;
     if (n == 0) return 0;
-    const KParams<T> kp = make_kparams<T>(*p);
+    const KParams<T> kp = make_kparams<T>(*p, b->meta_hi != nullptr);
+    const int keep = (flags & COPTER_F_KEEP_EPISODE) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     switch (variant) {
-        case COPTER_LANDER3D: return launch_reset_v<T, COPTER_LANDER3D>(kp, b, n, s);
-        case COPTER_LANDER2D: return launch_reset_v<T, COPTER_LANDER2D>(kp, b, n, s);
-        case COPTER_LANDER1D: return launch_reset_v<T, COPTER_LANDER1D>(kp, b, n, s);
-        case COPTER_HOVER3D:  return launch_reset_v<T, COPTER_HOVER3D>(kp, b, n, s);
-        case COPTER_HOVER2D:  return launch_reset_v<T, COPTER_HOVER2D>(kp, b, n, s);
-        default:              return launch_reset_v<T, COPTER_HOVER1D>(kp, b, n, s);
+        case COPTER_LANDER3D: return launch_reset_v<T, COPTER_LANDER3D>(kp, b, n, keep, s);
+        case COPTER_LANDER2D: return launch_reset_v<T, COPTER_LANDER2D>(kp, b, n, keep, s);
+        case COPTER_LANDER1D: return launch_reset_v<T, COPTER_LANDER1D>(kp, b, n, keep, s);
+        case COPTER_HOVER3D:  return launch_reset_v<T, COPTER_HOVER3D>(kp, b, n, keep, s);
+        case COPTER_HOVER2D:  return launch_reset_v<T, COPTER_HOVER2D>(kp, b, n, keep, s);
+        case COPTER_HOVER1D:  return launch_reset_v<T, COPTER_HOVER1D>(kp, b, n, keep, s);
+        default:              return launch_reset_v<T, COPTER_TAKEOFF>(kp, b, n, keep, s);
     }
 }
 
@@ -1240,13 +1459,7 @@ int launch_reset_force(const CopterParams* p, T* out, const uint32_t* episode, i
 // persistent grids for the policy kernels: the weights are converted to bf16 fragments once per CTA
 template <auto Kernel>
 int persistent_grid_for(int64_t n) {
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        int q = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, Kernel, 128, 0) != cudaSuccess || q <= 0) q = 4;
-        per_sm = q;
-    }
-    const int64_t tiles = (n + 127) / 128, cap = (int64_t)sm_count() * per_sm;
+    const int64_t tiles = (n + 127) / 128, cap = (int64_t)sm_count() * ctas_per_sm<Kernel>(128);
     return (int)(tiles < cap ? tiles : cap);
 }
 
@@ -1278,14 +1491,14 @@ PolicyWeights policy_weights(const CopterMlpPolicy* m) {
 // host-buffer pipeline: the step for callers that hold numpy-style HOST arrays
 // ------------------------------------------------------------------------------------------
 struct Pipeline {
-    int n_streams;
+    int n_streams, device;
     cudaStream_t streams[8];
     cudaEvent_t start, done[8];
 };
 
 template <typename T>
 int step_host(Pipeline* pl, const CopterParams* p, const CopterBuffers* dev, const void* h_action, float* h_obs,
-              void* h_reward, uint8_t* h_done, int64_t n, int64_t env_offset, uint64_t seed, int k, int variant,
+              void* h_reward, uint8_t* h_done, uint8_t* h_cause, float* h_final_obs, int64_t n, int64_t env_offset, uint64_t seed, int k, int variant,
               int flags, int64_t chunk, void* caller_stream) {
     if (!pl || !dev || !h_action || !h_reward || !h_done || !dev->action) return COPTER_E_ARG;
     if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
@@ -1306,6 +1519,7 @@ int step_host(Pipeline* pl, const CopterParams* p, const CopterBuffers* dev, con
         b.state = (T*)dev->state + lo * V;               // same planes, shifted by `lo` vectors
         b.state_stride = stride;
         b.meta = dev->meta + lo;
+        b.meta_hi = dev->meta_hi ? dev->meta_hi + lo : nullptr;
         b.action = (const T*)dev->action + lo * A;
         b.obs = dev->obs ? dev->obs + lo * O : nullptr;
         b.reward = (T*)dev->reward + lo;
@@ -1320,6 +1534,8 @@ int step_host(Pipeline* pl, const CopterParams* p, const CopterBuffers* dev, con
         if (h_obs && b.obs && (ce = cudaMemcpyAsync(h_obs + lo * O, b.obs, sizeof(float) * m * O, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)ce;
         if ((ce = cudaMemcpyAsync((T*)h_reward + lo, b.reward, sizeof(T) * m, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)ce;
         if ((ce = cudaMemcpyAsync(h_done + lo, b.done, m, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)ce;
+        if (h_cause && b.cause && (ce = cudaMemcpyAsync(h_cause + lo, b.cause, m, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)ce;
+        if (h_final_obs && b.final_obs && (ce = cudaMemcpyAsync(h_final_obs + lo * O, b.final_obs, sizeof(float) * m * O, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return (int)ce;
     }
     for (int s = 0; s < pl->n_streams; ++s) {
         if ((ce = cudaEventRecord(pl->done[s], pl->streams[s])) != cudaSuccess) return (int)ce;
@@ -1349,21 +1565,22 @@ void copter_default_params(CopterParams* p) {
     p->target_radius = 2; p->yaw_penalty_factor = 50; p->xyz_penalty_factor = 25;                  // lander.py:17-23
     p->dz_max = 10; p->dz_penalty = 100; p->inside_radius_bonus = 100;
     p->rho = 1.225; p->lift_coefficient = 0.4;      // attic/mars/dynamics/__init__.py:83-84, ingenuity.py:55
+    p->takeoff_target_altitude = 5;                 // attic/gym_copter/envs/takeoff.py:20
     p->dynamics_model = 0;
 }
 
 int copter_obs_size(int variant) {
-    static const int o[COPTER_NUM_VARIANTS] = {10, 6, 2, 12, 6, 2};
+    static const int o[COPTER_NUM_VARIANTS] = {10, 6, 2, 12, 6, 2, 10};
     return (variant < 0 || variant >= COPTER_NUM_VARIANTS) ? COPTER_E_VARIANT : o[variant];
 }
 
 int copter_action_size(int variant) {
-    static const int a[COPTER_NUM_VARIANTS] = {4, 2, 1, 4, 2, 1};
+    static const int a[COPTER_NUM_VARIANTS] = {4, 2, 1, 4, 2, 1, 4};
     return (variant < 0 || variant >= COPTER_NUM_VARIANTS) ? COPTER_E_VARIANT : a[variant];
 }
 
-int copter_reset_f32(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, void* stream) { return launch_reset<float>(p, b, n, variant, stream); }
-int copter_reset_f64(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, void* stream) { return launch_reset<double>(p, b, n, variant, stream); }
+int copter_reset_f32(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, int flags, void* stream) { return launch_reset<float>(p, b, n, variant, flags, stream); }
+int copter_reset_f64(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, int flags, void* stream) { return launch_reset<double>(p, b, n, variant, flags, stream); }
 
 int copter_step_f32(const CopterParams* p, const CopterBuffers* b, int64_t n, int64_t env_offset, uint64_t seed, int k, int variant, int flags, void* stream) {
     return launch_step<float>(p, b, n, env_offset, seed, k, variant, flags, stream);
@@ -1425,23 +1642,25 @@ int copter_policy_mlp_f32(const void* state, int64_t state_stride, int64_t n, in
         case COPTER_LANDER1D: return launch_policy_v<COPTER_LANDER1D>(a, s);
         case COPTER_HOVER3D:  return launch_policy_v<COPTER_HOVER3D>(a, s);
         case COPTER_HOVER2D:  return launch_policy_v<COPTER_HOVER2D>(a, s);
-        default:              return launch_policy_v<COPTER_HOVER1D>(a, s);
+        case COPTER_HOVER1D:  return launch_policy_v<COPTER_HOVER1D>(a, s);
+        default:              return launch_policy_v<COPTER_TAKEOFF>(a, s);
     }
 }
 
 int copter_policy_rollout_f32(const CopterParams* p, const CopterBuffers* b, const CopterMlpPolicy* policy, int64_t n,
                               int64_t env_offset, uint64_t seed, int64_t first_step, int n_steps, int variant, int flags,
                               float* reward_tn, uint8_t* done_tn, float* action_tn, float* obs_tn, void* stream) {
-    int e = check_params(p);
+    if (!b) return COPTER_E_ARG;
+    int e = check_params(p, b->meta_hi != nullptr);
     if (e) return e;
-    if (!b || !b->state || !b->meta || !policy_ok(policy)) return COPTER_E_ARG;
+    if (!b->state || !b->meta || !policy_ok(policy)) return COPTER_E_ARG;
     if (n < 0 || env_offset < 0 || first_step < 0 || n_steps < 1 || policy->hidden != kPolH || (b->state_stride > 0 && b->state_stride < n)) return COPTER_E_RANGE;
     if (variant < 0 || variant >= COPTER_NUM_VARIANTS) return COPTER_E_VARIANT;
     if (!aligned16(b->state) || (b->obs && !aligned16(b->obs)) || (action_tn && !aligned16(action_tn)) || (obs_tn && !aligned16(obs_tn))) return COPTER_E_ALIGN;
     if (n == 0) return 0;
-    const KParams<float> kp = make_kparams<float>(*p);
+    const KParams<float> kp = make_kparams<float>(*p, b->meta_hi != nullptr);
     PolicyRolloutArgs a;
-    a.state = (float*)b->state; a.meta = b->meta; a.obs = b->obs; a.reward_sum = (float*)b->reward; a.done_any = b->done;
+    a.state = (float*)b->state; a.meta = b->meta; a.meta_hi = b->meta_hi; a.obs = b->obs; a.reward_sum = (float*)b->reward; a.done_any = b->done;
     a.init_force = (const float*)b->init_force; a.ep_return = (float*)b->ep_return; a.stats = b->stats;
     a.reward_tn = reward_tn; a.done_tn = done_tn; a.action_tn = action_tn; a.obs_tn = obs_tn;
     a.n = n; a.stride = b->state_stride > 0 ? b->state_stride : n; a.env_offset = env_offset; a.seed = seed;
@@ -1454,20 +1673,32 @@ int copter_policy_rollout_f32(const CopterParams* p, const CopterBuffers* b, con
         case COPTER_LANDER1D: return launch_policy_rollout_v<COPTER_LANDER1D>(kp, a, s);
         case COPTER_HOVER3D:  return launch_policy_rollout_v<COPTER_HOVER3D>(kp, a, s);
         case COPTER_HOVER2D:  return launch_policy_rollout_v<COPTER_HOVER2D>(kp, a, s);
-        default:              return launch_policy_rollout_v<COPTER_HOVER1D>(kp, a, s);
+        case COPTER_HOVER1D:  return launch_policy_rollout_v<COPTER_HOVER1D>(kp, a, s);
+        default:              return launch_policy_rollout_v<COPTER_TAKEOFF>(kp, a, s);
     }
 }
 
 int copter_pipeline_create(int n_streams, void** out) {
     if (!out || n_streams < 1 || n_streams > 8) return COPTER_E_ARG;
     Pipeline* pl = new Pipeline();
-    pl->n_streams = n_streams;
-    cudaError_t ce = cudaEventCreateWithFlags(&pl->start, cudaEventDisableTiming);
+    pl->n_streams = 0;
+    pl->device = 0;
+    cudaError_t ce = cudaGetDevice(&pl->device);
+    bool have_start = false;
+    if (ce == cudaSuccess) { ce = cudaEventCreateWithFlags(&pl->start, cudaEventDisableTiming); have_start = ce == cudaSuccess; }
     for (int s = 0; s < n_streams && ce == cudaSuccess; ++s) {
         ce = cudaStreamCreateWithFlags(&pl->streams[s], cudaStreamNonBlocking);
-        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&pl->done[s], cudaEventDisableTiming);
+        if (ce != cudaSuccess) break;
+        ce = cudaEventCreateWithFlags(&pl->done[s], cudaEventDisableTiming);
+        if (ce != cudaSuccess) { cudaStreamDestroy(pl->streams[s]); break; }
+        pl->n_streams = s + 1;                       // stream s and its event both exist
     }
-    if (ce != cudaSuccess) { delete pl; return (int)ce; }
+    if (ce != cudaSuccess) {                         // release what was created before the failure
+        for (int s = 0; s < pl->n_streams; ++s) { cudaStreamDestroy(pl->streams[s]); cudaEventDestroy(pl->done[s]); }
+        if (have_start) cudaEventDestroy(pl->start);
+        delete pl;
+        return (int)ce;
+    }
     *out = pl;
     return 0;
 }
@@ -1475,21 +1706,24 @@ int copter_pipeline_create(int n_streams, void** out) {
 int copter_pipeline_destroy(void* pipeline) {
     Pipeline* pl = (Pipeline*)pipeline;
     if (!pl) return COPTER_E_ARG;
+    int prev = -1;                                   // the streams belong to the device that was current at creation
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != pl->device) cudaSetDevice(pl->device); else prev = -1;
     for (int s = 0; s < pl->n_streams; ++s) { cudaStreamDestroy(pl->streams[s]); cudaEventDestroy(pl->done[s]); }
     cudaEventDestroy(pl->start);
+    if (prev >= 0) cudaSetDevice(prev);
     delete pl;
     return 0;
 }
 
 int copter_step_host_f32(void* pipeline, const CopterParams* p, const CopterBuffers* dev, const float* h_action, float* h_obs,
-                         float* h_reward, uint8_t* h_done, int64_t n, int64_t env_offset, uint64_t seed, int k, int variant,
-                         int flags, int64_t chunk_envs, void* stream) {
-    return step_host<float>((Pipeline*)pipeline, p, dev, h_action, h_obs, h_reward, h_done, n, env_offset, seed, k, variant, flags, chunk_envs, stream);
+                         float* h_reward, uint8_t* h_done, uint8_t* h_cause, float* h_final_obs, int64_t n, int64_t env_offset,
+                         uint64_t seed, int k, int variant, int flags, int64_t chunk_envs, void* stream) {
+    return step_host<float>((Pipeline*)pipeline, p, dev, h_action, h_obs, h_reward, h_done, h_cause, h_final_obs, n, env_offset, seed, k, variant, flags, chunk_envs, stream);
 }
 int copter_step_host_f64(void* pipeline, const CopterParams* p, const CopterBuffers* dev, const double* h_action, float* h_obs,
-                         double* h_reward, uint8_t* h_done, int64_t n, int64_t env_offset, uint64_t seed, int k, int variant,
-                         int flags, int64_t chunk_envs, void* stream) {
-    return step_host<double>((Pipeline*)pipeline, p, dev, h_action, h_obs, h_reward, h_done, n, env_offset, seed, k, variant, flags, chunk_envs, stream);
+                         double* h_reward, uint8_t* h_done, uint8_t* h_cause, float* h_final_obs, int64_t n, int64_t env_offset,
+                         uint64_t seed, int k, int variant, int flags, int64_t chunk_envs, void* stream) {
+    return step_host<double>((Pipeline*)pipeline, p, dev, h_action, h_obs, h_reward, h_done, h_cause, h_final_obs, n, env_offset, seed, k, variant, flags, chunk_envs, stream);
 }
 
 }  // extern "C"

@@ -23,8 +23,11 @@ from . import _lib
 from ._lib import CopterActionSource, CopterBuffers, CopterError, SOURCE_KINDS, VARIANT_IDS, STAT_NAMES
 
 _OBS_IDX = {'Lander3D': tuple(range(10)), 'Lander2D': (2, 3, 4, 5, 6, 7), 'Lander1D': (4, 5),
-            'Hover3D': tuple(range(12)), 'Hover2D': (2, 3, 4, 5, 6, 7), 'Hover1D': (4, 5)}
-_ACT_SIZE = {'Lander3D': 4, 'Lander2D': 2, 'Lander1D': 1, 'Hover3D': 4, 'Hover2D': 2, 'Hover1D': 1}
+            'Hover3D': tuple(range(12)), 'Hover2D': (2, 3, 4, 5, 6, 7), 'Hover1D': (4, 5),
+            'Takeoff': tuple(range(10))}
+_ACT_SIZE = {'Lander3D': 4, 'Lander2D': 2, 'Lander1D': 1, 'Hover3D': 4, 'Hover2D': 2, 'Hover1D': 1, 'Takeoff': 4}
+# attic/gym_copter/envs/takeoff.py:45-55: starts on the ground (state zeros -> LANDED), no reset perturbation
+_VARIANT_DEFAULTS = {'Takeoff': dict(initial_altitude=0.0, initial_random_force=0.0)}
 _ALL_NAMES = ['X', 'dX', 'Y', 'dY', 'Z', 'dZ', 'Phi', 'dPhi', 'Theta', 'dTheta', 'Psi', 'dPsi']
 
 
@@ -65,7 +68,9 @@ class CopterVecEnv:
     N independent copter envs stepped in lockstep on one GPU.
 
     variant      'Lander3D' (the reference's live `Lander`), 'Lander2D', 'Lander1D',
-                 'Hover3D', 'Hover2D', 'Hover1D' 
+                 'Hover3D', 'Hover2D', 'Hover1D' (SURVEY.md 2.2), 'Takeoff' (the attic take-off env,
+                 attic/gym_copter/envs/takeoff.py: unclipped commands, starts LANDED, reward =
+                 change of -|altitude - 5|, only the step limit ends an episode)
     dtype        torch.float32 (throughput path) or torch.float64 (trajectory-exact path)
     k_substeps   reference steps fused per `step()` under one action (frame-skip)
     auto_reset   same-step auto-reset: a finished env reports done/terminal reward and is
@@ -82,6 +87,10 @@ class CopterVecEnv:
     report_cause  record why each env finished (`info['cause']`, COPTER_CAUSE_* bits) and report
                  the env's own step limit as `truncated` the way gymnasium's
                  TimeLimit(max_episode_steps) wrapper does for the reference (gym_copter/__init__.py:9-13)
+    wide_counters  keep the step counter (30 bits) and the episode index (32 bits) in a second
+                 uint32 per env instead of the packed 11 + 19 bits: any `max_steps` the reference takes
+                 (task.py:35) and no repetition of an env's reset-force stream after 2^19 episodes.
+                 Switched on automatically when max_steps > 2046
     kwargs       any CopterParams field, e.g. initial_altitude=5, max_steps=500 (task.py:32-38)
     """
 
@@ -91,7 +100,7 @@ class CopterVecEnv:
     def __init__(self, variant='Lander3D', num_envs=1, dtype=torch.float32, device=None, seed=0,
                  env_offset=0, k_substeps=1, auto_reset=True, track_stats=False,
                  track_returns=False, keep_final_obs=False, write_obs=True, report_cause=False,
-                 **params):
+                 wide_counters=None, **params):
         if variant not in VARIANT_IDS:
             raise ValueError('unknown variant %r' % (variant,))
         if dtype not in (torch.float32, torch.float64):
@@ -105,7 +114,8 @@ class CopterVecEnv:
         self.variant, self.num_envs, self.dtype = variant, int(num_envs), dtype
         self.seed_value, self.env_offset = int(seed), int(env_offset)
         self.k_substeps, self.auto_reset = int(k_substeps), bool(auto_reset)
-        self.params = _lib.default_params(**params)
+        self.params = _lib.default_params(**dict(_VARIANT_DEFAULTS.get(variant, {}), **params))
+        self.wide = bool(self.params.max_steps > _lib.MAX_STEPS_LIMIT) if wide_counters is None else bool(wide_counters)
         self.FRAMES_PER_SECOND = self.params.fps
         self.TARGET_RADIUS = self.params.target_radius
         self.obs_size, self.action_size = len(_OBS_IDX[variant]), _ACT_SIZE[variant]
@@ -122,10 +132,12 @@ class CopterVecEnv:
         self._f32 = dtype == torch.float32
         self.state_planes = torch.zeros((12 // V, n, V), dtype=dtype, device=dev)
         self.meta = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.meta_hi = torch.zeros(n, dtype=torch.int32, device=dev) if self.wide else None
         self.obs = torch.zeros((n, self.obs_size), dtype=torch.float32, device=dev)
         self.reward = torch.zeros(n, dtype=dtype, device=dev)
         self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._truncated = torch.zeros(n, dtype=torch.bool, device=dev)
+        self._truncated_host = np.zeros(n, np.bool_)
         self._action = torch.zeros((n, self.action_size), dtype=dtype, device=dev)
         track_stats = track_stats or track_returns
         self.ep_return = torch.zeros(n, dtype=dtype, device=dev) if track_returns else None
@@ -154,6 +166,7 @@ class CopterVecEnv:
         b.ep_return = self.ep_return.data_ptr() if self.ep_return is not None else None
         b.stats = self._stats.data_ptr() if self._stats is not None else None
         b.final_obs = self.final_obs.data_ptr() if self.final_obs is not None else None
+        b.meta_hi = self.meta_hi.data_ptr() if self.meta_hi is not None else None
         return b
 
     def _stream(self):
@@ -179,11 +192,17 @@ class CopterVecEnv:
 
     def reset(self, seed=None, options=None, force=None):
         """
-        Resets every env (envs/task.py:145-197).  `seed` re-keys the Philox reset-force
-        stream (the reference's seed argument is dead code, task.py:147).  `force` ([N,3],
-        newtons) injects the reset perturbation instead of the Philox draw -- it is then used
-        for every episode of the env until `reset()` is called without it.
+        Resets every env (envs/task.py:145-197).  The reset force of env i is the Philox draw for
+        (seed, global env id, episode index).  The first reset() -- and any reset(seed=...), which
+        re-keys the stream (the reference's seed argument is dead code, task.py:147) -- starts every
+        env at episode 0, so a seeded reset is reproducible; every other reset() moves each env on to
+        its NEXT episode index, so the reference's caller loop `env.reset()` once per episode
+        (lander.py:29) sees a new perturbation every time, as it does with the reference's
+        np.random.uniform (task.py:175-184,199-202).  `force` ([N,3], newtons) injects the reset
+        perturbation instead of the Philox draw -- it is then used for every episode of the env
+        until `reset()` is called without it.
         """
+        keep = self._is_reset and seed is None
         if seed is not None:
             self.seed_value = int(seed)
         self._force = None
@@ -194,7 +213,7 @@ class CopterVecEnv:
             fn = self._lib.copter_reset_f32 if self._f32 else self._lib.copter_reset_f64
             b = self._buffers()
             _lib.check(fn(C.byref(self.params), C.byref(b), self.num_envs, VARIANT_IDS[self.variant],
-                          self._stream()), 'copter_reset')
+                          _lib.F_KEEP_EPISODE if keep else 0, self._stream()), 'copter_reset')
         self.launches += 1
         self._is_reset = True
         if self.controller is not None:
@@ -307,13 +326,18 @@ class CopterVecEnv:
 
     def host_buffers(self):
         """Page-locked host arrays (numpy views) the host-array step reads and fills:
-        dict(action [N,A], obs [N,O] f32, reward [N], done [N] uint8)."""
+        dict(action [N,A], obs [N,O] f32, reward [N], done [N] uint8, plus cause [N] uint8 with
+        report_cause and final_obs [N,O] with keep_final_obs)."""
         if self._host is None:
             n = self.num_envs
             t = {'action': torch.zeros((n, self.action_size), dtype=self.dtype).pin_memory(),
                  'obs': torch.zeros((n, self.obs_size), dtype=torch.float32).pin_memory(),
                  'reward': torch.zeros(n, dtype=self.dtype).pin_memory(),
                  'done': torch.zeros(n, dtype=torch.uint8).pin_memory()}
+            if self.cause is not None:
+                t['cause'] = torch.zeros(n, dtype=torch.uint8).pin_memory()
+            if self.final_obs is not None:
+                t['final_obs'] = torch.zeros((n, self.obs_size), dtype=torch.float32).pin_memory()
             self._host_t = t
             self._host = {k: v.numpy() for k, v in t.items()}
         return self._host
@@ -344,14 +368,23 @@ class CopterVecEnv:
             b = self._buffers(self._action, self._force)
             t = self._host_t
             _lib.check(fn(self._pipeline, C.byref(self.params), C.byref(b), t['action'].data_ptr(),
-                          t['obs'].data_ptr(), t['reward'].data_ptr(), t['done'].data_ptr(),
+                          t['obs'].data_ptr() if self.write_obs else None, t['reward'].data_ptr(), t['done'].data_ptr(),
+                          t['cause'].data_ptr() if 'cause' in t else None,
+                          t['final_obs'].data_ptr() if 'final_obs' in t else None,
                           self.num_envs, self.env_offset, self.seed_value & 0xFFFFFFFFFFFFFFFF,
                           self.k_substeps, VARIANT_IDS[self.variant],
                           _lib.F_AUTO_RESET if self.auto_reset else 0, int(chunk_envs), self._stream()),
                        'copter_step_host')
         chunk = (int(chunk_envs) + 255) // 256 * 256
         self.launches += (self.num_envs + chunk - 1) // chunk
-        return h['obs'], h['reward'], h['done'].view(np.bool_), np.zeros(self.num_envs, np.bool_), {}
+        info = {}
+        truncated = self._truncated_host
+        if 'cause' in h:                # as step(): the env's own step limit is TimeLimit's `truncated`
+            info['cause'] = h['cause']
+            truncated = (h['cause'] & _lib.CAUSE_TIMEOUT) != 0
+        if 'final_obs' in h:
+            info['final_obs'] = h['final_obs']
+        return (h['obs'] if self.write_obs else None), h['reward'], h['done'].view(np.bool_), truncated, info
 
     def close(self):
         if self.viewer is not None:
@@ -408,12 +441,12 @@ class CopterVecEnv:
         s = s.to(device=self.device, dtype=self.dtype).reshape(self.num_envs, 12)
         V = self.state_planes.shape[2]
         self.state_planes.copy_(s.reshape(self.num_envs, 12 // V, V).permute(1, 0, 2))
-        m = self.meta.to(torch.int64) & 0xFFFFFFFF
+        m = self._meta64()
         st = torch.where(s[:, 4] < 0, 3, 1).to(torch.int64) if status is None else \
             torch.as_tensor(status, device=self.device).to(torch.int64).expand(self.num_envs)
-        stp = ((m >> 2) & 2047) if steps is None else \
+        stp = self.steps.to(torch.int64) if steps is None else \
             torch.as_tensor(steps, device=self.device).to(torch.int64).expand(self.num_envs)
-        m = (m & ~0x1FFF) | st | (stp << 2)
+        m = (st | (stp << 2)) if self.wide else ((m & ~0x1FFF) | st | (stp << 2))
         self.meta.copy_(torch.where(m >= 2 ** 31, m - 2 ** 32, m).to(torch.int32))
         self.obs.copy_(s[:, list(_OBS_IDX[self.variant])].to(torch.float32))
 
@@ -426,11 +459,15 @@ class CopterVecEnv:
 
     @property
     def steps(self):
-        return ((self._meta64() >> 2) & 2047).to(torch.int32)
+        m = self._meta64() >> 2
+        return (m if self.wide else (m & 2047)).to(torch.int32)
 
     @property
     def episodes(self):
-        return (self._meta64() >> 13).to(torch.int32)
+        """Episode index of every env (int64: the wide counter is a full uint32)."""
+        if self.wide:
+            return self.meta_hi.to(torch.int64) & 0xFFFFFFFF
+        return self._meta64() >> 13
 
     def stats(self, reduce_group=None):
         """
@@ -458,25 +495,39 @@ class CopterVecEnv:
     # ---- checkpoint ---------------------------------------------------------------------
 
     def state_dict(self):
+        """Everything a restored env needs to continue bit for bit: the SoA buffers and counters, the
+        Philox keys and stream positions, the injected reset force, the PID controller memories and the
+        parameter block (checked on load)."""
         d = {'variant': self.variant, 'seed': self.seed_value, 'env_offset': self.env_offset,
+             'dtype': str(self.dtype), 'k_substeps': self.k_substeps, 'auto_reset': self.auto_reset,
+             'rollout_step': self.rollout_step, 'params': bytes(self.params),
              'state_planes': self.state_planes.clone(), 'meta': self.meta.clone(), 'obs': self.obs.clone()}
-        if self._stats is not None:
-            d['stats'] = self._stats.clone()
-        if self.ep_return is not None:
-            d['ep_return'] = self.ep_return.clone()
+        for k in ('meta_hi', '_stats', 'ep_return', '_force', 'controller', 'cause', 'final_obs'):
+            v = getattr(self, k)
+            if v is not None:
+                d[k.lstrip('_')] = v.clone()
         return d
 
     def load_state_dict(self, d):
-        if d['variant'] != self.variant or d['state_planes'].shape != self.state_planes.shape:
-            raise CopterError('checkpoint does not match this env')
+        if d['variant'] != self.variant or d['state_planes'].shape != self.state_planes.shape \
+                or d.get('dtype', str(self.dtype)) != str(self.dtype):
+            raise CopterError('checkpoint does not match this env (variant / size / dtype)')
+        if 'params' in d and d['params'] != bytes(self.params):
+            raise CopterError('checkpoint was taken with different CopterParams (e.g. max_steps, initial_altitude): '
+                              'construct the env with the same parameters')
+        if ('meta_hi' in d) != (self.meta_hi is not None):
+            raise CopterError('checkpoint and env disagree on wide_counters')
         self.seed_value, self.env_offset = d['seed'], d['env_offset']
+        self.rollout_step = d.get('rollout_step', 0)
         self.state_planes.copy_(d['state_planes'])
         self.meta.copy_(d['meta'])
         self.obs.copy_(d['obs'])
-        if self._stats is not None and 'stats' in d:
-            self._stats.copy_(d['stats'])
-        if self.ep_return is not None and 'ep_return' in d:
-            self.ep_return.copy_(d['ep_return'])
+        for k in ('meta_hi', '_stats', 'ep_return', 'cause', 'final_obs'):
+            v = getattr(self, k)
+            if v is not None and k.lstrip('_') in d:
+                v.copy_(d[k.lstrip('_')])
+        self._force = d['force'].to(self.device).clone() if 'force' in d else None
+        self.controller = d['controller'].to(self.device).clone() if 'controller' in d else None
         self._is_reset = True
 
 
@@ -492,29 +543,73 @@ Lander1DVec = _variant_class('Lander1D')
 Hover3DVec = _variant_class('Hover3D')
 Hover2DVec = _variant_class('Hover2D')
 Hover1DVec = _variant_class('Hover1D')
+TakeoffVec = _variant_class('Takeoff')
 LanderVec = Lander3DVec
+
+
+class _EnvDynamics:
+    """`env.dynamics` of the single-env facade: the `Dynamics` accessors the reference's callers and
+    renderer use on a live env (gym_copter/dynamics/__init__.py:199-229; the env creates a fresh
+    Dynamics per reset, task.py:161), served from the env's own device buffers."""
+
+    def __init__(self, vec):
+        self._vec = vec
+
+    def getState(self):
+        s = self._vec.state_planes.reshape(12).cpu().numpy().astype(np.float64)
+        return dict(zip(('x', 'dx', 'y', 'dy', 'z', 'dz', 'phi', 'dphi', 'theta', 'dtheta', 'psi', 'dpsi'), s))
+
+    def getStatus(self):
+        return int(self._vec.status[0].item())
+
+    def getTime(self):
+        # ticks * dt (dynamics:219-221): one tick per executed setMotors; the env's `steps` counter is 1
+        # after reset and the priming step does not tick (task.py:93,197)
+        return (int(self._vec.steps[0].item()) - 1) / float(self._vec.params.fps)
+
+    def setState(self, state):
+        self._vec.set_state(np.asarray(state, np.float64).reshape(1, 12))
+
+    def perturb(self, force):
+        """dynamics:227-229 on a freshly reset env: replaces the reset force (the first three components;
+        the env path perturbs x, y, z only, task.py:179-184), exactly what the oracle harness does with the
+        reference."""
+        f = np.asarray(force, np.float64).reshape(-1)[:3]
+        self._vec._force = torch.as_tensor(f.reshape(1, 3)).to(device=self._vec.device, dtype=self._vec.dtype).contiguous()
 
 
 class SingleEnv:
     """
     The reference's single-env call shapes over a one-env batch: numpy float32 obs, python
     float reward, python bool done, `truncated` always False (envs/task.py:133-137).
-    No auto-reset and float64 arithmetic by default, like the reference.
+    No auto-reset and float64 arithmetic by default, like the reference.  Attributes of the
+    reference env its callers read are served too: `pose`, `done`, `viewer`, `steps`, `spinning`,
+    `dynamics` (envs/task.py:80,87,92,102,106,130,161).
     """
 
     def __init__(self, variant, dtype=torch.float64, **kw):
         kw.setdefault('auto_reset', False)
+        self._report_truncation = bool(kw.get('report_cause', False))
+        kw['report_cause'] = True                     # one byte per step: `spinning` is derived from it
         self.vec = CopterVecEnv(variant, 1, dtype=dtype, **kw)
         for k in ('observation_space', 'action_space'):
             setattr(self, k, getattr(self.vec, 'single_' + k))
         self.STATE_NAMES, self.TARGET_RADIUS = self.vec.STATE_NAMES, self.vec.TARGET_RADIUS
         self.FRAMES_PER_SECOND, self.metadata = self.vec.FRAMES_PER_SECOND, self.vec.metadata
         self.viewer, self.done = None, False
+        self.spinning = False                         # task.py:87,92: any motor commanded on the last step
+        self._landed_before = False
+        self.dynamics = _EnvDynamics(self.vec)
         self._host = self.vec.host_buffers()        # page-locked action / obs / reward / done of the one env
 
     @property
     def unwrapped(self):
         return self
+
+    @property
+    def steps(self):
+        """The env's own step counter (task.py:128-130,191): 1 right after reset()."""
+        return int(self.vec.steps[0].item())
 
     @property
     def pose(self):
@@ -526,17 +621,33 @@ class SingleEnv:
 
     def reset(self, seed=None, options=None, force=None):
         obs, info = self.vec.reset(seed, options, None if force is None else np.asarray(force).reshape(1, 3))
-        self.done = False
+        self.done, self.spinning, self._landed_before = False, False, False
         return obs[0].cpu().numpy(), info
 
     def step(self, action):
-        # one library call per step: the command goes in and observation / reward / done come back
+        # one library call per step: the command goes in and observation / reward / done / cause come back
         # through the page-locked buffers of copter_step_host_* (H2D + kernel + D2H + one stream sync)
         h = self._host
-        h['action'][0, :] = np.asarray(action, dtype=h['action'].dtype).reshape(-1)
-        obs, r, term, _, _ = self.vec.step_host(None, n_streams=1)
+        a = np.asarray(action, dtype=h['action'].dtype).reshape(-1)
+        h['action'][0, :] = a
+        obs, r, term, trunc, info = self.vec.step_host(None, n_streams=1)
         self.done = bool(term[0])
-        return obs[0].copy(), float(r[0]), self.done, False, {}
+        # `spinning` as the reference leaves it after the step (task.py:86-92,121-125, lander.py:64-67):
+        # off when the status BEFORE the step was LANDED, or CRASHED without an out-of-bounds / over-angle
+        # ending; otherwise "some motor is commanded"
+        c = int(info['cause'][0])
+        spin = bool(np.clip(a, 0, 1).sum() > 0)
+        if (c & _lib.CAUSE_LANDED) or self._landed_before:
+            spin = False
+        elif (c & _lib.CAUSE_CRASHED) and not (c & (_lib.CAUSE_OOB | _lib.CAUSE_ANGLE)):
+            spin = False
+        self.spinning = spin
+        # variants where LANDED does not end the episode (hover): remember it for the next step; the
+        # device is only asked once the vehicle is at ground level (NED: z >= 0)
+        zi = self.vec.STATE_NAMES.index('Z')
+        self._landed_before = (self.vec.variant.startswith('Hover') and float(obs[0, zi]) >= 0.0
+                               and self.dynamics.getStatus() == _lib.STATUS_LANDED)
+        return obs[0].copy(), float(r[0]), self.done, bool(trunc[0]) if self._report_truncation else False, {}
 
     def set_altitude(self, altitude):
         self.vec.set_altitude(altitude)
@@ -561,6 +672,7 @@ Lander1D = _single_class('Lander1D')
 Hover3D = _single_class('Hover3D')
 Hover2D = _single_class('Hover2D')
 Hover1D = _single_class('Hover1D')
+Takeoff = _single_class('Takeoff')
 
 
 def make(env_id, **kw):
@@ -569,7 +681,7 @@ def make(env_id, **kw):
     name = env_id.split(':')[-1]
     name = name[:-3] if name.endswith('-v0') else name
     table = {'Lander': Lander, 'Lander3D': Lander, 'Lander2D': Lander2D, 'Lander1D': Lander1D,
-             'Hover3D': Hover3D, 'Hover2D': Hover2D, 'Hover1D': Hover1D,
+             'Hover3D': Hover3D, 'Hover2D': Hover2D, 'Hover1D': Hover1D, 'Takeoff': Takeoff, 'TakeoffVec': TakeoffVec,
              'LanderVec': Lander3DVec, 'Lander3DVec': Lander3DVec, 'Lander2DVec': Lander2DVec,
              'Lander1DVec': Lander1DVec, 'Hover3DVec': Hover3DVec, 'Hover2DVec': Hover2DVec,
              'Hover1DVec': Hover1DVec}

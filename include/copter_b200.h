@@ -39,6 +39,11 @@
  *   meta    uint32[N]       bits 0-1 flight status (COPTER_STATUS_*), bits 2-12 the env's
  *                           `steps` counter (envs/task.py:128-130; saturates at 2047), bits 13-31
  *                           episode index (wraps at 2^19; keys the reset-force stream).
+ *   meta_hi uint32[N]       optional WIDE counters (the reference takes any max_steps, envs/task.py:35):
+ *                           when CopterBuffers.meta_hi is given, meta holds status (bits 0-1) and a
+ *                           30-bit steps counter (bits 2-31), meta_hi the 32-bit episode index; max_steps
+ *                           may then be anything up to COPTER_MAX_STEPS_LIMIT_WIDE.  4 more bytes read
+ *                           and written per env and launch; the default layout is unchanged.
  *   action  T[N][A]         row-major, A = action size of the variant.
  *   obs     float[N][O]     row-major float32 (envs/task.py:133), O = observation size.
  *   reward  T[N]; done uint8[N] (0/1).
@@ -52,14 +57,20 @@
 extern "C" {
 #endif
 
-#define COPTER_ABI_VERSION 2
+#define COPTER_ABI_VERSION 3
 
 /* dynamics/__init__.py:65-68 */
 enum { COPTER_STATUS_CRASHED = 0, COPTER_STATUS_LANDED = 1, COPTER_STATUS_LEVELING = 2, COPTER_STATUS_AIRBORNE = 3 };
 
 /* env variants: the live Lander (= Lander3D) and the attic-defined projections */
+/* COPTER_TAKEOFF is the attic take-off env (attic/gym_copter/envs/takeoff.py:18-91): the 10-component
+   observation, four motor commands handed to Dynamics.setMotors UNCLIPPED whatever the flight status
+   (so a LANDED vehicle takes off, dynamics/__init__.py:147-149), reward = change of -|altitude -
+   takeoff_target_altitude|, no bounds / angle limit / landing logic: only the step limit ends an episode.
+   Construct it with initial_altitude = 0 and initial_random_force = 0 to start LANDED and unperturbed
+   as that env does (the Python shell does). */
 enum { COPTER_LANDER3D = 0, COPTER_LANDER2D = 1, COPTER_LANDER1D = 2,
-       COPTER_HOVER3D = 3, COPTER_HOVER2D = 4, COPTER_HOVER1D = 5, COPTER_NUM_VARIANTS = 6 };
+       COPTER_HOVER3D = 3, COPTER_HOVER2D = 4, COPTER_HOVER1D = 5, COPTER_TAKEOFF = 6, COPTER_NUM_VARIANTS = 7 };
 
 enum { COPTER_E_ARG = -1, COPTER_E_VARIANT = -2, COPTER_E_ALIGN = -3, COPTER_E_RANGE = -4 };
 
@@ -70,12 +81,13 @@ enum { COPTER_E_ARG = -1, COPTER_E_VARIANT = -2, COPTER_E_ALIGN = -3, COPTER_E_R
 enum { COPTER_CAUSE_LANDED = 1, COPTER_CAUSE_BONUS = 2, COPTER_CAUSE_OOB = 4, COPTER_CAUSE_ANGLE = 8,
        COPTER_CAUSE_CRASHED = 16, COPTER_CAUSE_TIMEOUT = 32 };
 
-/* flags for copter_step_* */
-enum { COPTER_F_AUTO_RESET = 1 };
+/* flags: COPTER_F_AUTO_RESET for copter_step_* / copter_rollout_* / copter_policy_rollout_f32 /
+   copter_step_host_*; COPTER_F_KEEP_EPISODE for copter_reset_* */
+enum { COPTER_F_AUTO_RESET = 1, COPTER_F_KEEP_EPISODE = 2 };
 
 /* episode statistics: double[COPTER_STATS_SLOTS][COPTER_STATS_LEN], accumulated with atomics and never
-   cleared by the library.  A CTA adds to slot (blockIdx.x % COPTER_STATS_SLOTS) so that the atomics of
-   concurrent CTAs land on different 128-byte lines; the statistic is the sum over the slots. */
+   cleared by the library.  Each WARP adds to slot (global warp index % COPTER_STATS_SLOTS) so that the
+   atomics of concurrent warps land on different 128-byte lines; the statistic is the sum over the slots. */
 #define COPTER_STATS_SLOTS 64
 enum { COPTER_STAT_EPISODES = 0, COPTER_STAT_RETURN_SUM = 1, COPTER_STAT_LENGTH_SUM = 2,
        COPTER_STAT_LANDED = 3, COPTER_STAT_BONUS = 4, COPTER_STAT_CRASHED = 5, COPTER_STAT_OOB = 6,
@@ -84,7 +96,8 @@ enum { COPTER_STAT_EPISODES = 0, COPTER_STAT_RETURN_SUM = 1, COPTER_STAT_LENGTH_
 #define COPTER_META_STATUS(m)  ((m) & 3u)
 #define COPTER_META_STEPS(m)   (((m) >> 2) & 2047u)
 #define COPTER_META_EPISODE(m) ((m) >> 13)
-#define COPTER_MAX_STEPS_LIMIT 2046
+#define COPTER_MAX_STEPS_LIMIT 2046                 /* compact meta word (11-bit steps counter) */
+#define COPTER_MAX_STEPS_LIMIT_WIDE 0x3FFFFFFE      /* with CopterBuffers.meta_hi (30-bit steps counter) */
 
 typedef struct CopterParams {
     /* vehicle (dji_phantom.py:9-26) */
@@ -97,6 +110,8 @@ typedef struct CopterParams {
     double target_radius, yaw_penalty_factor, xyz_penalty_factor, dz_max, dz_penalty, inside_radius_bonus;
     /* alternate vehicle/world model of attic/mars/dynamics/__init__.py (see dynamics_model) */
     double rho, lift_coefficient;
+    /* attic/gym_copter/envs/takeoff.py:20 (COPTER_TAKEOFF only) */
+    double takeoff_target_altitude;
     int32_t max_steps;
     int32_t dynamics_model;     /* bit set of COPTER_MODEL_*; 0 = the live gym_copter/dynamics model */
 } CopterParams;
@@ -133,16 +148,20 @@ typedef struct CopterBuffers {
                                 COPTER_CAUSE_*; 0 when it did not finish */
     int64_t     state_stride;/* vectors per state plane in the allocation; 0 means n. Lets a call step a
                                 sub-range [lo, lo+n) of a larger shard: pass state + lo vectors, stride = shard size */
+    uint32_t*   meta_hi;     /* [n] nullable: wide counters (see "Memory layout"): 32-bit episode index */
 } CopterBuffers;
 
 /*
- * Reset every env of the shard: default pose, status, steps = 1, episode = 0, obs of the
- * initial state.  The reset force is not stored: it is (re)generated on the first step of
+ * Reset every env of the shard: default pose, status, steps = 1, obs of the initial state.
+ * The episode index becomes 0 -- or, with COPTER_F_KEEP_EPISODE, the env's previous index + 1, so that
+ * a caller's reset() per episode (the reference's loop, lander.py:29) draws a NEW reset force each
+ * time, as the reference's np.random.uniform does (envs/task.py:175-184,199-202).
+ * The reset force is not stored: it is (re)generated on the first step of
  * an episode from Philox4x32-10 with counter (env_lo, env_hi, episode, 0), key = seed,
  * env = env_offset + i, unless init_force is given to copter_step_*.
  */
-int copter_reset_f32(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, void* stream);
-int copter_reset_f64(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, void* stream);
+int copter_reset_f32(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, int flags, void* stream);
+int copter_reset_f64(const CopterParams* p, const CopterBuffers* b, int64_t n, int variant, int flags, void* stream);
 
 /*
  * One launch = k_substeps reference steps for each of the n envs under one action (rewards
@@ -285,17 +304,18 @@ int copter_policy_rollout_f32(const CopterParams* p, const CopterBuffers* b, con
  * two PCIe directions and the kernel overlap.  `dev` are the device buffers of the whole
  * shard (dev->action is the device staging area for the actions).  Host arrays should be
  * page-locked for the copies to be asynchronous.  Work is ordered after `stream`; the call
- * returns when all chunks have landed in the host arrays.
+ * returns when all chunks have landed in the host arrays.  h_cause / h_final_obs (nullable)
+ * receive dev->cause / dev->final_obs when those device buffers are given.
  */
 int copter_pipeline_create(int n_streams, void** out_pipeline);      /* 1..8 streams */
 int copter_pipeline_destroy(void* pipeline);
 int copter_step_host_f32(void* pipeline, const CopterParams* p, const CopterBuffers* dev,
                          const float* h_action, float* h_obs_or_null, float* h_reward, uint8_t* h_done,
-                         int64_t n, int64_t env_offset, uint64_t seed, int k_substeps, int variant,
+                         uint8_t* h_cause_or_null, float* h_final_obs_or_null, int64_t n, int64_t env_offset, uint64_t seed, int k_substeps, int variant,
                          int flags, int64_t chunk_envs, void* stream);
 int copter_step_host_f64(void* pipeline, const CopterParams* p, const CopterBuffers* dev,
                          const double* h_action, float* h_obs_or_null, double* h_reward, uint8_t* h_done,
-                         int64_t n, int64_t env_offset, uint64_t seed, int k_substeps, int variant,
+                         uint8_t* h_cause_or_null, float* h_final_obs_or_null, int64_t n, int64_t env_offset, uint64_t seed, int k_substeps, int variant,
                          int flags, int64_t chunk_envs, void* stream);
 
 #ifdef __cplusplus

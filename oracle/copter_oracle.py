@@ -50,6 +50,12 @@ VARIANTS = {
     'Hover1D': ('hover', (4, 5), 1, (0, 0, 0, 0)),
 }
 
+# attic/gym_copter/envs/takeoff.py:18-91: the 10-component observation, four motor commands handed to
+# setMotors UNCLIPPED whatever the flight status, reward = change of -|altitude - target|, never done.
+# Kept out of VARIANTS because the golden trajectory files cover the six _Task-shaped variants.
+EXTRA_VARIANTS = {'Takeoff': ('takeoff', tuple(range(10)), 4, (0, 1, 2, 3))}
+ALL_VARIANTS = dict(VARIANTS, **EXTRA_VARIANTS)
+
 # done-cause bits reported by env_step (non-exclusive; the product's episode statistics)
 CAUSE_LANDED, CAUSE_BONUS, CAUSE_OOB, CAUSE_ANGLE, CAUSE_CRASHED, CAUSE_TIMEOUT = 1, 2, 4, 8, 16, 32
 
@@ -90,6 +96,7 @@ class OracleParams:
     rho: float = 1.225
     lift_coefficient: float = 0.4
     dynamics_model: int = 0          # bit 0: lift-model thrust, bit 1: live gyroscopic Omega
+    takeoff_target_altitude: float = 5   # attic/gym_copter/envs/takeoff.py:20
 
 
 # ---------------------------------------------------------------------------------------
@@ -288,7 +295,7 @@ class EnvBatch:
 
     def __init__(self, variant, n, params=None, dtype=np.float64, seed=0, env_offset=0,
                  auto_reset=True, env_ids=None):
-        self.kind, self.obs_idx, self.act_size, self.fanout = VARIANTS[variant]
+        self.kind, self.obs_idx, self.act_size, self.fanout = ALL_VARIANTS[variant]
         self.obs_idx, self.fanout = list(self.obs_idx), list(self.fanout)
         self.variant, self.n = variant, n
         self.p = params or OracleParams()
@@ -301,6 +308,7 @@ class EnvBatch:
         self.steps = np.zeros(n, np.int64)
         self.episode = np.zeros(n, np.int64)
         self.max_angle = np.radians(self.p.max_angle_deg)          # envs/task.py:58
+        self.ep_mask = 0x7FFFF                                     # the product's compact episode field (wide: 2^32 - 1)
 
     # ---- helpers ----------------------------------------------------------------------
 
@@ -339,8 +347,16 @@ class EnvBatch:
         self.dyn.set_perturb(f6, w)
         self.steps[w] = 1
 
-    def reset(self, force=None):
-        self.episode[:] = 0
+    def reset(self, force=None, keep_episode=None):
+        """keep_episode=None mirrors the product's host shell: the first reset() starts every env at
+        episode 0, every later one moves each env on to its next episode index, so that a reset() per
+        episode draws a NEW force each time like the reference's np.random.uniform (task.py:175-184)."""
+        keep = getattr(self, '_ever_reset', False) if keep_episode is None else keep_episode
+        if keep:
+            self.episode[:] = (self.episode + 1) & self.ep_mask
+        else:
+            self.episode[:] = 0
+        self._ever_reset = True
         self.reset_where(np.ones(self.n, bool), force)
         return self.observe()
 
@@ -354,11 +370,20 @@ class EnvBatch:
         T, p, d = self.dtype.type, self.p, self.dyn
         st0 = d.status.copy()                                      # :81 (stale status)
         a = np.asarray(action, self.dtype).reshape(self.n, self.act_size)
+        cause = np.zeros(self.n, np.int32)
+        if self.kind == 'takeoff':                                 # attic takeoff.py:57-88
+            pre_t = -np.abs(-d.x[:, 4] - T(p.takeoff_target_altitude))
+            d.set_motors(a[:, self.fanout], live)                  # no clip (:64), whatever the status
+            reward = -np.abs(-d.x[:, 4] - T(p.takeoff_target_altitude)) - pre_t       # :77-86
+            timeout = self.steps == p.max_steps                    # the batched step limit (not in the attic env)
+            done = live & timeout
+            cause |= timeout * CAUSE_TIMEOUT
+            self.steps[live] += 1
+            return np.where(live, reward, T(0)), done, np.where(done, cause, 0)
         motors = np.clip(a, 0, 1)[:, self.fanout]                  # :91 + _get_motors
         pre = self._shaping(d.x)                                   # == prev_shaping
         d.set_motors(motors, live & (st0 != STATUS_LANDED))        # :86-94
         x = d.x
-        cause = np.zeros(self.n, np.int32)
         if self.kind == 'lander':
             reward = self._shaping(x) - pre                        # lander.py:58-62
             landed = live & (st0 == STATUS_LANDED)                 # lander.py:64-72
@@ -404,7 +429,7 @@ class EnvBatch:
             cause_any |= cs
             done_any |= dn
             if self.auto_reset and np.any(dn):
-                self.episode[dn] += 1
+                self.episode[dn] = (self.episode[dn] + 1) & self.ep_mask
                 self.reset_where(dn, force)
         return self.observe(), total, done_any, {
             'steps_taken': taken, 'final_steps': final_steps, 'cause': cause_any}

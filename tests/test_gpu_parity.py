@@ -451,8 +451,11 @@ def test_abi_argument_errors(pkg):
     assert lib.copter_step_f32(C.byref(p), C.byref(b2), 64, 0, 0, 1, 0, 1, None) == -3       # alignment
     b3 = env._buffers(None)
     assert lib.copter_step_f32(C.byref(p), C.byref(b3), 64, 0, 0, 1, 0, 1, None) == -1       # missing action
-    bad = pkg.default_params(max_steps=5000)
+    bad = pkg.default_params(max_steps=5000)            # past the 11-bit steps field: needs wide counters (meta_hi)
     assert lib.copter_step_f32(C.byref(bad), C.byref(b), 64, 0, 0, 1, 0, 1, None) == -4
+    wide = pkg.CopterVecEnv('Lander3D', 64, max_steps=5000)
+    wide.reset()
+    assert wide.wide and lib.copter_step_f32(C.byref(bad), C.byref(wide._buffers(a)), 64, 0, 0, 1, 0, 1, None) == 0
     with pytest.raises(pkg.CopterError):
         pkg.CopterVecEnv('Lander3D', 8).step(torch.zeros(8, 4))                              # step before reset
     with pytest.raises(ValueError):
@@ -651,3 +654,38 @@ def test_mars_model_vs_oracle(pkg, model, dtype):
         d.setMotors(m); o.set_motors(m)
         assert np.array_equal(d.getStatus().cpu().numpy(), o.status)
     assert merr(d.state.cpu().numpy(), o.x) <= TOL[dtype] and (o.status == STATUS_AIRBORNE).all()
+
+
+def test_integration_md_stub_replays_kat3(pkg, kat):
+    """The reference-side ctypes stub printed in INTEGRATION.md, executed as it stands (only the
+    library path is filled in) and driven through KAT-3."""
+    import re
+    from gym_copter_b200 import _lib as binding
+    doc = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'INTEGRATION.md')).read()
+    code = re.search(r'```python\n(# gym_copter/envs/_b200.py.*?)```', doc, flags=re.S).group(1)
+    code = code.replace("C.CDLL('libcopter_b200.so')", 'C.CDLL(%r)' % binding.LIB_PATH)
+    ns = {}
+    exec(code, ns)
+    g = kat['kat3']
+    env = ns['B200Lander'](num_envs=3)
+    obs, info = env.reset(force=np.tile(np.asarray(g['force'], np.float64)[:3], (3, 1)))
+    assert obs.dtype == np.float32 and obs.shape == (3, 10)
+    rewards = []
+    for k in range(1, 1001):
+        obs, r, done, trunc, info = env.step(np.tile(1.625e-2 * np.ones(4), (3, 1)))
+        rewards.append(r.copy())
+        if k == 1:
+            assert merr(obs[1], g['obs1']) <= 1e-7
+        if done.any():
+            break
+    assert k == g['done_step'] and done.all()
+    rewards = np.array(rewards)
+    assert merr(rewards[:3, 0], g['rewards_first3']) <= 1e-9 and (rewards[-1] == 0.0).all()
+    assert abs(rewards[:, 2].sum() - g['ret']) <= 1e-9 * abs(g['ret'])
+    # a reset() per episode draws a new force each time (task.py:175-184)
+    env2 = ns['B200Lander'](num_envs=4)
+    firsts = []
+    for _ in range(3):
+        env2.reset()
+        firsts.append(env2.step(np.tile(0.0166 * np.ones(4), (4, 1)))[0][:, 1].copy())
+    assert not np.array_equal(firsts[0], firsts[1]) and not np.array_equal(firsts[1], firsts[2])

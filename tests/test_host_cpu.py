@@ -43,11 +43,11 @@ def test_params_struct_matches_header_and_reference_constants(lib):
             p.initial_altitude, p.max_steps) == (100, 30, 100, 45, 10, 10, 1000)
     assert (p.target_radius, p.yaw_penalty_factor, p.xyz_penalty_factor, p.dz_max, p.dz_penalty,
             p.inside_radius_bonus) == (2, 50, 25, 10, 100, 100)
-    assert (p.rho, p.lift_coefficient, p.dynamics_model) == (1.225, 0.4, 0)
-    assert C.sizeof(CopterParams) == 27 * 8 + 8
-    assert [lib.copter_obs_size(v) for v in range(6)] == [10, 6, 2, 12, 6, 2]
-    assert [lib.copter_action_size(v) for v in range(6)] == [4, 2, 1, 4, 2, 1]
-    assert lib.copter_obs_size(6) == -2 and lib.copter_action_size(-1) == -2
+    assert (p.rho, p.lift_coefficient, p.dynamics_model, p.takeoff_target_altitude) == (1.225, 0.4, 0, 5)
+    assert C.sizeof(CopterParams) == 28 * 8 + 8
+    assert [lib.copter_obs_size(v) for v in range(7)] == [10, 6, 2, 12, 6, 2, 10]
+    assert [lib.copter_action_size(v) for v in range(7)] == [4, 2, 1, 4, 2, 1, 4]
+    assert lib.copter_obs_size(7) == -2 and lib.copter_action_size(-1) == -2
     with pytest.raises(TypeError):
         default_params(not_a_field=1)
 
@@ -79,10 +79,10 @@ def test_argument_validation_without_a_gpu(lib):
     from gym_copter_b200._lib import CopterBuffers
     p, b = default_params(), CopterBuffers()
     assert lib.copter_step_f32(C.byref(p), C.byref(b), 16, 0, 0, 1, 0, 1, None) == -1      # null buffers
-    assert lib.copter_reset_f64(C.byref(p), C.byref(b), 16, 0, None) == -1
+    assert lib.copter_reset_f64(C.byref(p), C.byref(b), 16, 0, 0, None) == -1
     assert lib.copter_step_f32(None, C.byref(b), 16, 0, 0, 1, 0, 1, None) == -1
     bad = default_params(max_steps=4000)
-    assert lib.copter_reset_f32(C.byref(bad), C.byref(b), 16, 0, None) == -4
+    assert lib.copter_reset_f32(C.byref(bad), C.byref(b), 16, 0, 0, None) == -4
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')

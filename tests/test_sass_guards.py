@@ -14,7 +14,7 @@ import subprocess
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ACTION = {0: 4, 1: 2, 2: 1, 3: 4, 4: 2, 5: 1}           # variant id -> action size (include/copter_b200.h)
+ACTION = {0: 4, 1: 2, 2: 1, 3: 4, 4: 2, 5: 1, 6: 4}           # variant id -> action size (include/copter_b200.h)
 
 
 @pytest.mark.skipif(shutil.which('cuobjdump') is None, reason='cuobjdump not on PATH')
@@ -40,4 +40,4 @@ def test_step_kernel_issues_all_input_loads_together():
         # nothing in between may wait on a loaded value: no floating-point compare / min-max (the clip)
         assert not [op for op in between if re.match(r'(@!?U?P\d+\s+)?(DSETP|FSETP|FMNMX|DMNMX)', op)], m.group(0)
         seen += 1
-    assert seen == 24          # 6 variants x 2 precisions x with/without statistics
+    assert seen == 28          # 7 variants x 2 precisions x with/without statistics

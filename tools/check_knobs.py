@@ -13,6 +13,8 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from gym_copter_b200.build import NVCC_FLAGS          # noqa: E402
 SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
 COMBOS = [
     ['-DCOPTER_PERSISTENT=1'],
@@ -20,7 +22,8 @@ COMBOS = [
     ['-DCOPTER_TMA_MIN_K=1'],
     ['-DCOPTER_TMA_MIN_K=2', '-DCOPTER_TMA_CLC=0', '-DCOPTER_TMA_CTAS_PER_SM=7'],
     ['-DCOPTER_TIE_LOADS=0', '-DCOPTER_CALM_STREAK=0'],
-    ['-DCOPTER_FAST_SUBSTEP=0', '-DCOPTER_LIBM_ONLY=1'],
+    ['-DCOPTER_FAST_SUBSTEP=0', '-DCOPTER_LIBM_ONLY=1', '-DCOPTER_PAIR_MIN_K=0'],
+    ['-DCOPTER_PAIR_MIN_K=2', '-DCOPTER_PAIR_CTAS_PER_SM=3'],
     ['-DCOPTER_STREAMING=1', '-DCOPTER_K1_SPECIALIZE=0', '-DCOPTER_K_UNROLL=4'],
     ['-DCOPTER_POLICY_POLY_MASK=0x88', '-DCOPTER_POLICY_MT=1'],
     ['-DCOPTER_POLICY_POLY_MASK=0xff', '-DCOPTER_POLICY_POLY_F32X2=0', '-DCOPTER_POLICY_TANH_BF16X2=1'],
@@ -31,8 +34,7 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         procs = []
         for i, flags in enumerate(COMBOS):
-            cmd = ['nvcc', '-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-Xcompiler', '-fPIC', '-shared'] \
-                  + flags + ['-o', os.path.join(tmp, 'lib_%d.so' % i), SRC]
+            cmd = ['nvcc'] + NVCC_FLAGS + flags + ['-o', os.path.join(tmp, 'lib_%d.so' % i), SRC]
             procs.append((flags, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         bad = 0
         for flags, p in procs:

@@ -16,8 +16,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VDIR = os.path.join(ROOT, 'tools', 'variants')
 SRC = os.path.join(ROOT, 'gym_copter_b200', 'csrc', 'copter_kernels.cu')
 
+sys.path.insert(0, ROOT)
+from gym_copter_b200.build import NVCC_FLAGS          # noqa: E402  (the product's own flags: -fmad=false etc.)
+
 VARIANTS = {}
 VARIANTS['current'] = []
+VARIANTS['nopair'] = ['-DCOPTER_PAIR_MIN_K=0']        # K-fused fp32 launches on the one-env-per-thread kernel
+VARIANTS['pair_c3'] = ['-DCOPTER_PAIR_CTAS_PER_SM=3']  # packed kernel at 3 / 5 CTAs per SM (168 / 96 registers)
+VARIANTS['pair_c5'] = ['-DCOPTER_PAIR_CTAS_PER_SM=5']
 VARIANTS['nofast'] = ['-DCOPTER_FAST_SUBSTEP=0']      # K-fused loop without the straight-line substep
 VARIANTS['nostreak'] = ['-DCOPTER_CALM_STREAK=0']     # K-fused loop: flags + hot test + two votes on every substep
 VARIANTS['tma_k2'] = ['-DCOPTER_TMA_MIN_K=2']         # K-fused launches through the TMA-prefetch + cluster-launch-control kernel
@@ -35,8 +41,7 @@ def build():
     procs = []
     for name, flags in VARIANTS.items():
         out = os.path.join(VDIR, 'lib_%s.so' % name)
-        cmd = ['nvcc', '-std=c++17', '-O3', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
-               '-Xcompiler', '-fPIC', '-shared'] + flags + ['-o', out, SRC]
+        cmd = ['nvcc'] + NVCC_FLAGS + flags + ['-o', out, SRC]
         procs.append((name, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         if len(procs) >= 8:
             for n, p in procs:
