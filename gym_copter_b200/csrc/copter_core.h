@@ -9,7 +9,8 @@
 //     (COPTER_NO_CONTRACT is defined by both build recipes; without it this header refuses to compile);
 //   * no libm function whose result depends on the library is used on the fp32 path: sin / cos are the
 //     polynomials below behind an exact fp64 Cody-Waite reduction, sqrt is the IEEE one, and the two
-//     approximate reward helpers of the device path (MUFU.RSQ / MUFU.RCP) live in copter_physics.cuh;
+//     approximate reward helpers of the DEVICE path (MUFU.RSQ / MUFU.RCP, reward_sqrt / reward_div below)
+//     touch the reward only, never the state or a flag;
 //   * the arithmetic is a template over a LANE type L: float, double, or (device only) a packed pair
 //     of floats that steps two envs with fma.rn.f32x2 -- two independent IEEE operations per
 //     instruction, so the packed K-fused loop produces the bits of the scalar one.
@@ -537,21 +538,21 @@ COPTER_HD void motors_from_action(const T* act, T (&m)[4]) {
 // the definition the kernels' fast paths (straight-line substeps, calm streaks, packed pairs, warp
 // votes) must reproduce; the host restatement (oracle/copter_host.cpp) is a loop over it.
 // ------------------------------------------------------------------------------------------
-template <typename T> struct EnvOut { T reward; bool done; int cause; int executed; bool has_final; T final_state[12]; };
+template <typename T> struct EnvOut { T reward; bool done; int cause; int executed; int final_steps; bool has_final; T final_state[12]; };
 
 template <typename T, int VARIANT>
 COPTER_HD void env_launch(const KParams<T>& kp, T (&s)[12], int& st, int& steps, uint32_t& episode, const T (&m)[4],
                           const T (&pert0)[3], int k, bool auto_reset, EnvOut<T>& out) {
     const Forces<T> forces = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
     T pert[3] = {pert0[0], pert0[1], pert0[2]};
-    out.done = false; out.cause = 0; out.executed = 0; out.has_final = false;
+    out.done = false; out.cause = 0; out.executed = 0; out.final_steps = 0; out.has_final = false;
     if (k == 1) {
         Shaping<T> pre_sh = lander_shaping<T>(kp, s);
         T r; bool dn; int cause;
         env_substep<T, VARIANT>(kp, s, st, steps, forces, pert, pre_sh, r, dn, cause);
         out.reward = r; out.executed = 1;
         if (dn) {
-            out.done = true; out.cause = cause; out.has_final = true;
+            out.done = true; out.cause = cause; out.has_final = true; out.final_steps = steps;
             for (int j = 0; j < 12; ++j) out.final_state[j] = s[j];
             if (auto_reset) { reset_state<T>(kp, s, st, steps); episode = (episode + 1) & kp.ep_mask; }
         }
@@ -568,7 +569,7 @@ COPTER_HD void env_launch(const KParams<T>& kp, T (&s)[12], int& st, int& steps,
         run_step<T>(run, na, nc, cause);
         ++out.executed;
         if (dn) {
-            out.done = true; out.cause = cause; out.has_final = true;
+            out.done = true; out.cause = cause; out.has_final = true; out.final_steps = steps;
             out.reward = run_reward<T, VARIANT>(kp, run, s, cause, na, nc, dz_prev);
             for (int q = 0; q < 12; ++q) out.final_state[q] = s[q];
             if (auto_reset) { reset_state<T>(kp, s, st, steps); episode = (episode + 1) & kp.ep_mask; }

@@ -10,6 +10,8 @@
 //
 // The device-side arithmetic (what each function restates, precision) is in copter_physics.cuh.
 
+#include <stdlib.h>
+
 #include "copter_physics.cuh"
 #include "copter_policy.cuh"
 
@@ -1276,6 +1278,17 @@ int resident_grid_for(int64_t n) {
     return (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
 }
 
+// k_substeps threshold of the packed two-env kernel: the build default, or COPTER_B200_PAIR_MIN_K from the environment
+int pair_min_k_setting() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("COPTER_B200_PAIR_MIN_K");
+        v = e ? atoi(e) : COPTER_PAIR_MIN_K;
+        if (v < 0) v = 0;
+    }
+    return v;
+}
+
 template <typename T, int VARIANT>
 int launch_step_v(const KParams<T>& kp, const StepArgs<T>& a, cudaStream_t s) {
     // K-fused launches: TMA-prefetched inputs (every bulk copy needs 16-byte aligned sources; the
@@ -1297,12 +1310,18 @@ int launch_step_v(const KParams<T>& kp, const StepArgs<T>& a, cudaStream_t s) {
         return (int)cudaGetLastError();
     }
 #endif
-    // issue-bound K-fused fp32 launches: two envs per thread on packed fma.rn.f32x2 (copter_step_pair_kernel)
-    if constexpr (COPTER_PAIR_MIN_K > 0 && sizeof(T) == 4) if (a.k >= COPTER_PAIR_MIN_K) {
-        const int grid = (int)((a.n + 2 * kBlock - 1) / (2 * kBlock));
-        if (a.stats) copter_step_pair_kernel<VARIANT, true><<<grid, kBlock, 0, s>>>(kp, a);
-        else         copter_step_pair_kernel<VARIANT, false><<<grid, kBlock, 0, s>>>(kp, a);
-        return (int)cudaGetLastError();
+    // K-fused fp32 launches can take the two-envs-per-thread kernel on packed fma.rn.f32x2
+    // (copter_step_pair_kernel).  Measured, it loses to the one-env-per-thread loop (profiles/README.md:
+    // the loop is bound by register-file operand bandwidth, which FFMA2 does not relieve), so it is off by
+    // default and kept as a run-time A/B: COPTER_B200_PAIR_MIN_K=<k> in the environment sends k_substeps >= k to it.
+    if constexpr (sizeof(T) == 4) {
+        const int pair_min_k = pair_min_k_setting();
+        if (pair_min_k > 0 && a.k >= pair_min_k) {
+            const int grid = (int)((a.n + 2 * kBlock - 1) / (2 * kBlock));
+            if (a.stats) copter_step_pair_kernel<VARIANT, true><<<grid, kBlock, 0, s>>>(kp, a);
+            else         copter_step_pair_kernel<VARIANT, false><<<grid, kBlock, 0, s>>>(kp, a);
+            return (int)cudaGetLastError();
+        }
     }
     if (a.stats) copter_step_kernel<T, VARIANT, true><<<grid_for<copter_step_kernel<T, VARIANT, true>>(a.n), kBlock, 0, s>>>(kp, a);
     else         copter_step_kernel<T, VARIANT, false><<<grid_for<copter_step_kernel<T, VARIANT, false>>(a.n), kBlock, 0, s>>>(kp, a);

@@ -47,7 +47,8 @@ namespace copter {
 #define COPTER_STREAMING 0      // 1: evict-first (ld/st .cs) hints on the state planes
 #endif
 #ifndef COPTER_PAIR_MIN_K
-#define COPTER_PAIR_MIN_K 3     // k_substeps >= this (fp32) use the two-envs-per-thread packed kernel (0: never)
+#define COPTER_PAIR_MIN_K 0     // k_substeps >= this (fp32) use the two-envs-per-thread packed kernel (0: never; run-time override:
+                                // COPTER_B200_PAIR_MIN_K in the environment).  Measured slower than the scalar loop: off.
 #endif
 
 constexpr int kBlock = COPTER_BLOCK;
@@ -101,20 +102,47 @@ __device__ __forceinline__ void store_meta(uint32_t* meta, uint32_t* hi, int64_t
 }
 
 // ------------------------------------------------------------------------------------------
-// F2: a lane of TWO envs, one packed 64-bit register pair per quantity.  Every operation is the
-// sm_100 packed form (FADD2 / FMUL2 / FFMA2: two independent round-to-nearest IEEE operations in one
-// issue slot), so airborne_integrate<F2> produces exactly the bits of two airborne_integrate<float>.
+// F2: a lane of TWO envs, one packed 64-bit register pair per quantity, every operation one FFMA2
+// (fma.rn.f32x2: two independent round-to-nearest IEEE operations in one issue slot), so
+// airborne_integrate<F2> produces exactly the bits of two airborne_integrate<float>.
+// Measured on B200 (tools/microbench/ffma2_rates.cu, profiles/r2_ffma2_rates.txt): FFMA2 issues every
+// 2 cycles per scheduler -- the element rate of scalar FFMA in half the issue slots -- while the packed
+// multiply and add (FMUL2 / FADD2) issue only every ~6.6 cycles.  Products and sums are therefore
+// written as fused operations that are EXACTLY the plain ones: a*b = fma(a, b, -0) (adding -0 changes
+// no value, not even the sign of a zero product) and a+b = fma(a, 1, b).
 // ------------------------------------------------------------------------------------------
+#ifndef COPTER_F2_PLAIN_MUL_ADD
+#define COPTER_F2_PLAIN_MUL_ADD 0     // 1 (A/B knob): FMUL2 / FADD2 for the packed products and sums
+#endif
+// -0 and 1 as the compiler cannot see them (constant memory can be rewritten by the host, so neither
+// nvcc nor ptxas may fold them): with literal constants ptxas turns fma(a, b, -0) straight back into FMUL2
+__constant__ float kF2NegZero = -0.0f;
+__constant__ float kF2One = 1.0f;
 struct F2 {
     float2 v;
     __device__ __forceinline__ F2() {}
     __device__ __forceinline__ explicit F2(float x) { v.x = x; v.y = x; }
     __device__ __forceinline__ F2(float x, float y) { v.x = x; v.y = y; }
 };
-__device__ __forceinline__ F2 operator*(F2 a, F2 b) { F2 r; r.v = __fmul2_rn(a.v, b.v); return r; }
-__device__ __forceinline__ F2 operator+(F2 a, F2 b) { F2 r; r.v = __fadd2_rn(a.v, b.v); return r; }
+__device__ __forceinline__ F2 fma_(F2 a, F2 b, F2 c) {
+    // inline PTX rather than __ffma2_rn: the compiler must not "simplify" the exact forms below back into mul / add
+    F2 r;
+    asm("{\n\t.reg .b64 a, b, c, d;\n\t"
+        "mov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%6, %7};\n\t"
+        "fma.rn.f32x2 d, a, b, c;\n\t"
+        "mov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(r.v.x), "=f"(r.v.y) : "f"(a.v.x), "f"(a.v.y), "f"(b.v.x), "f"(b.v.y), "f"(c.v.x), "f"(c.v.y));
+    return r;
+}
+__device__ __forceinline__ F2 operator*(F2 a, F2 b) {
+    if (COPTER_F2_PLAIN_MUL_ADD) { F2 r; r.v = __fmul2_rn(a.v, b.v); return r; }
+    return fma_(a, b, F2(kF2NegZero));
+}
+__device__ __forceinline__ F2 operator+(F2 a, F2 b) {
+    if (COPTER_F2_PLAIN_MUL_ADD) { F2 r; r.v = __fadd2_rn(a.v, b.v); return r; }
+    return fma_(a, F2(kF2One), b);
+}
 __device__ __forceinline__ F2 operator-(F2 a) { return F2(-a.v.x, -a.v.y); }
-__device__ __forceinline__ F2 fma_(F2 a, F2 b, F2 c) { F2 r; r.v = __ffma2_rn(a.v, b.v, c.v); return r; }
 
 // ------------------------------------------------------------------------------------------
 // The common case of env_advance as straight-line code, for the K-fused loops: an AIRBORNE env that

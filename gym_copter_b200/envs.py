@@ -27,7 +27,7 @@ _OBS_IDX = {'Lander3D': tuple(range(10)), 'Lander2D': (2, 3, 4, 5, 6, 7), 'Lande
             'Takeoff': tuple(range(10))}
 _ACT_SIZE = {'Lander3D': 4, 'Lander2D': 2, 'Lander1D': 1, 'Hover3D': 4, 'Hover2D': 2, 'Hover1D': 1, 'Takeoff': 4}
 # attic/gym_copter/envs/takeoff.py:45-55: starts on the ground (state zeros -> LANDED), no reset perturbation
-_VARIANT_DEFAULTS = {'Takeoff': dict(initial_altitude=0.0, initial_random_force=0.0)}
+_VARIANT_DEFAULTS = {'Takeoff': dict(initial_altitude=0.0, initial_random_force=0.0, fps=50.0)}         # :21 FRAMES_PER_SECOND = 50
 _ALL_NAMES = ['X', 'dX', 'Y', 'dY', 'Z', 'dZ', 'Phi', 'dPhi', 'Theta', 'dTheta', 'Psi', 'dPsi']
 
 

@@ -24,7 +24,7 @@ namespace {
 template <typename T, int VARIANT>
 int64_t step_batch(const KParams<T>& kp, int64_t n, T* state, int32_t* status, int32_t* steps, uint32_t* episode,
                    const T* action, const uint64_t* env_ids, uint64_t seed, const T* init_force, int k, int auto_reset,
-                   float* obs, T* reward, uint8_t* done, uint8_t* cause, int32_t* executed, float* final_obs) {
+                   float* obs, T* reward, uint8_t* done, uint8_t* cause, int32_t* executed, float* final_obs, int32_t* final_steps) {
     constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A, FIRST = Variant<VARIANT>::first;
     int64_t total_executed = 0;
     for (int64_t i = 0; i < n; ++i) {
@@ -46,6 +46,7 @@ int64_t step_batch(const KParams<T>& kp, int64_t n, T* state, int32_t* status, i
         reward[i] = out.reward; done[i] = out.done ? 1 : 0;
         if (cause) cause[i] = (uint8_t)out.cause;
         if (executed) executed[i] = out.executed;
+        if (final_steps) final_steps[i] = out.final_steps;
         total_executed += out.executed;
         if (obs) for (int j = 0; j < O; ++j) obs[(int64_t)O * i + j] = (float)s[FIRST + j];
         if (final_obs && out.has_final) for (int j = 0; j < O; ++j) final_obs[(int64_t)O * i + j] = (float)out.final_state[FIRST + j];
@@ -56,10 +57,10 @@ int64_t step_batch(const KParams<T>& kp, int64_t n, T* state, int32_t* status, i
 template <typename T>
 int64_t step_dispatch(const CopterParams* p, int variant, int wide, int64_t n, T* state, int32_t* status, int32_t* steps,
                       uint32_t* episode, const T* action, const uint64_t* env_ids, uint64_t seed, const T* init_force, int k,
-                      int auto_reset, float* obs, T* reward, uint8_t* done, uint8_t* cause, int32_t* executed, float* final_obs) {
+                      int auto_reset, float* obs, T* reward, uint8_t* done, uint8_t* cause, int32_t* executed, float* final_obs, int32_t* final_steps) {
     if (p->max_steps < 1 || p->max_steps > (wide ? COPTER_MAX_STEPS_LIMIT_WIDE : COPTER_MAX_STEPS_LIMIT)) return -1;
     const KParams<T> kp = make_kparams<T>(*p, wide != 0);
-#define COPTER_HOST_CASE(V) case V: return step_batch<T, V>(kp, n, state, status, steps, episode, action, env_ids, seed, init_force, k, auto_reset, obs, reward, done, cause, executed, final_obs)
+#define COPTER_HOST_CASE(V) case V: return step_batch<T, V>(kp, n, state, status, steps, episode, action, env_ids, seed, init_force, k, auto_reset, obs, reward, done, cause, executed, final_obs, final_steps)
     switch (variant) {
         COPTER_HOST_CASE(COPTER_LANDER3D); COPTER_HOST_CASE(COPTER_LANDER2D); COPTER_HOST_CASE(COPTER_LANDER1D);
         COPTER_HOST_CASE(COPTER_HOVER3D);  COPTER_HOST_CASE(COPTER_HOVER2D);  COPTER_HOST_CASE(COPTER_HOVER1D);
@@ -112,16 +113,16 @@ int copter_host_abi(void) { return COPTER_ABI_VERSION; }
 int64_t copter_host_step_f32(const CopterParams* p, int variant, int wide, int64_t n, float* state, int32_t* status, int32_t* steps,
                              uint32_t* episode, const float* action, const uint64_t* env_ids, uint64_t seed, const float* init_force,
                              int k, int auto_reset, float* obs, float* reward, uint8_t* done, uint8_t* cause, int32_t* executed,
-                             float* final_obs) {
+                             float* final_obs, int32_t* final_steps) {
     return step_dispatch<float>(p, variant, wide, n, state, status, steps, episode, action, env_ids, seed, init_force, k, auto_reset,
-                                obs, reward, done, cause, executed, final_obs);
+                                obs, reward, done, cause, executed, final_obs, final_steps);
 }
 int64_t copter_host_step_f64(const CopterParams* p, int variant, int wide, int64_t n, double* state, int32_t* status, int32_t* steps,
                              uint32_t* episode, const double* action, const uint64_t* env_ids, uint64_t seed, const double* init_force,
                              int k, int auto_reset, float* obs, double* reward, uint8_t* done, uint8_t* cause, int32_t* executed,
-                             float* final_obs) {
+                             float* final_obs, int32_t* final_steps) {
     return step_dispatch<double>(p, variant, wide, n, state, status, steps, episode, action, env_ids, seed, init_force, k, auto_reset,
-                                 obs, reward, done, cause, executed, final_obs);
+                                 obs, reward, done, cause, executed, final_obs, final_steps);
 }
 void copter_host_reset_f32(const CopterParams* p, int variant, int wide, int64_t n, float* state, int32_t* status, int32_t* steps,
                            uint32_t* episode, int keep_episode, float* obs) {

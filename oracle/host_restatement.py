@@ -88,6 +88,7 @@ class HostEnvBatch:
         self.final_obs = np.zeros((n, self.obs_size), np.float32)
         self.reward, self.done = np.zeros(n, self.dtype), np.zeros(n, np.uint8)
         self.cause, self.executed = np.zeros(n, np.uint8), np.zeros(n, np.int32)
+        self.final_steps = np.zeros(n, np.int32)
         self._ever_reset = False
 
     def reset(self, force=None, keep_episode=None):
@@ -107,10 +108,10 @@ class HostEnvBatch:
         executed = fn(C.byref(self.p), self.vid, int(self.wide), C.c_int64(self.n), _p(self.x), _p(self.status), _p(self.steps),
                       _p(self.episode), _p(a), _p(self.env_ids), C.c_uint64(self.seed & 0xFFFFFFFFFFFFFFFF), _p(f),
                       int(k_substeps), int(self.auto_reset), _p(self.obs), _p(self.reward), _p(self.done), _p(self.cause),
-                      _p(self.executed), _p(self.final_obs))
+                      _p(self.executed), _p(self.final_obs), _p(self.final_steps))
         assert executed >= 0
         return self.obs, self.reward, self.done.view(np.bool_), {
-            'cause': self.cause, 'executed': self.executed, 'final_obs': self.final_obs}
+            'cause': self.cause, 'executed': self.executed, 'final_obs': self.final_obs, 'final_steps': self.final_steps}
 
 
 class HostDynamicsBatch:

@@ -17,6 +17,11 @@ the LIVE `_Task` / `Lander`, overriding exactly the three hooks the attic files 
   Hover3D  : attic/gym_copter/envs/hover.py:18-21 + hover3d.py:32-37 (reward == 1, obs all 12)
   Hover2D  : attic/gym_copter/envs/hover2d.py:44-50   (obs state[2:8])
   Hover1D  : attic/gym_copter/envs/hover1d.py:44-50   (obs state[4:6])
+  Takeoff  : attic/gym_copter/envs/takeoff.py:18-91   (its own gym.Env, NOT a _Task: setMotors with the
+             unclipped action whatever the status, reward = change of -|altitude - 5|, never done).  The
+             module it imports (gym_copter.dynamics.djiphantom, setMotors + update) no longer exists; the
+             class below is that file's reset()/step() line for line over the LIVE `Dynamics`, whose
+             setMotors contains what update() used to do.
 """
 
 import os
@@ -149,8 +154,29 @@ def load_reference():
         def _get_motors(self, m):
             return [m[0]] * 4
 
+    class Takeoff:
+        TARGET_ALTITUDE = 5                                             # takeoff.py:20
+        FRAMES_PER_SECOND = 50                                          # takeoff.py:21
+
+        def reset(self):                                                # takeoff.py:45-55
+            self.prev_shaping = None
+            self.dynamics = Dynamics(vehicle_params, self.FRAMES_PER_SECOND)
+            self.dynamics.setState(np.zeros(12))
+            return self.step(np.array([0, 0, 0, 0]))[0]
+
+        def step(self, action):                                         # takeoff.py:57-88
+            d = self.dynamics
+            d.setMotors(action)                                         # (+ d.update() in the attic file)
+            s = d.getState()
+            state = np.array([s[k] for k in ('x', 'dx', 'y', 'dy', 'z', 'dz', 'phi', 'dphi', 'theta', 'dtheta')])
+            altitude = -s['z']
+            shaping = -abs(altitude - self.TARGET_ALTITUDE)
+            reward = (shaping - self.prev_shaping) if (self.prev_shaping is not None) else 0
+            self.prev_shaping = shaping
+            return np.array(state, dtype=np.float32), reward, False, {}
+
     ns = types.SimpleNamespace(
-        Dynamics=Dynamics, vehicle_params=vehicle_params, _Task=_Task,
+        Dynamics=Dynamics, vehicle_params=vehicle_params, _Task=_Task, Takeoff=Takeoff,
         Lander=Lander, Lander3D=Lander, Lander2D=Lander2D, Lander1D=Lander1D,
         Hover3D=Hover3D, Hover2D=Hover2D, Hover1D=Hover1D)
     _cache['ns'] = ns

@@ -12,7 +12,8 @@ one-env-at-a-time loop.  Here, on every action stream, variant and K:
     state (all 12 components), observation, flight status, step counter, episode index, done flag,
     ending cause and terminal observation: identical bits / values, ZERO flips allowed;
     reward: the device takes the two square roots and the quotient of the shaping difference on the
-    MUFU unit (<= 2 ulp each), the host with IEEE sqrt / division: <= 2e-6 relative.
+    MUFU unit (<= 2 ulp each), the host with IEEE sqrt / division: max <= 5e-5 (a few ulps of the larger
+    shaping term where the position and yaw terms cancel; north_star allows 1e-4), mean <= 1e-7.
 The fp64-oracle comparisons to 1e-4 / 1e-9 stay in tests/test_gpu_parity.py.
 """
 import numpy as np
@@ -70,7 +71,7 @@ def assert_same(env, host, term, r, obs, info, h_obs, h_r, h_done, h_info, t):
         assert np.array_equal(bits(info['final_obs'].cpu().numpy()[h_done]), bits(h_info['final_obs'][h_done])), t
     rr = r.cpu().numpy()
     err = np.abs(rr - h_r) / np.maximum(np.abs(h_r), 1.0)
-    assert err.max() <= 2e-6, (t, float(err.max()))
+    assert err.max() <= 5e-5 and err.mean() <= 1e-7, (t, float(err.max()), float(err.mean()))
 
 
 @pytest.mark.parametrize('k', [1, 2, 3, 16])
@@ -83,7 +84,7 @@ def test_fp32_step_kernels_equal_the_host_instantiation(pkg, variant, k):
     kw = dict(max_steps=150) if variant == 'Takeoff' else {}
     env = pkg.CopterVecEnv(variant, N, dtype=torch.float32, seed=seed, env_offset=off, k_substeps=k,
                            report_cause=True, keep_final_obs=True, **kw)
-    hkw = dict(initial_altitude=0.0, initial_random_force=0.0, max_steps=150) if variant == 'Takeoff' else {}
+    hkw = dict(initial_altitude=0.0, initial_random_force=0.0, fps=50.0, max_steps=150) if variant == 'Takeoff' else {}   # the shell's Takeoff defaults
     host = HostEnvBatch(variant, N, OracleParams(**hkw), dtype=np.float32, seed=seed, env_offset=off)
     obs, _ = env.reset()
     assert np.array_equal(bits(obs.cpu().numpy()), bits(host.reset()))
@@ -154,7 +155,7 @@ def test_fp32_rollout_kernel_equals_the_host_instantiation(pkg, source):
         for t in range(T // 3):
             h_obs, h_r, h_done, _ = host.step(acts[t], 1)
             assert np.array_equal(dones[t], h_done), (chunk, t)
-            assert (np.abs(rews[t] - h_r) / np.maximum(np.abs(h_r), 1)).max() <= 2e-6
+            assert (np.abs(rews[t] - h_r) / np.maximum(np.abs(h_r), 1)).max() <= 5e-5
         assert np.array_equal(bits(env.state.cpu().numpy()), bits(host.x))
         assert np.array_equal(env.steps.cpu().numpy(), host.steps) and np.array_equal(env.status.cpu().numpy(), host.status)
         assert np.array_equal(env.episodes.cpu().numpy(), host.episode.astype(np.int64))
@@ -198,3 +199,43 @@ def test_fp32_dynamics_facade_equals_the_host_instantiation(pkg):
         assert np.array_equal(d._ticks.cpu().numpy(), h.ticks)
         assert np.array_equal(bits(d.state.cpu().numpy()), bits(h.x)), t
     assert len(set(h.status.tolist())) >= 3
+
+
+def test_packed_two_env_kernel_is_bit_exact_too():
+    """The A/B kernel (two envs per thread on fma.rn.f32x2, off by default because it is slower): the same
+    bit-for-bit check, in a subprocess because the switch COPTER_B200_PAIR_MIN_K is read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import gym_copter_b200 as g
+from oracle.host_restatement import HostEnvBatch
+sys.path.insert(0, %r)
+from test_gpu_host_exact import mixed_streams, bits
+for variant, A in (('Lander3D', 4), ('Hover2D', 2)):
+    for k in (3, 16):
+        N, T = 2048 + 77, 640 // k
+        act = mixed_streams(np.random.default_rng(k), N, T, A)
+        env = g.CopterVecEnv(variant, N, dtype=torch.float32, seed=9, k_substeps=k, track_returns=True, report_cause=True, keep_final_obs=True)
+        host = HostEnvBatch(variant, N, dtype=np.float32, seed=9)
+        env.reset(); host.reset()
+        ep = 0
+        for t in range(T):
+            obs, r, term, trunc, info = env.step(torch.as_tensor(act[t]))
+            h_obs, h_r, h_done, h_info = host.step(act[t], k)
+            assert np.array_equal(bits(env.state.cpu().numpy()), bits(host.x)), (variant, k, t)
+            assert np.array_equal(term.cpu().numpy(), h_done) and np.array_equal(env.steps.cpu().numpy(), host.steps)
+            assert np.array_equal(env.status.cpu().numpy(), host.status) and np.array_equal(info['cause'].cpu().numpy(), h_info['cause'])
+            assert np.array_equal(bits(obs.cpu().numpy()), bits(h_obs))
+            assert np.array_equal(bits(info['final_obs'].cpu().numpy()[h_done]), bits(h_info['final_obs'][h_done]))
+            assert (np.abs(r.cpu().numpy() - h_r) / np.maximum(np.abs(h_r), 1)).max() <= 5e-5
+            ep += int(h_done.sum())
+        s = env.stats()
+        assert s['episodes'] == ep and ep > N // 2, (s['episodes'], ep)
+print('PAIR-OK')
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, COPTER_B200_PAIR_MIN_K='3'),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'PAIR-OK' in r.stdout, (r.stdout[-500:], r.stderr[-1500:])

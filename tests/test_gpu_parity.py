@@ -5,10 +5,16 @@ the oracle and the golden vectors recorded from the reference.
 Tolerances (BASELINE.json north_star / SURVEY.md 8d), metric err = |a - ref| / max(|ref|, 1)
 per component:
   fp64 path: state / obs / reward <= 1e-9, done flags and step counters bit-exact;
-  fp32 path: state / obs <= 1e-4 over 1000 steps, reward <= 1e-4 (same metric), flags
-             bit-exact except where an fp32 rounding flips a threshold comparison one step
-             early/late -- such envs are counted (must stay below 1 % of episodes) and leave
-             the comparison from that step on, since their episode timeline differs.
+  fp32 path: state / obs <= 1e-4 over 1000 steps, reward <= 1e-4 (same metric).  Discrete outputs:
+             the fp32 kernels are bit-exact -- zero flips -- against the fp32 CPU instantiation of
+             their own arithmetic (tests/test_gpu_host_exact.py).  Against the fp64 oracle HERE an
+             fp32 rounding can flip a threshold comparison one step early/late; that rate is
+             measured per action stream on the CPU (tests/test_host_restatement.py, tools/flip_rates.py,
+             profiles/r2_fp32_flip_rates.json: 2.2e-3 per episode on the constant-thrust stream, whose
+             every episode ends by crossing z = 0; <= 2.4e-4 on the others).  Such envs are counted
+             (bound: 0.6 % of episodes, i.e. the measured worst case with margin; every test appends
+             its count to gpurun_out/r2_tracker_flips.jsonl) and leave the comparison from that step
+             on, since their episode timeline differs.
 Saturating action stream.  Actions ~ U(-1,1) command up to 60x hover thrust (SURVEY.md
 section 6 "scale note"): accelerations of 1e4 m/s^2, velocity swings of > 100 m/s per step,
 episodes of 5-40 steps.  There every fp32 quantity carries an absolute error of 2^-24 times
@@ -108,7 +114,8 @@ class Tracker:
             self.max_state = max(self.max_state, self._err(state, o_state, scale))
             self.max_obs = max(self.max_obs, self._err(obs, o_obs, scale))
 
-    def finish(self, min_episodes=1):
+    def finish(self, min_episodes=1, what=''):
+        self.record(what)
         assert self.max_state <= self.tol, self.max_state
         assert self.max_obs <= max(self.tol, self.F32_EPS), self.max_obs
         assert self.max_reward <= self.tol, self.max_reward
@@ -117,7 +124,20 @@ class Tracker:
         if self.exact:
             assert self.flips == 0
         else:
-            assert self.flips <= max(1, 0.01 * self.episodes), (self.flips, self.episodes)
+            assert self.flips <= max(2, 0.006 * self.episodes), (self.flips, self.episodes)
+
+    def record(self, what):
+        """One line per comparison into gpurun_out/ (when that directory exists: runs under gpurun)."""
+        import inspect
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+        if not os.path.isdir(out):
+            return
+        caller = what or next((f.function for f in inspect.stack()[2:] if f.function.startswith('test_')), '?')
+        with open(os.path.join(out, 'r2_tracker_flips.jsonl'), 'a') as f:
+            f.write(json.dumps({'test': caller, 'fp64': self.exact, 'episodes': self.episodes, 'flips': self.flips,
+                                'flips_per_episode': self.flips / max(self.episodes, 1), 'max_state': self.max_state,
+                                'max_state_per_component': self.max_component, 'max_obs': self.max_obs,
+                                'max_reward': self.max_reward}) + '\n')
 
 
 # ---------------------------------------------------------------------------------------
@@ -598,17 +618,19 @@ def test_random_shapes_vs_oracle(pkg):
         orc = EnvBatch(variant, n, seed=seed, env_offset=off, auto_reset=auto)
         assert np.array_equal(env.reset()[0].cpu().numpy(), orc.reset())
         rng = np.random.default_rng(seed % 2 ** 32)
-        tr = Tracker(n, dtype, saturating=np.ones(n, bool))
+        sat = rng.random(n) < 0.3                   # these envs get U(-1,1) commands throughout; the others stay near hover
+        tr = Tracker(n, dtype, saturating=sat)      # and are held to the per-component 1e-4
         for t in range(12):
-            a = np.where(rng.random((n, 1)) < 0.3, rng.uniform(-1, 1, (n, env.action_size)),
+            a = np.where(sat[:, None], rng.uniform(-1, 1, (n, env.action_size)),
                          HOVER * (1 + 0.2 * rng.standard_normal((n, env.action_size)))).astype(np.float32)
             obs, r, term, _, _ = env.step(a)
             o_obs, o_r, o_done, _ = orc.step(a.astype(np.float64), k_substeps=k)
             tr.compare(term.cpu().numpy(), r.cpu().numpy(), env.state.cpu().numpy(), obs.cpu().numpy(),
                        [env.steps.cpu().numpy(), env.status.cpu().numpy(), env.episodes.cpu().numpy()],
                        o_done, o_r, orc.dyn.x, o_obs, [orc.steps, orc.dyn.status, orc.episode])
+        tr.record('test_random_shapes_vs_oracle')
         assert tr.max_state <= tr.tol and tr.max_reward <= tr.tol and tr.max_obs <= max(tr.tol, tr.F32_EPS)
-        assert tr.flips == 0 if f64 else tr.flips <= max(1, n // 50)
+        assert tr.flips == 0 if f64 else tr.flips <= 2
 
     check()
 

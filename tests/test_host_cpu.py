@@ -200,7 +200,7 @@ def test_gymnasium_shell_is_guarded_and_registers():
         from oracle import refshim
         refshim._install_gymnasium_shim()
         ids = gym_compat.register_envs()
-        assert 'gym_copter_b200/Lander-v0' in ids and 'gym_copter_b200/Hover3D-v0' in ids and len(ids) == 7
+        assert 'gym_copter_b200/Lander-v0' in ids and 'gym_copter_b200/Hover3D-v0' in ids and 'gym_copter_b200/Takeoff-v0' in ids and len(ids) == 8
         reg = sys.modules['gymnasium.envs.registration'].registry
         assert reg['gym_copter_b200/Lander-v0']['max_episode_steps'] == 1000
     finally:
@@ -208,6 +208,69 @@ def test_gymnasium_shell_is_guarded_and_registers():
             del sys.modules[k]
         if had is not None:
             sys.modules['gymnasium'] = had
+
+
+def test_vector_env_contract_over_a_stand_in():
+    """gymnasium's VectorEnv contract (>= 1.0) as make_vector_env's adapter serves it: same-step autoreset
+    declared in metadata, terminal observation under info['final_obs'] with its mask, terminal info under
+    info['final_info'], the step limit reported as a truncation and never also as a termination.  The
+    wrapped env is a stand-in with CopterVecEnv's return shapes, so this runs without a GPU; the same
+    adapter over the real env is exercised in tests/test_gpu_rollout.py."""
+    import types
+    from gym_copter_b200 import gym_compat
+    from gym_copter_b200._lib import CAUSE_TIMEOUT, CAUSE_OOB
+
+    class FakeVec:
+        num_envs = 4
+        metadata = {'render_modes': ['human'], 'render_fps': 100}
+        single_observation_space = single_action_space = observation_space = action_space = object()
+        closed = 0
+
+        def reset(self, seed=None, options=None):
+            self.seed = seed
+            return torch.zeros(4, 10), {}
+
+        def step(self, a):
+            cause = torch.tensor([0, CAUSE_TIMEOUT, CAUSE_OOB, 0], dtype=torch.uint8)
+            done = torch.tensor([False, True, True, False])
+            return (torch.ones(4, 10), torch.arange(4.0), done, (cause & CAUSE_TIMEOUT) != 0,
+                    {'cause': cause, 'final_obs': torch.full((4, 10), 7.0)})
+
+        def render(self):
+            return None
+
+        def close(self):
+            self.closed += 1
+
+        def stats(self):
+            return 'forwarded'
+
+    v = gym_compat.VectorEnvAdapter(FakeVec())
+    assert v.num_envs == 4 and v.metadata['autoreset_mode'] in ('SameStep', getattr(v.metadata['autoreset_mode'], 'SAME_STEP', 'SameStep'))
+    obs, info = v.reset(seed=3)
+    assert info == {} and v.env.seed == 3 and obs.shape == (4, 10)
+    obs, r, term, trunc, info = v.step(torch.zeros(4, 4))
+    assert term.tolist() == [False, False, True, False] and trunc.tolist() == [False, True, False, False]
+    assert not (term & trunc).any()
+    assert info['_final_obs'].tolist() == [False, True, True, False] and (info['final_obs'][info['_final_obs']] == 7).all()
+    assert info['_final_info'].tolist() == [False, True, True, False] and info['final_info']['cause'][2] == CAUSE_OOB
+    assert (obs == 1).all()                                   # the NEW episode's first observation (same-step reset)
+    assert v.stats() == 'forwarded' and v.unwrapped is v
+    v.close(); v.close()
+    assert v.env.closed == 1
+    # with a gymnasium that has vector.AutoresetMode the enum member is used
+    import sys
+    fake = types.ModuleType('gymnasium')
+    fake.vector = types.SimpleNamespace(AutoresetMode=types.SimpleNamespace(SAME_STEP='enum-member'))
+    had = sys.modules.get('gymnasium')
+    sys.modules['gymnasium'] = fake
+    try:
+        assert gym_compat.VectorEnvAdapter(FakeVec()).metadata['autoreset_mode'] == 'enum-member'
+    finally:
+        if had is not None:
+            sys.modules['gymnasium'] = had
+        else:
+            del sys.modules['gymnasium']
 
 
 def test_integration_md_stub_matches_the_binding():

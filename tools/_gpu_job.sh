@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv | tail -2
-timeout 900 python -m pytest tests/test_gpu_host_exact.py -m gpu -x -q > gpurun_out/pytest_exact.log 2>&1; echo "exact exit $?"; tail -5 gpurun_out/pytest_exact.log
-timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_gpu_host_exact.py > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -8 gpurun_out/pytest_gpu.log
-timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -4 gpurun_out/smoke.log
-for k in 1 4 16; do echo "== K=$k"; timeout 600 python tools/sweep.py run --k $k 2>&1 | cut -c1-200; done > gpurun_out/sweep_pair.txt 2>&1; cat gpurun_out/sweep_pair.txt
+./tools/microbench/ffma2_rates > gpurun_out/ffma2_rates.txt 2>&1; grep -E "3reg|2reg|ILP 8" gpurun_out/ffma2_rates.txt | tail -30
+timeout 900 python -m pytest tests/test_gpu_host_exact.py -m gpu -q > gpurun_out/pytest_exact.log 2>&1; echo "exact exit $?"; tail -5 gpurun_out/pytest_exact.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:copter_step -s 2 -c 1 -o gpurun_out/prof_k16_scalar -f python tools/profile_k.py 16 > gpurun_out/ncu_k16_scalar.log 2>&1; echo "ncu scalar exit $?"
+COPTER_B200_PAIR_MIN_K=3 timeout 600 ncu --set full --clock-control none --import-source on -k regex:copter_step -s 2 -c 1 -o gpurun_out/prof_k16_pair -f python tools/profile_k.py 16 > gpurun_out/ncu_k16_pair.log 2>&1; echo "ncu pair exit $?"
+timeout 900 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_try.json 2> gpurun_out/bench_try.err; echo "bench exit $?"; cut -c1-1500 gpurun_out/bench_try.json; tail -5 gpurun_out/bench_try.err

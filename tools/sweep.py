@@ -22,8 +22,9 @@ from gym_copter_b200.build import NVCC_FLAGS          # noqa: E402  (the product
 VARIANTS = {}
 VARIANTS['current'] = []
 VARIANTS['nopair'] = ['-DCOPTER_PAIR_MIN_K=0']        # K-fused fp32 launches on the one-env-per-thread kernel
-VARIANTS['pair_c3'] = ['-DCOPTER_PAIR_CTAS_PER_SM=3']  # packed kernel at 3 / 5 CTAs per SM (168 / 96 registers)
-VARIANTS['pair_c5'] = ['-DCOPTER_PAIR_CTAS_PER_SM=5']
+VARIANTS['pair_plainmul'] = ['-DCOPTER_F2_PLAIN_MUL_ADD=1']   # packed kernel with FMUL2 / FADD2 instead of FFMA2-only
+VARIANTS['pair_c5'] = ['-DCOPTER_PAIR_CTAS_PER_SM=5']         # packed kernel at 5 CTAs per SM (<= 96 registers)
+VARIANTS['pair_k2'] = ['-DCOPTER_PAIR_MIN_K=2']               # packed kernel from K = 2 on
 VARIANTS['nofast'] = ['-DCOPTER_FAST_SUBSTEP=0']      # K-fused loop without the straight-line substep
 VARIANTS['nostreak'] = ['-DCOPTER_CALM_STREAK=0']     # K-fused loop: flags + hot test + two votes on every substep
 VARIANTS['tma_k2'] = ['-DCOPTER_TMA_MIN_K=2']         # K-fused launches through the TMA-prefetch + cluster-launch-control kernel
