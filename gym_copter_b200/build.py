@@ -11,7 +11,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 SRC = [os.path.join(PKG, 'csrc', 'copter_kernels.cu')]
 HDR = [os.path.join(ROOT, 'include', 'copter_b200.h'), os.path.join(PKG, 'csrc', 'copter_physics.cuh'), os.path.join(PKG, 'csrc', 'copter_core.h'),
-       os.path.join(PKG, 'csrc', 'copter_policy.cuh')]
+       os.path.join(PKG, 'csrc', 'copter_policy.cuh'), os.path.join(PKG, 'csrc', 'copter_policy_tc.cuh')]
 LIB = os.path.join(PKG, 'libcopter_b200.so')
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-fmad=false", "-DCOPTER_NO_CONTRACT=1", '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',

@@ -14,6 +14,7 @@
 
 #include "copter_physics.cuh"
 #include "copter_policy.cuh"
+#include "copter_policy_tc.cuh"
 
 namespace {
 
@@ -1482,9 +1483,37 @@ int persistent_grid_for(int64_t n) {
     return (int)(tiles < cap ? tiles : cap);
 }
 
+// Which policy kernel: 1 = tcgen05 / TMEM (copter_policy_tc.cuh), 0 = warp-level mma.sync (copter_policy.cuh).
+// COPTER_B200_POLICY_TC in the environment overrides the build default (A/B runs, tests of both).
+#ifndef COPTER_POLICY_TC
+#define COPTER_POLICY_TC 1
+#endif
+int policy_tc_setting() {
+    const char* e = getenv("COPTER_B200_POLICY_TC");        // read on every call: tests and A/B runs flip it inside one process
+    return e ? (atoi(e) != 0) : COPTER_POLICY_TC;
+}
+
 template <int VARIANT>
 int launch_policy_v(const PolicyArgs& a, cudaStream_t s) {
     using V = Variant<VARIANT>;
+    if (policy_tc_setting()) {
+        tc::Args t;
+        t.state = a.state; t.stride = a.stride; t.n = a.n;
+        t.w1 = a.w.w1; t.b1 = a.w.b1; t.w2 = a.w.w2; t.b2 = a.w.b2; t.w3 = a.w.w3; t.b3 = a.w.b3;
+        t.out_scale = a.w.out_scale; t.out_offset = a.w.out_offset; t.action = a.action;
+        constexpr auto kernel = tc::copter_mlp_policy_tc_kernel<V::first, V::O, V::A>;
+        constexpr int smem = (int)sizeof(tc::Smem) + 128;                     // dynamic: past the 48 KB static limit
+        static bool configured[kMaxDevices] = {false};
+        const int dev = current_device();
+        if (!configured[dev]) {
+            if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return (int)cudaGetLastError();
+            configured[dev] = true;
+        }
+        const int64_t tiles = (a.n + tc::kTile - 1) / tc::kTile, pairs = (tiles + tc::kSlots - 1) / tc::kSlots;
+        const int64_t cap = (int64_t)sm_count() * COPTER_POLICY_TC_CTAS_PER_SM;
+        kernel<<<(int)(pairs < cap ? pairs : cap), tc::kThreads, smem, s>>>(t);
+        return (int)cudaGetLastError();
+    }
     copter_mlp_policy_kernel<V::first, V::O, V::A><<<persistent_grid_for<copter_mlp_policy_kernel<V::first, V::O, V::A>>(a.n), 128, 0, s>>>(a);
     return (int)cudaGetLastError();
 }

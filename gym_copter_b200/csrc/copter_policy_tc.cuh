@@ -1,0 +1,391 @@
+// copter_policy_tc.cuh -- the tanh MLP policy of BASELINE.json configs[4] (O -> 64 -> 64 -> A) on the
+// 5th-generation tensor cores: tcgen05.mma with the accumulators in tensor memory (TMEM).
+//
+// A tile is 128 envs.  Epilogue thread t owns env t of the tile AND lane t of tensor memory, so a layer is:
+//   the MMA warp's elected lane issues the layer's MMAs (A = the tile's activations in shared memory,
+//   B = the layer's weights in shared memory, D = 128 x 64 fp32 in TMEM)  ->  tcgen05.commit on an mbarrier
+//   ->  every epilogue thread pulls ITS OWN row of D out of TMEM (tcgen05.ld 32x32b), applies tanh, rounds
+//   to bf16 and writes the row back to shared memory as the next layer's A operand  ->  mbarrier arrive.
+// The epilogue warps issue no MMA, no fragment loads and no bias adds (the biases ride along as one extra
+// K-step: a constant A tile of ones times a B tile holding each bias split into two bf16 halves, hi + lo,
+// so the bias keeps ~16 bits).  What is left per env is 132 tanh + 66 packs + the TMEM loads; the floor is
+// the MUFU pipe, and because three quarters of the issue slots and the whole FMA pipe are free here, a
+// quarter of the hidden tanh are evaluated as a polynomial on the FMA pipe instead (COPTER_POLICY_TC_POLY).
+//
+// Operand layout: the canonical K-major, no-swizzle UMMA layout -- 8-row x 16-byte "core matrices" of
+// 128 contiguous bytes; core matrices adjacent in K are LBO = 128 B apart, 8-row groups SBO = (K/8) x
+// 128 B apart.  A thread writing its own 128-byte activation row therefore writes eight 16-byte chunks
+// 128 B apart; consecutive threads are 16 B apart inside a core matrix, so a warp's store is conflict-free.
+// TMEM: 64 hidden + 16 output accumulator columns per tile in flight; with one tile in flight per CTA
+// (128 columns allocated) four CTAs share an SM's 512 columns and overlap one another's phases.
+// Measured history and the A/B against the warp-MMA kernel (copter_policy.cuh): the comment on the kernel.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace copter {
+namespace tc {
+
+constexpr int kTile = 128, kH = 64, kK1 = 16, kN3 = 16;
+#ifndef COPTER_POLICY_TC_SLOTS
+#define COPTER_POLICY_TC_SLOTS 1             // tiles in flight per CTA
+#endif
+constexpr int kSlots = COPTER_POLICY_TC_SLOTS;
+static_assert(kSlots >= 1 && kSlots <= 3, "TMEM budget: 64 hidden + 16 output columns per slot, <= 256 columns per CTA");
+// TMEM columns of a CTA: the slots' hidden accumulators (64 columns each) first, then their output accumulators (16 each)
+constexpr uint32_t kTmemCols = kSlots == 1 ? 128 : 256;          // tcgen05.alloc takes powers of two
+__host__ __device__ constexpr uint32_t col_hidden(int slot) { return 64u * slot; }
+__host__ __device__ constexpr uint32_t col_out(int slot) { return 64u * kSlots + 16u * slot; }
+
+// element offset of (row r, column k) in a canonical K-major tile with KC = K/8 chunks per row
+__device__ __forceinline__ int canon(int r, int k, int KC) { return (((r >> 3) * KC + (k >> 3)) << 6) + ((r & 7) << 3) + (k & 7); }
+
+struct alignas(128) SlotSmem {
+    __nv_bfloat16 a1[kTile * kK1];       // layer 1 activations: the observation rows
+    __nv_bfloat16 a[kTile * kH];         // layer 2 / layer 3 activations
+};
+struct alignas(128) Smem {
+    __nv_bfloat16 w1[kH * kK1];          // layer 1 weights  [64 x 16]  (columns OBS.. are zero, 14 / 15 carry the bias hi / lo)
+    __nv_bfloat16 w2[kH * kH];           // layer 2 weights  [64 x 64]
+    __nv_bfloat16 b2[kH * kK1];          // layer 2 bias step [64 x 16] (column 0 = hi, 1 = lo)
+    __nv_bfloat16 w3[kN3 * kH];          // layer 3 weights  [16 x 64]  (rows ACT.. are zero)
+    __nv_bfloat16 b3[kN3 * kK1];         // layer 3 bias step [16 x 16]
+    __nv_bfloat16 ones[kTile * kK1];     // A tile of the bias steps: columns 0, 1 = 1
+    SlotSmem slot[kSlots];               // kSlots tiles in flight per CTA (see the kernel)
+    uint64_t done[kSlots];               // MMA warp -> epilogue warps: the slot's accumulator is complete (tcgen05.commit)
+    uint64_t ready[kSlots];              // epilogue threads -> MMA warp: the slot's next A tile is in shared memory (128 arrivals)
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor: canonical K-major, SWIZZLE_NONE, version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(const void* tile, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr(tile) >> 4) & 0x3FFFu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24); }
+
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem()  { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 16 consecutive fp32 columns of this thread's TMEM lane (asynchronous: tmem_wait() before the values are used)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+    tmem_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+__device__ __forceinline__ float tanh_mufu(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// this thread's hidden accumulator row (64 columns of TMEM) -> tanh -> bf16 -> its row of the A tile.
+// TMEM is read at 64 B per clock per SM (B300_MICROARCH.md): the 32 KB of a tile's hidden accumulator
+// take as long to read (512 cycles) as its 8192 tanh take on the four MUFU pipes, so the two must
+// overlap: the load of chunk q + 1 is in flight while the tanh of chunk q issue (tcgen05.wait::ld waits
+// for every outstanding load, so it is placed after the next load has been issued AND the previous
+// chunk's work is done -- by then the load has landed).
+// tanh on the FMA pipe: clamp to |x| <= 3.25 and evaluate the odd degree-13 polynomial x P(x^2) fitted in
+// tools/fit_tanh_poly.py (copter_policy.cuh: tanh_poly_coef; |error| <= 2.0e-3, inside the half-ulp of the bf16
+// rounding that follows).  In this kernel the warps issue no MMAs, so three quarters of the issue slots and
+// the whole FMA pipe are idle while the MUFU pipe is the floor: COPTER_POLICY_TC_POLY of every 16 hidden
+// activations take this route (the FlashAttention-4 exp2 trick, applied to tanh).
+#ifndef COPTER_POLICY_TC_POLY
+#define COPTER_POLICY_TC_POLY 4         // measured, 2^23 envs: 0: 0.375 ms, 4: 0.344 ms, 6: 0.348 ms, 8: 0.380 ms (warp-MMA kernel: 0.358 ms)
+#endif
+__device__ __forceinline__ float tanh_fma(float x) {
+    x = fminf(fmaxf(x, -kTanhClamp), kTanhClamp);
+    const float u = x * x;
+    float p = tanh_poly_coef(6);
+#pragma unroll
+    for (int k = 5; k >= 0; --k) p = fmaf(p, u, tanh_poly_coef(k));
+    return p * x;
+}
+template <int NCHUNK>      // NCHUNK chunks of 16 columns starting at column col0 (the row's 64 columns may be split between two threads)
+__device__ __forceinline__ void hidden_epilogue(uint32_t taddr_row, __nv_bfloat16* a_tile, int row, int col0) {
+    uint32_t r[2][16];
+    tmem_ld16(taddr_row + col0, r[0]);
+#pragma unroll
+    for (int q = 0; q < NCHUNK; ++q) {
+        tmem_wait();                                               // chunk q has landed
+        if (q + 1 < NCHUNK) tmem_ld16(taddr_row + col0 + 16 * (q + 1), r[(q + 1) & 1]);
+        float y[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float x = __uint_as_float(r[q & 1][j]);
+            // the polynomial lanes are spread over the chunk so that the two pipes interleave
+            const bool poly = COPTER_POLICY_TC_POLY > 0 && ((j * COPTER_POLICY_TC_POLY) % 16) < COPTER_POLICY_TC_POLY;
+            y[j] = poly ? tanh_fma(x) : tanh_mufu(x);
+        }
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = pack2(y[2 * j], y[2 * j + 1]);
+        *reinterpret_cast<uint4*>(a_tile + canon(row, col0 + 16 * q, kH / 8)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(a_tile + canon(row, col0 + 16 * q + 8, kH / 8)) = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
+// Weights -> shared memory in the canonical layout, biases split into bf16 hi + lo.  Whole CTA; sync after.
+template <int OBS, int ACT>
+__device__ __forceinline__ void load_weights(Smem& sm, const float* w1, const float* b1, const float* w2, const float* b2,
+                                             const float* w3, const float* b3) {
+    const __nv_bfloat16 zero = __float2bfloat16(0.0f), one = __float2bfloat16(1.0f);
+    auto hi = [](float b) { return __float2bfloat16(b); };
+    auto lo = [](float b) { return __float2bfloat16(b - __bfloat162float(__float2bfloat16(b))); };
+    for (int e = threadIdx.x; e < kH * kK1; e += blockDim.x) {
+        const int n = e / kK1, k = e % kK1;
+        sm.w1[canon(n, k, kK1 / 8)] = k < OBS ? __float2bfloat16(w1[n * OBS + k]) : (k == 14 ? hi(b1[n]) : (k == 15 ? lo(b1[n]) : zero));
+        sm.b2[canon(n, k, kK1 / 8)] = k == 0 ? hi(b2[n]) : (k == 1 ? lo(b2[n]) : zero);
+    }
+    for (int e = threadIdx.x; e < kH * kH; e += blockDim.x) {
+        const int n = e / kH, k = e % kH;
+        sm.w2[canon(n, k, kH / 8)] = __float2bfloat16(w2[n * kH + k]);
+    }
+    for (int e = threadIdx.x; e < kN3 * kH; e += blockDim.x) {
+        const int n = e / kH, k = e % kH;
+        sm.w3[canon(n, k, kH / 8)] = n < ACT ? __float2bfloat16(w3[n * kH + k]) : zero;
+    }
+    for (int e = threadIdx.x; e < kN3 * kK1; e += blockDim.x) {
+        const int n = e / kK1, k = e % kK1;
+        sm.b3[canon(n, k, kK1 / 8)] = (n < ACT && k == 0) ? hi(b3[n]) : ((n < ACT && k == 1) ? lo(b3[n]) : zero);
+    }
+    for (int e = threadIdx.x; e < kTile * kK1; e += blockDim.x) {
+        const int r = e / kK1, k = e % kK1;
+        sm.ones[canon(r, k, kK1 / 8)] = k < 2 ? one : zero;
+    }
+}
+
+struct Args {
+    const float* state; int64_t stride, n;           // fp32 state planes [3][stride][4]
+    const float *w1, *b1, *w2, *b2, *w3, *b3;
+    float out_scale, out_offset;
+    float* action;                                   // [n][ACT]
+};
+
+// One elected thread issues the MMAs of layer `layer` (1..3) of a slot and commits them to the slot's mbarrier.
+__device__ __forceinline__ void issue_layer(Smem& sm, int slot, int layer, uint32_t tmem_base) {
+    constexpr uint32_t kLBO = 128, kSBO16 = (kK1 / 8) * 128, kSBO64 = (kH / 8) * 128, kStep = 256;   // one K = 16 step = two chunks
+    constexpr uint32_t idesc64 = make_idesc(kH), idesc16 = make_idesc(kN3);
+    SlotSmem& ss = sm.slot[slot];
+    fence_after_sync();
+    if (layer == 1) {            // D[128 x 64] = A1[128 x 16] W1^T (bias in columns 14, 15)
+        mma_bf16(tmem_base + col_hidden(slot), make_desc(ss.a1, kLBO, kSBO16), make_desc(sm.w1, kLBO, kSBO16), idesc64, 0u);
+    } else if (layer == 2) {     // D[128 x 64] = A[128 x 64] W2^T + ones b2^T
+#pragma unroll
+        for (int j = 0; j < kH / 16; ++j)
+            mma_bf16(tmem_base + col_hidden(slot), make_desc(reinterpret_cast<const char*>(ss.a) + j * kStep, kLBO, kSBO64),
+                     make_desc(reinterpret_cast<const char*>(sm.w2) + j * kStep, kLBO, kSBO64), idesc64, j > 0 ? 1u : 0u);
+        mma_bf16(tmem_base + col_hidden(slot), make_desc(sm.ones, kLBO, kSBO16), make_desc(sm.b2, kLBO, kSBO16), idesc64, 1u);
+    } else {                     // D[128 x 16] = A[128 x 64] W3^T + ones b3^T
+#pragma unroll
+        for (int j = 0; j < kH / 16; ++j)
+            mma_bf16(tmem_base + col_out(slot), make_desc(reinterpret_cast<const char*>(ss.a) + j * kStep, kLBO, kSBO64),
+                     make_desc(reinterpret_cast<const char*>(sm.w3) + j * kStep, kLBO, kSBO64), idesc16, j > 0 ? 1u : 0u);
+        mma_bf16(tmem_base + col_out(slot), make_desc(sm.ones, kLBO, kSBO16), make_desc(sm.b3, kLBO, kSBO16), idesc16, 1u);
+    }
+    mma_commit(&sm.done[slot]);
+}
+
+// this thread's observation -> its row of the slot's layer-1 A tile (16 bf16: OBS values, zeros, 1, 1)
+template <int FIRST, int OBS>
+__device__ __forceinline__ void write_obs_row(SlotSmem& ss, int row, const float4 (&p)[3]) {
+    const float s[12] = {p[0].x, p[0].y, p[0].z, p[0].w, p[1].x, p[1].y, p[1].z, p[1].w, p[2].x, p[2].y, p[2].z, p[2].w};
+    float x[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = j < OBS ? s[(FIRST + j) % 12] : ((j == 14 || j == 15) ? 1.0f : 0.0f);
+    *reinterpret_cast<uint4*>(ss.a1 + canon(row, 0, kK1 / 8)) = make_uint4(pack2(x[0], x[1]), pack2(x[2], x[3]), pack2(x[4], x[5]), pack2(x[6], x[7]));
+    *reinterpret_cast<uint4*>(ss.a1 + canon(row, 8, kK1 / 8)) = make_uint4(pack2(x[8], x[9]), pack2(x[10], x[11]), pack2(x[12], x[13]), pack2(x[14], x[15]));
+    fence_async_smem();
+}
+
+__device__ __forceinline__ void tmem_alloc(Smem& sm) {         // warp 0, converged
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_addr(&sm.tmem_base)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free(uint32_t base) {     // warp 0, converged
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(base), "n"(kTmemCols) : "memory");
+}
+
+#ifndef COPTER_POLICY_TC_SPLIT
+#define COPTER_POLICY_TC_SPLIT 1             // epilogue threads per env row: 1, or 2 (each takes 32 of the 64 hidden columns)
+#endif
+#ifndef COPTER_POLICY_TC_CTAS_PER_SM
+#define COPTER_POLICY_TC_CTAS_PER_SM (COPTER_POLICY_TC_SLOTS == 1 ? (COPTER_POLICY_TC_SPLIT == 1 ? 4 : 3) : 2)   // x kTmemCols <= the SM's 512 TMEM columns
+#endif
+constexpr int kSplit = COPTER_POLICY_TC_SPLIT;
+constexpr int kEpilogueThreads = kTile * kSplit;
+constexpr int kThreads = kEpilogueThreads + 32;      // the epilogue warps + the MMA warp
+
+// state planes -> action rows.  Persistent, warp-specialised CTAs (weights converted once per CTA), 128 envs
+// per tile, kSlots tiles in flight per CTA.
+//   epilogue warps   kSplit threads per env row (a warp may only touch the TMEM lanes 32 (warp % 4) .. + 31, so
+//              with kSplit = 2 warps w and w + 4 share a lane quarter and split the 64 hidden columns): pull
+//              the accumulator out of TMEM, tanh, bf16, write it to shared memory as the next layer's A
+//              operand, arrive on ready[slot]; after layer 3 the first thread of a row stores its action
+//              and puts the NEXT tile's observation row in place.  They never wait for one another: the only
+//              thing a thread waits for is done[slot] of the layer it is about to read.
+//   last warp  one elected lane: waits for ready[slot] (all epilogue threads), issues the layer's
+//              tcgen05.mma, commits them to done[slot].
+// The MUFU pipe is the floor (132 tanh per env) and what keeps it busy is WARPS: every wait in an epilogue
+// warp (mbarrier, TMEM load, shared-memory fence) has to be covered by another warp's tanh.
+// History, 2^23 envs (warp-MMA kernel of copter_policy.cuh: 0.358 ms, XU 72 %):
+//   one tile per CTA, __syncthreads + thread 0 issuing, 4 CTAs/SM          0.627 ms  (CTAs march in step)
+//   two tiles in flight per CTA, still __syncthreads, 2 CTAs/SM            0.484 ms
+//   + MMA warp and mbarriers instead of __syncthreads                      0.428 ms  (XU 60 %; three tiles: 0.437)
+//   one tile in flight, 4 CTAs/SM (16 epilogue warps per SM instead of 8)  0.374 ms
+//   two threads per row: 3 CTAs/SM (24 epilogue warps) 0.406 ms, 4 CTAs/SM (32 warps, 56 registers) 0.387 ms: more warps do not help
+//   one tile in flight, 4 CTAs/SM, 4 of every 16 hidden tanh on the FMA pipe 0.344 ms  <- shipped (profiles/r2_policy_tc_*)
+template <int FIRST, int OBS, int ACT>
+__global__ void __launch_bounds__(kThreads, COPTER_POLICY_TC_CTAS_PER_SM)
+copter_mlp_policy_tc_kernel(const __grid_constant__ Args a) {
+    static_assert(OBS <= 12 && ACT <= 4, "tile shapes");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    const int t = threadIdx.x, warp = t >> 5;
+    constexpr int kMmaWarp = kEpilogueThreads / 32;
+    if (t == 0) {
+        for (int q = 0; q < kSlots; ++q) { bar_init(&sm.done[q], 1); bar_init(&sm.ready[q], kEpilogueThreads); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) tmem_alloc(sm);
+    load_weights<OBS, ACT>(sm, a.w1, a.b1, a.w2, a.b2, a.w3, a.b3);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = sm.tmem_base;
+    const int64_t n_tiles = (a.n + kTile - 1) / kTile;
+    // slot s works through tiles blockIdx.x + (kSlots r + s) gridDim.x, r = 0, 1, ...: both roles walk the same sequence
+    const int64_t stride = kSlots * (int64_t)gridDim.x;
+    auto any = [](const int (&l)[kSlots]) { int v = 0; for (int q = 0; q < kSlots; ++q) v |= l[q]; return v != 0; };
+
+    if (warp == kMmaWarp) {
+        // ===== MMA issuer =====
+        if ((t & 31) == 0) {
+            int64_t tile[kSlots];
+            int layer[kSlots];                                                            // the layer to issue next
+            uint32_t phase[kSlots];
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) { tile[s] = (int64_t)blockIdx.x + s * (int64_t)gridDim.x; layer[s] = tile[s] < n_tiles ? 1 : 0; phase[s] = 0; }
+            while (any(layer)) {
+#pragma unroll
+                for (int s = 0; s < kSlots; ++s) {
+                    if (layer[s] == 0) continue;
+                    bar_wait(&sm.ready[s], phase[s]); phase[s] ^= 1u;
+                    issue_layer(sm, s, layer[s], tmem_base);
+                    if (layer[s] < 3) ++layer[s];
+                    else { tile[s] += stride; layer[s] = tile[s] < n_tiles ? 1 : 0; }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warps: thread <-> (env row, column half) <-> TMEM lane `row` =====
+        const int row = t & (kTile - 1), half = t / kTile;                          // half is warp-uniform
+        const bool owner = half == 0;                                               // holds the env's state, writes its observation row, stores its action
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16); // this warp's quarter of the 128 TMEM lanes
+        const float4* planes = reinterpret_cast<const float4*>(a.state);
+        auto fetch = [&](int64_t tl, float4 (&p)[3]) {
+            const int64_t i = tl * kTile + row;
+            if (owner && tl < n_tiles && i < a.n) { p[0] = planes[i]; p[1] = planes[a.stride + i]; p[2] = planes[2 * a.stride + i]; }
+            else p[0] = p[1] = p[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        int64_t tile[kSlots];
+        int layer[kSlots];                      // the layer whose result this thread reads next (0: the slot has run out of tiles)
+        uint32_t phase[kSlots];
+        float4 nxt[kSlots][3];
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+            tile[s] = (int64_t)blockIdx.x + s * (int64_t)gridDim.x; layer[s] = 0; phase[s] = 0;
+            fetch(tile[s], nxt[s]);
+            if (tile[s] < n_tiles) {
+                if (owner) write_obs_row<FIRST, OBS>(sm.slot[s], row, nxt[s]);
+                fence_before_sync();
+                bar_arrive(&sm.ready[s]);
+                layer[s] = 1;
+                fetch(tile[s] + stride, nxt[s]);                // arrives under the three layers
+            }
+        }
+        while (any(layer)) {
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                if (layer[s] == 0) continue;
+                bar_wait(&sm.done[s], phase[s]); phase[s] ^= 1u;
+                fence_after_sync();
+                if (layer[s] < 3) {
+                    // (layer 2 overwrites the tile its finished MMAs read)
+                    hidden_epilogue<4 / kSplit>(lane_base + col_hidden(s), sm.slot[s].a, row, half * (kH / kSplit));
+                    fence_async_smem();
+                    fence_before_sync();
+                    bar_arrive(&sm.ready[s]);
+                    ++layer[s];
+                } else {
+                    float pre[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (owner) tmem_ld4(lane_base + col_out(s), pre);
+                    const int64_t i = tile[s] * kTile + row;
+                    tile[s] += stride;
+                    if (tile[s] < n_tiles) {                                       // the next tile's observation row first: the MMA warp is waiting for it
+                        if (owner) write_obs_row<FIRST, OBS>(sm.slot[s], row, nxt[s]);
+                        fence_before_sync();
+                        bar_arrive(&sm.ready[s]);
+                        layer[s] = 1;
+                        fetch(tile[s] + stride, nxt[s]);
+                    } else {
+                        layer[s] = 0;
+                    }
+                    if (owner && i < a.n) {
+                        float act[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) act[j] = fmaf(a.out_scale, tanh_mufu(pre[j]), a.out_offset);
+                        if constexpr (ACT == 4) reinterpret_cast<float4*>(a.action)[i] = make_float4(act[0], act[1], act[2], act[3]);
+                        else if constexpr (ACT == 2) reinterpret_cast<float2*>(a.action)[i] = make_float2(act[0], act[1]);
+                        else a.action[i] = act[0];
+                    }
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_free(tmem_base);
+}
+
+}  // namespace tc
+}  // namespace copter

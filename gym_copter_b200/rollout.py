@@ -104,10 +104,12 @@ class PlanarLinear(torch.nn.Module):
 
 class FusedMLPPolicy:
     """
-    The tanh MLP O -> 64 -> 64 -> A evaluated by ONE hand-written kernel (copter_policy_mlp_f32:
-    warp-level bf16 tensor-core MMAs with fp32 accumulation, activations in registers, tanh on
-    the MUFU pipe) straight from the env's fp32 state planes -- no observation tensor, no [N,64]
-    intermediates in HBM.  `net` is a torch.nn.Sequential(Linear, Tanh, Linear, Tanh, Linear,
+    The tanh MLP O -> 64 -> 64 -> A evaluated by ONE hand-written kernel (copter_policy_mlp_f32)
+    straight from the env's fp32 state planes -- no observation tensor, no [N,64] intermediates in
+    HBM.  Two implementations, bf16 operands with fp32 accumulation in both: tcgen05.mma with the
+    accumulators in tensor memory, 128 envs per tile (the default; csrc/copter_policy_tc.cuh), and
+    warp-level mma.sync with the activations in registers (csrc/copter_policy.cuh; selected by
+    COPTER_B200_POLICY_TC=0 in the environment, and the one the fused rollout kernel embeds).  `net` is a torch.nn.Sequential(Linear, Tanh, Linear, Tanh, Linear,
     Tanh) (e.g. mlp_policy(...).net); its weights are read in place, so optimizer updates to
     fp32 parameters are picked up by the next call.  action = out_offset + out_scale * net(obs).
     Use with PolicyRollout(..., planar=True) and CopterVecEnv(write_obs=False).

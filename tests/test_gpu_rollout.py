@@ -335,13 +335,32 @@ def test_planar_heuristics_rollout_vs_oracle(pkg, variant, source, scale, offset
         assert s['timeout'] == s['episodes']
 
 
-@pytest.mark.parametrize('variant', ['Lander3D', 'Lander2D', 'Hover3D', 'Lander1D'])
-def test_fused_mlp_policy_vs_torch_fp32(pkg, variant):
-    """The hand-written policy kernel (bf16 tensor-core MMAs, fp32 accumulation, MUFU tanh)
-    against the plain PyTorch fp32 evaluation of the same network on the same observations.
+@pytest.fixture
+def policy_kernel_choice():
+    """COPTER_B200_POLICY_TC selects the policy kernel per call: '1' tcgen05 / TMEM (the default), '0' warp-level mma.sync."""
+    import os
+    old = os.environ.get('COPTER_B200_POLICY_TC')
+
+    def choose(v):
+        os.environ['COPTER_B200_POLICY_TC'] = v
+    yield choose
+    if old is None:
+        os.environ.pop('COPTER_B200_POLICY_TC', None)
+    else:
+        os.environ['COPTER_B200_POLICY_TC'] = old
+
+
+@pytest.mark.parametrize('kernel', ['1', '0'])
+@pytest.mark.parametrize('variant', ['Lander3D', 'Lander2D', 'Hover3D', 'Lander1D', 'Takeoff'])
+def test_fused_mlp_policy_vs_torch_fp32(pkg, variant, kernel, policy_kernel_choice):
+    """The hand-written policy kernels -- tcgen05.mma with TMEM accumulators (kernel '1', the default) and
+    warp-level mma.sync (kernel '0') -- against the plain PyTorch fp32 evaluation of the same network on
+    the same observations (bf16 inputs / weights / activations, fp32 accumulation, MUFU tanh; the
+    tcgen05 kernel evaluates a quarter of the hidden tanh as a polynomial on the FMA pipe).
     Tolerance: bf16 rounding of inputs, weights and two layers of activations (2^-9 relative
     each) plus tanh.approx (2^-11) on outputs in [-1, 1]."""
-    n = 4099
+    policy_kernel_choice(kernel)
+    n = 4099 if kernel == '0' else 4099 + 128 * 700          # the tcgen05 kernel: more tiles than resident CTAs, ragged tail
     env = pkg.CopterVecEnv(variant, n, seed=3)
     env.reset()
     g = torch.Generator(device='cuda').manual_seed(0)
@@ -358,6 +377,11 @@ def test_fused_mlp_policy_vs_torch_fp32(pkg, variant):
     assert got.shape == (n, env.action_size)
     assert err.max().item() <= 2e-2 and err.mean().item() <= 3e-3, (err.max().item(), err.mean().item())
     assert ref.std().item() > 0.01       # the comparison is not vacuous
+    if kernel == '1':                    # and the two kernels agree with each other more closely than either with fp32
+        policy_kernel_choice('0')
+        other = pkg.FusedMLPPolicy(env, pol.net, out_scale=0.5, out_offset=0.25)()
+        policy_kernel_choice('1')
+        assert (got - other).abs().max().item() <= 1.5e-2 and (got - other).abs().mean().item() <= 1e-3
     # in the loop: same trajectories as the torch policy up to the policy's own rounding
     ro = pkg.PolicyRollout(env, fused, 4, planar=True, use_cuda_graph=True)
     r, d, _ = ro.run()
@@ -365,11 +389,15 @@ def test_fused_mlp_policy_vs_torch_fp32(pkg, variant):
 
 
 @pytest.mark.parametrize('variant,n', [('Lander3D', 4099), ('Lander2D', 1000), ('Hover3D', 257), ('Lander1D', 31)])
-def test_fused_policy_rollout_equals_policy_kernel_plus_step(pkg, variant, n):
+def test_fused_policy_rollout_equals_policy_kernel_plus_step(pkg, variant, n, policy_kernel_choice):
     """copter_policy_rollout_f32 (policy + env step for T steps in one launch, state in
     registers) against the same network evaluated by copter_policy_mlp_f32 and stepped by
     copter_step_f32, launch by launch: done flags, recorded actions / observations, final state
-    and counters are bit-identical, rewards agree to a few ulp (ragged n covers partly filled warps)."""
+    and counters are bit-identical, rewards agree to a few ulp (ragged n covers partly filled warps).
+    The fused kernel evaluates the network with warp-level MMAs, so the standalone policy kernel is
+    pinned to that implementation here (the tcgen05 kernel rounds differently: hi + lo bf16 biases,
+    a quarter of the tanh as polynomials)."""
+    policy_kernel_choice('0')
     T = 150
     envs = [pkg.CopterVecEnv(variant, n, seed=11, track_returns=True) for _ in range(2)]
     pol = pkg.mlp_policy(envs[0].obs_size, envs[0].action_size, dtype=torch.float32, seed=2)

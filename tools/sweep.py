@@ -25,6 +25,13 @@ VARIANTS['nopair'] = ['-DCOPTER_PAIR_MIN_K=0']        # K-fused fp32 launches on
 VARIANTS['pair_plainmul'] = ['-DCOPTER_F2_PLAIN_MUL_ADD=1']   # packed kernel with FMUL2 / FADD2 instead of FFMA2-only
 VARIANTS['pair_c5'] = ['-DCOPTER_PAIR_CTAS_PER_SM=5']         # packed kernel at 5 CTAs per SM (<= 96 registers)
 VARIANTS['pair_k2'] = ['-DCOPTER_PAIR_MIN_K=2']               # packed kernel from K = 2 on
+VARIANTS['tc_s1'] = ['-DCOPTER_POLICY_TC_SLOTS=1', '-DCOPTER_POLICY_TC_SPLIT=1']    # tcgen05 policy kernel: 1 tile in flight per CTA, 4 CTAs per SM, one thread per row
+VARIANTS['tc_s1x2'] = ['-DCOPTER_POLICY_TC_SLOTS=1', '-DCOPTER_POLICY_TC_SPLIT=2']  # two threads per row, 3 CTAs per SM
+VARIANTS['tc_s1x2c4'] = ['-DCOPTER_POLICY_TC_SLOTS=1', '-DCOPTER_POLICY_TC_SPLIT=2', '-DCOPTER_POLICY_TC_CTAS_PER_SM=4']  # 4 CTAs per SM (<= 56 registers)
+VARIANTS['tc_p4'] = ['-DCOPTER_POLICY_TC_POLY=4']     # 4 of every 16 hidden tanh on the FMA pipe
+VARIANTS['tc_p6'] = ['-DCOPTER_POLICY_TC_POLY=6']
+VARIANTS['tc_p8'] = ['-DCOPTER_POLICY_TC_POLY=8']
+VARIANTS['tc_s2x2'] = ['-DCOPTER_POLICY_TC_SLOTS=2', '-DCOPTER_POLICY_TC_SPLIT=2']  # 2 tiles in flight, 2 CTAs per SM, two threads per row
 VARIANTS['nofast'] = ['-DCOPTER_FAST_SUBSTEP=0']      # K-fused loop without the straight-line substep
 VARIANTS['nostreak'] = ['-DCOPTER_CALM_STREAK=0']     # K-fused loop: flags + hot test + two votes on every substep
 VARIANTS['tma_k2'] = ['-DCOPTER_TMA_MIN_K=2']         # K-fused launches through the TMA-prefetch + cluster-launch-control kernel
