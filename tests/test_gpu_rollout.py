@@ -448,11 +448,13 @@ def test_fused_policy_rollout_argument_errors(pkg):
         pkg.FusedPolicyRollout(pkg.CopterVecEnv('Lander3D', 64, k_substeps=2), good, 4)
 
 
-def test_fused_policy_rollout_exploration_noise(pkg):
+def test_fused_policy_rollout_exploration_noise(pkg, policy_kernel_choice):
     """action_std: the sampled command is policy(obs) + std * xi with xi the documented Philox
     stream (counter (env, step, 2), Box-Muller) -- checked against the oracle's restatement of
-    the stream and the policy kernel's own output on the recorded observations; the trajectory
-    equals stepping the recorded commands; cutting the horizon differently changes nothing."""
+    the stream and the policy kernel's own output on the recorded observations (the warp-MMA
+    kernel, whose arithmetic the fused rollout embeds); the trajectory equals stepping the
+    recorded commands; cutting the horizon differently changes nothing."""
+    policy_kernel_choice('0')
     n, T, seed, off = 1031, 24, 0xABCDEF0123, 5000
     mk = lambda: pkg.CopterVecEnv('Lander3D', n, seed=seed, env_offset=off)          # noqa: E731
     pol = pkg.mlp_policy(10, 4, dtype=torch.float32, seed=9)

@@ -1,5 +1,5 @@
-"""Developer tool: the launches `ncu -k regex:policy` captures for profiles/ (policy kernel alone,
-then the fused policy + step rollout kernel, 2^23 envs)."""
+"""Developer tool: the launches `ncu -k regex:policy` captures for profiles/ -- the tcgen05 / TMEM policy
+kernel (x2), the warp-MMA policy kernel (x2), then the fused policy + step rollout kernel (x2), 2^23 envs."""
 import os
 import sys
 
@@ -12,8 +12,10 @@ env = g.LanderVec(1 << 23, seed=1, write_obs=False)
 env.reset()
 pol = g.mlp_policy(10, 4, dtype=torch.float32, seed=5)
 fused = g.FusedMLPPolicy(env, pol.net, out_scale=0.2 * 0.0166, out_offset=0.0166)
-for _ in range(3):
-    fused()
+for tc in ('1', '0'):
+    os.environ['COPTER_B200_POLICY_TC'] = tc
+    for _ in range(2):
+        fused()
 ro = g.FusedPolicyRollout(env, pol.net, 8, out_scale=0.2 * 0.0166, out_offset=0.0166)
 for _ in range(2):
     ro.run()

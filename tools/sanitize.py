@@ -21,10 +21,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gym_copter_b200 as g      # noqa: E402
 
 rng = np.random.default_rng(0)
-for variant in ('Lander3D', 'Lander2D', 'Lander1D', 'Hover3D', 'Hover2D', 'Hover1D'):
+for variant in ('Lander3D', 'Lander2D', 'Lander1D', 'Hover3D', 'Hover2D', 'Hover1D', 'Takeoff'):
     for dtype in (torch.float32, torch.float64):
         for n in (1, 33, 129, 300):
-            env = g.CopterVecEnv(variant, n, dtype=dtype, seed=1, k_substeps=3, track_returns=True, keep_final_obs=True)
+            env = g.CopterVecEnv(variant, n, dtype=dtype, seed=1, k_substeps=3, track_returns=True, keep_final_obs=True,
+                                 report_cause=True, wide_counters=(n == 129))
             env.reset(force=rng.uniform(-30, 30, (n, 3)))
             for t in range(4):
                 a = rng.uniform(-1, 1, (n, env.action_size)).astype(np.float32)
@@ -32,15 +33,21 @@ for variant in ('Lander3D', 'Lander2D', 'Lander1D', 'Hover3D', 'Hover2D', 'Hover
             env.rollout(5, source='randn', record_rewards=True, record_dones=True, record_actions=True)
             env.rollout(3, source='uniform')
             env.rollout(4, source='pid', scale=2e-3, offset=0.0149, record_actions=True)            # 3-D / planar landing heuristics
-            if variant != 'Lander3D':                                                              # hover heuristics ([N,24] controller memories)
+            if variant not in ('Lander3D', 'Takeoff'):                                             # hover heuristics ([N,24] controller memories)
                 env.rollout(4, source='pid_hover', scale=0.0331, record_actions=True)
             env.stats()
 for variant in ('Lander3D', 'Lander2D', 'Lander1D', 'Hover3D'):
-    for n in (1, 33, 129, 300):
+    for n in (1, 33, 129, 300, 128 * 148 * 4 * 2 + 5):        # the last: more tiles than resident CTAs of the tcgen05 policy kernel
+        if n > 1000 and variant != 'Lander3D':
+            continue
         env = g.CopterVecEnv(variant, n, seed=4, track_returns=True)
         env.reset()
-        pol = g.mlp_policy(env.obs_size, env.action_size, dtype=torch.float32, seed=n)
-        g.FusedMLPPolicy(env, pol.net, out_scale=0.02, out_offset=0.0166)()
+        pol = g.mlp_policy(env.obs_size, env.action_size, dtype=torch.float32, seed=n % 97)
+        for tc in ('1', '0'):                                 # tcgen05 / TMEM kernel, then the warp-MMA kernel
+            os.environ['COPTER_B200_POLICY_TC'] = tc
+            g.FusedMLPPolicy(env, pol.net, out_scale=0.02, out_offset=0.0166)()
+        if n > 1000:
+            continue
         ro = g.FusedPolicyRollout(env, pol.net, 6, out_scale=0.02, out_offset=0.0166, store_obs=True, store_actions=True)
         ro.run()
         ro.run()
