@@ -1147,6 +1147,189 @@ copter_policy_rollout_kernel(const __grid_constant__ KParams<float> kp, const __
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same rollout on the 5th-generation tensor cores (round 2): the structure of
+// copter_mlp_policy_tc_kernel (copter_policy_tc.cuh) with the env step INSIDE its epilogue.
+// There a tile is 128 envs and epilogue thread t owns row t of the tile and lane t of tensor
+// memory -- which is exactly one thread per env, so the thread that pulls env t's action out of
+// TMEM also holds env t's state in registers and steps it.  Per env-step and CTA:
+//   epilogue thread   observation row (bf16) -> shared memory (layer-1 A operand)      arrive ready
+//   MMA warp          wait ready; tcgen05.mma layer 1 -> TMEM; tcgen05.commit -> done
+//   epilogue thread   wait done; tcgen05.ld its row; tanh; bf16 -> shared memory       arrive ready
+//   MMA warp          layer 2 ...                       epilogue: the same             arrive ready
+//   MMA warp          layer 3 (N = 16) ...              epilogue: tcgen05.ld 4 columns, action = offset +
+//                     scale tanh(.), exploration noise, Eq. 6, one reference step, reward / done row t
+// State, flight status and the running shaping never leave the registers between the steps of the
+// horizon; a CTA walks its tiles persistently, 4 CTAs (16 epilogue warps) share an SM and fill one
+// another's MMA round trips.  The per-env arithmetic is that of the tcgen05 policy kernel followed by
+// copter_step_f32 (k = 1): bit-identical to that two-kernel path
+// (tests/test_gpu_rollout.py::test_fused_policy_rollout_tc_equals_policy_tc_kernel_plus_step).
+// ------------------------------------------------------------------------------------------
+// Measured, 2^23 envs, horizon 16 (profiles/r2_sweep_policy_tc_ctas.txt, r2_sweep_policy_tc_rollout.txt), ms per env-step:
+//   3 CTAs/SM 0.501, 4 CTAs/SM (94 registers) 0.444 / 0.441 (TMEM read-back double- / single-buffered in registers),
+//   5 CTAs/SM (72 registers, 16 B of spills) 0.424 / 0.424, 6 CTAs/SM (64 registers) 0.524; __maxnreg__(80): 0.54.
+//   The warp-MMA kernel above: 0.404 -- its 20 warps per SM are independent chains, here four warps share every
+//   tile barrier and every layer costs an mbarrier round trip through the MMA warp, and one env-step of a tile is a
+//   strictly serial chain (observation -> 3 layers -> action -> step -> observation): only other tiles fill the gaps
+//   and registers allow five.  So the fused rollout DEFAULTS to the warp-MMA kernel; COPTER_B200_POLICY_ROLLOUT_TC=1
+//   (or -DCOPTER_POLICY_ROLLOUT_TC=1) selects this one.  The standalone policy kernel, whose threads hold no env,
+//   is faster on tcgen05 (0.321 vs 0.359 ms) and defaults to it.
+#ifndef COPTER_POLICY_ROLLOUT_TC_CTAS_PER_SM
+#define COPTER_POLICY_ROLLOUT_TC_CTAS_PER_SM 5      // x 64 TMEM columns <= the SM's 512
+#endif
+#ifndef COPTER_POLICY_ROLLOUT_TC_PIPELINED
+#define COPTER_POLICY_ROLLOUT_TC_PIPELINED 0        // TMEM read-back double-buffered in registers (16 more registers; no gain)
+#endif
+// (the A/B shapes of the standalone kernel with several tiles in flight or two threads per row do not apply here)
+#define COPTER_POLICY_ROLLOUT_TC_AVAILABLE (COPTER_POLICY_TC_SLOTS == 1 && COPTER_POLICY_TC_SPLIT == 1)
+#if COPTER_POLICY_ROLLOUT_TC_AVAILABLE
+
+struct RolloutTcSmem {
+    tc::Smem mlp;                                   // weights, the slot's A tiles, the two mbarriers
+    float tiles[4][32 * 12];                        // per-warp observation staging (write_obs_rows)
+};
+
+template <int VARIANT, bool STATS>
+__global__ void __launch_bounds__(tc::kTile + 32, COPTER_POLICY_ROLLOUT_TC_CTAS_PER_SM)
+copter_policy_rollout_tc_kernel(const __grid_constant__ KParams<float> kp, const __grid_constant__ PolicyRolloutArgs a) {
+    using T = float;
+    constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A, FIRST = Variant<VARIANT>::first;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    RolloutTcSmem& rs = *reinterpret_cast<RolloutTcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    tc::Smem& sm = rs.mlp;
+    const int t_id = threadIdx.x, warp = t_id >> 5, lane = t_id & 31;
+    constexpr int kMmaWarp = tc::kTile / 32;
+    if (t_id == 0) {
+        tc::bar_init(&sm.done[0], 1);
+        tc::bar_init(&sm.ready[0], tc::kTile);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kMmaWarp) tc::tmem_alloc(sm);
+    tc::load_weights<O, A>(sm, a.w.w1, a.w.b1, a.w.w2, a.w.b2, a.w.w3, a.w.b3);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = sm.tmem_base;
+    if (STATS) credit_env_steps(a.stats, a.n, a.n_steps);
+    const int64_t n_tiles = (a.n + tc::kTile - 1) / tc::kTile;
+
+    if (warp == kMmaWarp) {
+        // ===== MMA issuer: 3 layers per env-step, n_steps env-steps per tile =====
+        if (lane == 0) {
+            uint32_t phase = 0;
+            for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x)
+                for (int t = 0; t < a.n_steps; ++t)
+#pragma unroll
+                    for (int layer = 1; layer <= 3; ++layer) {
+                        tc::bar_wait(&sm.ready[0], phase); phase ^= 1u;
+                        tc::issue_layer(sm, 0, layer, tmem_base);
+                    }
+        }
+    } else {
+        // ===== epilogue warps: thread <-> env row <-> TMEM lane =====
+        const int row = t_id;                                                        // 0..127
+        const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);        // this warp's quarter of the TMEM lanes
+        tc::SlotSmem& ss = sm.slot[0];
+        uint32_t phase = 0;
+        for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+            const int64_t row0 = tile_id * tc::kTile + warp * 32, i = row0 + lane;
+            const bool valid = i < a.n;
+            const int64_t left = a.n - row0;
+            const int rows = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+            T s[12];
+            int st = ST_LANDED, steps = 1; uint32_t episode = 0;
+            T total = (T)0, ret = (T)0; bool done_any = false;
+            if (valid) {
+                load_state<T>(a.state, a.stride, i, s);
+                decode_meta(a.meta[i], a.meta_hi, i, st, steps, episode);
+                if (STATS && a.ep_return) ret = a.ep_return[i];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) s[j] = (T)0;
+            }
+            Shaping<T> pre_sh = lander_shaping<T>(kp, s);
+            for (int t = 0; t < a.n_steps; ++t) {
+                // the observation the policy acts on at step t
+                if (a.obs_tn && rows > 0) write_obs_rows<VARIANT, T>(a.obs_tn + (int64_t)t * a.n * O, rs.tiles[warp], lane, row0, rows, s);
+                tc::write_obs_row<FIRST, O>(ss, row, s);
+                tc::fence_before_sync();
+                tc::bar_arrive(&sm.ready[0]);
+#pragma unroll
+                for (int layer = 1; layer <= 2; ++layer) {
+                    tc::bar_wait(&sm.done[0], phase); phase ^= 1u;
+                    tc::fence_after_sync();
+                    tc::hidden_epilogue<4, COPTER_POLICY_ROLLOUT_TC_PIPELINED != 0>(lane_base + tc::col_hidden(0), ss.a, row, 0);
+                    tc::fence_async_smem();
+                    tc::fence_before_sync();
+                    tc::bar_arrive(&sm.ready[0]);
+                }
+                tc::bar_wait(&sm.done[0], phase); phase ^= 1u;
+                tc::fence_after_sync();
+                float pre[4];
+                tc::tmem_ld4(lane_base + tc::col_out(0), pre);
+                T act[A];
+#pragma unroll
+                for (int j = 0; j < A; ++j) act[j] = fmaf(a.w.out_scale, tc::tanh_mufu(pre[j]), a.w.out_offset);
+                bool dn = false; int cause = 0, ep_len = 0; T ep_ret = (T)0;
+                if (valid) {
+                    T m[4];
+                    if (a.action_std) {                                   // exploration: action ~ N(policy(obs), std^2)
+                        T xi[4];
+                        draw_variates<T>(a.seed, (uint64_t)(a.env_offset + i), (uint64_t)(a.first_step + t), 2u, false, xi);
+#pragma unroll
+                        for (int j = 0; j < A; ++j) act[j] = fmaf(a.action_std[j], xi[j], act[j]);
+                    }
+                    if (a.action_tn) {
+                        T* arow = a.action_tn + ((int64_t)t * a.n + i) * A;
+                        if constexpr (A == 4) *reinterpret_cast<float4*>(arow) = make_float4(act[0], act[1], act[2], act[3]);
+                        else if constexpr (A == 2) *reinterpret_cast<float2*>(arow) = make_float2(act[0], act[1]);
+                        else arow[0] = act[0];
+                    }
+                    motors_from_action<T, VARIANT>(act, m);                                     // task.py:91 + _get_motors
+                    const Forces<T> forces = motor_forces<T>(kp, m[0], m[1], m[2], m[3]);
+                    T pert[3] = {(T)0, (T)0, (T)0};
+                    if (steps == 1) {
+                        T f[3];
+                        if (a.init_force) { f[0] = a.init_force[3 * i]; f[1] = a.init_force[3 * i + 1]; f[2] = a.init_force[3 * i + 2]; }
+                        else reset_force<T>(kp, a.seed, (uint64_t)(a.env_offset + i), episode, f);
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) pert[j] = f[j] * kp.invM;
+                    }
+                    T r;
+                    env_substep<T, VARIANT>(kp, s, st, steps, forces, pert, pre_sh, r, dn, cause);
+                    total += r;
+                    if (STATS) ret += r;
+                    if (a.reward_tn) a.reward_tn[(int64_t)t * a.n + i] = r;
+                    if (a.done_tn) a.done_tn[(int64_t)t * a.n + i] = dn ? 1 : 0;
+                    if (dn) {
+                        done_any = true;
+                        if (STATS) { ep_len = steps - 1; ep_ret = ret; ret = (T)0; }
+                        if (a.auto_reset) {
+                            reset_state<T>(kp, s, st, steps);
+                            episode = (episode + 1) & kp.ep_mask;
+                            pre_sh = lander_shaping<T>(kp, s);
+                        }
+                    }
+                }
+                if (STATS) flush_episode_stats<T>(a.stats, lane, dn, cause, ep_len, ep_ret, a.ep_return != nullptr);
+            }
+            if (valid) {
+                store_state<T>(a.state, a.stride, i, s);
+                store_meta(a.meta, a.meta_hi, i, st, steps, episode);
+                if (a.reward_sum) a.reward_sum[i] = total;
+                if (a.done_any) a.done_any[i] = done_any ? 1 : 0;
+                if (STATS && a.ep_return) a.ep_return[i] = ret;
+            }
+            if (a.obs && rows > 0) write_obs_rows<VARIANT, T>(a.obs, rs.tiles[warp], lane, row0, rows, s);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) tc::tmem_free(tmem_base);
+}
+#endif  // COPTER_POLICY_ROLLOUT_TC_AVAILABLE
+
 template <typename T, int VARIANT>
 __global__ void __launch_bounds__(kBlock)
 copter_reset_kernel(const __grid_constant__ KParams<T> kp, T* state, uint32_t* meta, uint32_t* meta_hi, float* obs, T* ep_return,
@@ -1492,6 +1675,15 @@ int policy_tc_setting() {
     const char* e = getenv("COPTER_B200_POLICY_TC");        // read on every call: tests and A/B runs flip it inside one process
     return e ? (atoi(e) != 0) : COPTER_POLICY_TC;
 }
+// The same choice for the fused policy + step rollout (copter_policy_rollout_f32): measured, the warp-MMA kernel wins
+// there (the comment on copter_policy_rollout_tc_kernel), so it is the default.
+#ifndef COPTER_POLICY_ROLLOUT_TC
+#define COPTER_POLICY_ROLLOUT_TC 0
+#endif
+int policy_rollout_tc_setting() {
+    const char* e = getenv("COPTER_B200_POLICY_ROLLOUT_TC");
+    return e ? (atoi(e) != 0) : COPTER_POLICY_ROLLOUT_TC;
+}
 
 template <int VARIANT>
 int launch_policy_v(const PolicyArgs& a, cudaStream_t s) {
@@ -1518,8 +1710,29 @@ int launch_policy_v(const PolicyArgs& a, cudaStream_t s) {
     return (int)cudaGetLastError();
 }
 
+#if COPTER_POLICY_ROLLOUT_TC_AVAILABLE
+template <int VARIANT, bool STATS>
+int launch_policy_rollout_tc(const KParams<float>& kp, const PolicyRolloutArgs& a, cudaStream_t s) {
+    constexpr auto kernel = copter_policy_rollout_tc_kernel<VARIANT, STATS>;
+    constexpr int smem = (int)sizeof(RolloutTcSmem) + 128;                     // dynamic: past the 48 KB static limit
+    static bool configured[kMaxDevices] = {false};
+    const int dev = current_device();
+    if (!configured[dev]) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return (int)cudaGetLastError();
+        configured[dev] = true;
+    }
+    const int64_t tiles = (a.n + tc::kTile - 1) / tc::kTile, cap = (int64_t)sm_count() * COPTER_POLICY_ROLLOUT_TC_CTAS_PER_SM;
+    kernel<<<(int)(tiles < cap ? tiles : cap), tc::kTile + 32, smem, s>>>(kp, a);
+    return (int)cudaGetLastError();
+}
+#endif
+
 template <int VARIANT>
 int launch_policy_rollout_v(const KParams<float>& kp, const PolicyRolloutArgs& a, cudaStream_t s) {
+#if COPTER_POLICY_ROLLOUT_TC_AVAILABLE
+    if (policy_rollout_tc_setting())    // the tcgen05 / TMEM kernel; default: the warp-MMA kernel
+        return a.stats ? launch_policy_rollout_tc<VARIANT, true>(kp, a, s) : launch_policy_rollout_tc<VARIANT, false>(kp, a, s);
+#endif
     if (a.stats) copter_policy_rollout_kernel<VARIANT, true><<<persistent_grid_for<copter_policy_rollout_kernel<VARIANT, true>>(a.n), 128, 0, s>>>(kp, a);
     else         copter_policy_rollout_kernel<VARIANT, false><<<persistent_grid_for<copter_policy_rollout_kernel<VARIANT, false>>(a.n), 128, 0, s>>>(kp, a);
     return (int)cudaGetLastError();

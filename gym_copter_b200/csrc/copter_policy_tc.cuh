@@ -16,8 +16,9 @@
 // 128 contiguous bytes; core matrices adjacent in K are LBO = 128 B apart, 8-row groups SBO = (K/8) x
 // 128 B apart.  A thread writing its own 128-byte activation row therefore writes eight 16-byte chunks
 // 128 B apart; consecutive threads are 16 B apart inside a core matrix, so a warp's store is conflict-free.
-// TMEM: 64 hidden + 16 output accumulator columns per tile in flight; with one tile in flight per CTA
-// (128 columns allocated) four CTAs share an SM's 512 columns and overlap one another's phases.
+// TMEM: 64 accumulator columns per tile in flight (the 16 output columns of layer 3 reuse the hidden ones, see
+// col_out); with one tile in flight per CTA (64 columns allocated) up to eight CTAs could share an SM's 512
+// columns -- registers and shared memory allow five or six -- and overlap one another's phases.
 // Measured history and the A/B against the warp-MMA kernel (copter_policy.cuh): the comment on the kernel.
 #pragma once
 
@@ -32,18 +33,24 @@ constexpr int kTile = 128, kH = 64, kK1 = 16, kN3 = 16;
 #define COPTER_POLICY_TC_SLOTS 1             // tiles in flight per CTA
 #endif
 constexpr int kSlots = COPTER_POLICY_TC_SLOTS;
-static_assert(kSlots >= 1 && kSlots <= 3, "TMEM budget: 64 hidden + 16 output columns per slot, <= 256 columns per CTA");
-// TMEM columns of a CTA: the slots' hidden accumulators (64 columns each) first, then their output accumulators (16 each)
-constexpr uint32_t kTmemCols = kSlots == 1 ? 128 : 256;          // tcgen05.alloc takes powers of two
+static_assert(kSlots >= 1 && kSlots <= 4, "TMEM budget: 64 columns per slot, <= 256 columns per CTA");
+// TMEM columns of a CTA: 64 per slot.  The 16 output accumulator columns of layer 3 REUSE the first columns of the
+// slot's hidden accumulator: layer 3 is issued only after every epilogue thread has pulled its layer-2 row out of
+// TMEM (the ready barrier), and layer 1 of the next tile only after every thread has read its output columns.
+// 64 columns per tile instead of 128 is what lets more than four CTAs share an SM's 512 columns.
+constexpr uint32_t kTmemCols = kSlots == 1 ? 64 : (kSlots == 2 ? 128 : 256);          // tcgen05.alloc takes powers of two >= 32
 __host__ __device__ constexpr uint32_t col_hidden(int slot) { return 64u * slot; }
-__host__ __device__ constexpr uint32_t col_out(int slot) { return 64u * kSlots + 16u * slot; }
+__host__ __device__ constexpr uint32_t col_out(int slot) { return 64u * slot; }
 
 // element offset of (row r, column k) in a canonical K-major tile with KC = K/8 chunks per row
 __device__ __forceinline__ int canon(int r, int k, int KC) { return (((r >> 3) * KC + (k >> 3)) << 6) + ((r & 7) << 3) + (k & 7); }
 
 struct alignas(128) SlotSmem {
-    __nv_bfloat16 a1[kTile * kK1];       // layer 1 activations: the observation rows
-    __nv_bfloat16 a[kTile * kH];         // layer 2 / layer 3 activations
+    // layer 2 / layer 3 activations [128 x 64]; its first 4 KB double as the layer-1 A tile (the observation rows,
+    // [128 x 16]): that tile is dead once layer 1's MMAs have completed, which is before any thread writes `a`, and
+    // the next tile's observation rows are written only after layer 3's MMAs -- the last readers of `a` -- completed
+    __nv_bfloat16 a[kTile * kH];
+    __device__ __forceinline__ __nv_bfloat16* a1() { return a; }
 };
 struct alignas(128) Smem {
     __nv_bfloat16 w1[kH * kK1];          // layer 1 weights  [64 x 16]  (columns OBS.. are zero, 14 / 15 carry the bias hi / lo)
@@ -139,22 +146,26 @@ __device__ __forceinline__ float tanh_fma(float x) {
     for (int k = 5; k >= 0; --k) p = fmaf(p, u, tanh_poly_coef(k));
     return p * x;
 }
-template <int NCHUNK>      // NCHUNK chunks of 16 columns starting at column col0 (the row's 64 columns may be split between two threads)
+// PIPELINED: the load of chunk q + 1 is in flight under the tanh of chunk q (two 16-register buffers); without it
+// one buffer, each load awaited before use (16 registers fewer: the fused rollout kernel, which also holds an env).
+template <int NCHUNK, bool PIPELINED = true>      // NCHUNK chunks of 16 columns starting at column col0 (the row's 64 columns may be split between two threads)
 __device__ __forceinline__ void hidden_epilogue(uint32_t taddr_row, __nv_bfloat16* a_tile, int row, int col0) {
-    uint32_t r[2][16];
+    uint32_t r[PIPELINED ? 2 : 1][16];
     tmem_ld16(taddr_row + col0, r[0]);
 #pragma unroll
     for (int q = 0; q < NCHUNK; ++q) {
         tmem_wait();                                               // chunk q has landed
-        if (q + 1 < NCHUNK) tmem_ld16(taddr_row + col0 + 16 * (q + 1), r[(q + 1) & 1]);
+        constexpr int kMask = PIPELINED ? 1 : 0;
+        if (PIPELINED && q + 1 < NCHUNK) tmem_ld16(taddr_row + col0 + 16 * (q + 1), r[(q + 1) & kMask]);
         float y[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const float x = __uint_as_float(r[q & 1][j]);
+            const float x = __uint_as_float(r[q & kMask][j]);
             // the polynomial lanes are spread over the chunk so that the two pipes interleave
             const bool poly = COPTER_POLICY_TC_POLY > 0 && ((j * COPTER_POLICY_TC_POLY) % 16) < COPTER_POLICY_TC_POLY;
             y[j] = poly ? tanh_fma(x) : tanh_mufu(x);
         }
+        if (!PIPELINED && q + 1 < NCHUNK) tmem_ld16(taddr_row + col0 + 16 * (q + 1), r[0]);      // r[0] is dead: lands under the packs and stores
         uint32_t w[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) w[j] = pack2(y[2 * j], y[2 * j + 1]);
@@ -207,7 +218,7 @@ __device__ __forceinline__ void issue_layer(Smem& sm, int slot, int layer, uint3
     SlotSmem& ss = sm.slot[slot];
     fence_after_sync();
     if (layer == 1) {            // D[128 x 64] = A1[128 x 16] W1^T (bias in columns 14, 15)
-        mma_bf16(tmem_base + col_hidden(slot), make_desc(ss.a1, kLBO, kSBO16), make_desc(sm.w1, kLBO, kSBO16), idesc64, 0u);
+        mma_bf16(tmem_base + col_hidden(slot), make_desc(ss.a1(), kLBO, kSBO16), make_desc(sm.w1, kLBO, kSBO16), idesc64, 0u);
     } else if (layer == 2) {     // D[128 x 64] = A[128 x 64] W2^T + ones b2^T
 #pragma unroll
         for (int j = 0; j < kH / 16; ++j)
@@ -231,9 +242,15 @@ __device__ __forceinline__ void write_obs_row(SlotSmem& ss, int row, const float
     float x[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) x[j] = j < OBS ? s[(FIRST + j) % 12] : ((j == 14 || j == 15) ? 1.0f : 0.0f);
-    *reinterpret_cast<uint4*>(ss.a1 + canon(row, 0, kK1 / 8)) = make_uint4(pack2(x[0], x[1]), pack2(x[2], x[3]), pack2(x[4], x[5]), pack2(x[6], x[7]));
-    *reinterpret_cast<uint4*>(ss.a1 + canon(row, 8, kK1 / 8)) = make_uint4(pack2(x[8], x[9]), pack2(x[10], x[11]), pack2(x[12], x[13]), pack2(x[14], x[15]));
+    *reinterpret_cast<uint4*>(ss.a1() + canon(row, 0, kK1 / 8)) = make_uint4(pack2(x[0], x[1]), pack2(x[2], x[3]), pack2(x[4], x[5]), pack2(x[6], x[7]));
+    *reinterpret_cast<uint4*>(ss.a1() + canon(row, 8, kK1 / 8)) = make_uint4(pack2(x[8], x[9]), pack2(x[10], x[11]), pack2(x[12], x[13]), pack2(x[14], x[15]));
     fence_async_smem();
+}
+// the same from the 12 state components a thread holds in registers (the fused rollout kernel)
+template <int FIRST, int OBS>
+__device__ __forceinline__ void write_obs_row(SlotSmem& ss, int row, const float (&s)[12]) {
+    const float4 p[3] = {make_float4(s[0], s[1], s[2], s[3]), make_float4(s[4], s[5], s[6], s[7]), make_float4(s[8], s[9], s[10], s[11])};
+    write_obs_row<FIRST, OBS>(ss, row, p);
 }
 
 __device__ __forceinline__ void tmem_alloc(Smem& sm) {         // warp 0, converged
@@ -248,7 +265,7 @@ __device__ __forceinline__ void tmem_free(uint32_t base) {     // warp 0, conver
 #define COPTER_POLICY_TC_SPLIT 1             // epilogue threads per env row: 1, or 2 (each takes 32 of the 64 hidden columns)
 #endif
 #ifndef COPTER_POLICY_TC_CTAS_PER_SM
-#define COPTER_POLICY_TC_CTAS_PER_SM (COPTER_POLICY_TC_SLOTS == 1 ? (COPTER_POLICY_TC_SPLIT == 1 ? 4 : 3) : 2)   // x kTmemCols <= the SM's 512 TMEM columns
+#define COPTER_POLICY_TC_CTAS_PER_SM (COPTER_POLICY_TC_SLOTS == 1 ? (COPTER_POLICY_TC_SPLIT == 1 ? 5 : 3) : 2)   // x kTmemCols <= the SM's 512 TMEM columns
 #endif
 constexpr int kSplit = COPTER_POLICY_TC_SPLIT;
 constexpr int kEpilogueThreads = kTile * kSplit;
@@ -272,7 +289,12 @@ constexpr int kThreads = kEpilogueThreads + 32;      // the epilogue warps + the
 //   + MMA warp and mbarriers instead of __syncthreads                      0.428 ms  (XU 60 %; three tiles: 0.437)
 //   one tile in flight, 4 CTAs/SM (16 epilogue warps per SM instead of 8)  0.374 ms
 //   two threads per row: 3 CTAs/SM (24 epilogue warps) 0.406 ms, 4 CTAs/SM (32 warps, 56 registers) 0.387 ms: more warps do not help
-//   one tile in flight, 4 CTAs/SM, 4 of every 16 hidden tanh on the FMA pipe 0.344 ms  <- shipped (profiles/r2_policy_tc_*)
+//   one tile in flight, 4 CTAs/SM, 4 of every 16 hidden tanh on the FMA pipe 0.344 ms  (profiles/r2_policy_kernels_*)
+//   64 TMEM columns per tile (layer 3's output reuses the hidden columns), layer-1 A tile aliased into the hidden
+//   A tile (34.5 KB of shared memory per CTA): 5 CTAs/SM 0.321 ms  <- shipped; 6 CTAs/SM (64 registers) 0.322 ms;
+//   6 of 16 tanh as polynomials 0.330, 8 of 16 0.355 (profiles/r2_sweep_policy_tc_ctas.txt)
+//   (tools/microbench/tmem_rates.cu, profiles/r2_tmem_rates.txt: TMEM read-back is NOT the floor -- 184 B/clk/SM from
+//   one CTA, 370 B/clk/SM from four, and tcgen05.ld overlaps tanh.approx completely; the MUFU floor is 0.19 ms)
 template <int FIRST, int OBS, int ACT>
 __global__ void __launch_bounds__(kThreads, COPTER_POLICY_TC_CTAS_PER_SM)
 copter_mlp_policy_tc_kernel(const __grid_constant__ Args a) {

@@ -109,7 +109,7 @@ class FusedMLPPolicy:
     HBM.  Two implementations, bf16 operands with fp32 accumulation in both: tcgen05.mma with the
     accumulators in tensor memory, 128 envs per tile (the default; csrc/copter_policy_tc.cuh), and
     warp-level mma.sync with the activations in registers (csrc/copter_policy.cuh; selected by
-    COPTER_B200_POLICY_TC=0 in the environment, and the one the fused rollout kernel embeds).  `net` is a torch.nn.Sequential(Linear, Tanh, Linear, Tanh, Linear,
+    COPTER_B200_POLICY_TC=0 in the environment); FusedPolicyRollout has a fused kernel of each kind.  `net` is a torch.nn.Sequential(Linear, Tanh, Linear, Tanh, Linear,
     Tanh) (e.g. mlp_policy(...).net); its weights are read in place, so optimizer updates to
     fp32 parameters are picked up by the next call.  action = out_offset + out_scale * net(obs).
     Use with PolicyRollout(..., planar=True) and CopterVecEnv(write_obs=False).

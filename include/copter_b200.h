@@ -259,6 +259,13 @@ int copter_reset_force_f64(const CopterParams* p, double* out, const uint32_t* e
  * copter_step_f32 consumes:  action = out_offset + out_scale * tanh(W3 tanh(W2 tanh(W1 obs + b1) + b2) + b3).
  * Weights use the torch.nn.Linear layouts W[out][in] (fp32, device memory); they and the
  * activations are rounded to bf16 for the tensor-core MMAs (fp32 accumulation).  hidden must be 64.
+ * Two implementations of the same network exist, selectable per call through the environment (tests and
+ * A/B runs; the defaults are the measured-faster ones): COPTER_B200_POLICY_TC=1 (default) evaluates it with
+ * tcgen05.mma and accumulators in tensor memory, =0 with warp-level mma.sync; they differ in rounding
+ * (bias carried as bf16 hi + lo, a quarter of the hidden tanh as FMA-pipe polynomials in the former), both
+ * within 2e-2 of the fp32 network.  COPTER_B200_POLICY_ROLLOUT_TC=0 (default) / 1 makes the same choice
+ * for copter_policy_rollout_f32 below; each fused kernel is bit-identical to the standalone kernel of
+ * its own kind followed by copter_step_f32.
  */
 int copter_policy_mlp_f32(const void* state, int64_t state_stride, int64_t n, int variant, int hidden,
                           const float* w1, const float* b1, const float* w2, const float* b2,

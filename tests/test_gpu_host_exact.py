@@ -162,8 +162,11 @@ def test_fp32_rollout_kernel_equals_the_host_instantiation(pkg, source):
         assert np.array_equal(bits(out['obs'].cpu().numpy()), bits(h_obs))
 
 
-def test_fp32_policy_rollout_kernel_equals_the_host_instantiation(pkg):
-    """copter_policy_rollout_f32: the env half of the fused policy + step kernel, on the recorded actions."""
+@pytest.mark.parametrize('kernel', ['1', '0'])
+def test_fp32_policy_rollout_kernel_equals_the_host_instantiation(pkg, kernel, monkeypatch):
+    """copter_policy_rollout_f32: the env half of the fused policy + step kernels ('1': the tcgen05 / TMEM
+    kernel, '0': the warp-MMA kernel), on the recorded actions."""
+    monkeypatch.setenv('COPTER_B200_POLICY_ROLLOUT_TC', kernel)
     N, T = 777, 48
     env = pkg.CopterVecEnv('Lander3D', N, dtype=torch.float32, seed=3)
     host = HostEnvBatch('Lander3D', N, dtype=np.float32, seed=3)

@@ -98,15 +98,20 @@ def policy():
                 ms = timed(ro.run, 10)
                 print(json.dumps({'bench': 'policy-in-loop Lander3D 2^23 envs, FUSED MLP kernel 10-64-64-4, T=%d, %s' % (T, 'cuda graph' if graph else 'eager'),
                                   'ms_per_env_step': ms / T, 'steps_per_s': n * T / ms * 1e3, 'policy_kernel_ms': ms_pol}), flush=True)
-            # policy + env step fused over the whole horizon: ONE launch, state in registers
-            for T2, kw in ((8, {}), (32, {}), (32, dict(store_obs=True, store_actions=True)),
-                           (32, dict(store_obs=True, store_actions=True, action_std=0.002))):
-                fr = g.FusedPolicyRollout(env2, pol32.net, T2, out_scale=0.2 * 0.0166, out_offset=0.0166, **kw)
-                fr.run(); fr.run()
-                ms = timed(fr.run, 10)
-                print(json.dumps({'bench': 'policy-in-loop Lander3D 2^23 envs, FUSED policy+step rollout kernel, T=%d%s' % (T2, (', obs/action rows recorded' if kw else '') + (', Gaussian exploration noise' if 'action_std' in kw else '')),
-                                  'ms_per_env_step': ms / T2, 'steps_per_s': n * T2 / ms * 1e3}), flush=True)
-                del fr
+            # policy + env step fused over the whole horizon: ONE launch, state in registers -- on the tcgen05 / TMEM
+            # kernel (the default) and on the warp-MMA kernel
+            for tc in ('1', '0'):
+                os.environ['COPTER_B200_POLICY_ROLLOUT_TC'] = tc
+                for T2, kw in ((8, {}), (32, {}), (32, dict(store_obs=True, store_actions=True)),
+                               (32, dict(store_obs=True, store_actions=True, action_std=0.002))):
+                    fr = g.FusedPolicyRollout(env2, pol32.net, T2, out_scale=0.2 * 0.0166, out_offset=0.0166, **kw)
+                    fr.run(); fr.run()
+                    ms = timed(fr.run, 10)
+                    print(json.dumps({'bench': 'policy-in-loop Lander3D 2^23 envs, FUSED policy+step rollout kernel (%s), T=%d%s'
+                                               % ('tcgen05/TMEM' if tc == '1' else 'warp-MMA', T2, (', obs/action rows recorded' if kw else '') + (', Gaussian exploration noise' if 'action_std' in kw else '')),
+                                      'ms_per_env_step': ms / T2, 'steps_per_s': n * T2 / ms * 1e3}), flush=True)
+                    del fr
+            os.environ.pop('COPTER_B200_POLICY_ROLLOUT_TC', None)
             del env2
         # env-only share of the same loop
         a = torch.full((n, 4), 0.0166, device='cuda')

@@ -27,6 +27,8 @@ COMBOS = [
     ['-DCOPTER_STREAMING=1', '-DCOPTER_K1_SPECIALIZE=0', '-DCOPTER_K_UNROLL=4'],
     ['-DCOPTER_POLICY_POLY_MASK=0x88', '-DCOPTER_POLICY_MT=1'],
     ['-DCOPTER_POLICY_POLY_MASK=0xff', '-DCOPTER_POLICY_POLY_F32X2=0', '-DCOPTER_POLICY_TANH_BF16X2=1'],
+    ['-DCOPTER_POLICY_TC_SLOTS=2', '-DCOPTER_POLICY_TC_SPLIT=2', '-DCOPTER_POLICY_TC_POLY=0'],        # (no tcgen05 fused rollout in these shapes)
+    ['-DCOPTER_POLICY_TC_POLY=8', '-DCOPTER_POLICY_ROLLOUT_TC_CTAS_PER_SM=3', '-DCOPTER_POLICY_TC=0'],
 ]
 
 

@@ -1,5 +1,6 @@
 """Developer tool: the tcgen05 policy kernel against the warp-MMA kernel and the PyTorch fp32 network,
-and their timings.   COPTER_B200_POLICY_TC=1|0 python tools/policy_tc_check.py [envs]"""
+and their timings, then the fused policy + step rollout.
+   COPTER_B200_POLICY_TC=1|0 COPTER_B200_POLICY_ROLLOUT_TC=1|0 python tools/policy_tc_check.py [envs]"""
 import os
 import sys
 
@@ -33,4 +34,15 @@ for variant in ('Lander3D', 'Hover3D', 'Lander2D', 'Lander1D'):
             fused()
         e1.record(); torch.cuda.synchronize()
         print('  policy kernel: %.4f ms per launch (%d envs)' % (e0.elapsed_time(e1) / 50, m), flush=True)
+        T = 16
+        ro = g.FusedPolicyRollout(env, pol.net, T, out_scale=0.2 * 0.0166, out_offset=0.0166)
+        for _ in range(2):
+            ro.run()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(10):
+            ro.run()
+        e1.record(); torch.cuda.synchronize()
+        print('  fused policy + step rollout (tc=%s): %.4f ms per env-step (%d envs, horizon %d)' % (os.environ.get('COPTER_B200_POLICY_ROLLOUT_TC', 'default'), e0.elapsed_time(e1) / (10 * T), m, T), flush=True)
+        del ro
     del env, fused

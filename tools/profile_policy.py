@@ -1,5 +1,5 @@
 """Developer tool: the launches `ncu -k regex:policy` captures for profiles/ -- the tcgen05 / TMEM policy
-kernel (x2), the warp-MMA policy kernel (x2), then the fused policy + step rollout kernel (x2), 2^23 envs."""
+kernel (x2), the warp-MMA policy kernel (x2), then the fused policy + step rollout kernels (tcgen05 x2, warp-MMA x2), 2^23 envs."""
 import os
 import sys
 
@@ -17,6 +17,8 @@ for tc in ('1', '0'):
     for _ in range(2):
         fused()
 ro = g.FusedPolicyRollout(env, pol.net, 8, out_scale=0.2 * 0.0166, out_offset=0.0166)
-for _ in range(2):
-    ro.run()
+for tc in ('1', '0'):                       # the fused policy + step rollout: tcgen05 / TMEM kernel (x2), warp-MMA kernel (x2)
+    os.environ['COPTER_B200_POLICY_ROLLOUT_TC'] = tc
+    for _ in range(2):
+        ro.run()
 torch.cuda.synchronize()

@@ -49,8 +49,10 @@ for variant in ('Lander3D', 'Lander2D', 'Lander1D', 'Hover3D'):
         if n > 1000:
             continue
         ro = g.FusedPolicyRollout(env, pol.net, 6, out_scale=0.02, out_offset=0.0166, store_obs=True, store_actions=True)
-        ro.run()
-        ro.run()
+        for tc in ('1', '0'):                                 # fused rollout on the tcgen05 / TMEM kernel, then on the warp-MMA kernel
+            os.environ['COPTER_B200_POLICY_ROLLOUT_TC'] = tc
+            ro.run()
+            ro.run()
 env = g.LanderVec(1000, seed=2, track_stats=True)
 env.reset()
 for t in range(3):

@@ -31,6 +31,14 @@ VARIANTS['tc_s1x2c4'] = ['-DCOPTER_POLICY_TC_SLOTS=1', '-DCOPTER_POLICY_TC_SPLIT
 VARIANTS['tc_p4'] = ['-DCOPTER_POLICY_TC_POLY=4']     # 4 of every 16 hidden tanh on the FMA pipe
 VARIANTS['tc_p6'] = ['-DCOPTER_POLICY_TC_POLY=6']
 VARIANTS['tc_p8'] = ['-DCOPTER_POLICY_TC_POLY=8']
+VARIANTS['tc_c5'] = ['-DCOPTER_POLICY_TC_CTAS_PER_SM=5']          # 64 TMEM columns per tile: five / six CTAs per SM
+VARIANTS['tc_c6'] = ['-DCOPTER_POLICY_TC_CTAS_PER_SM=6']
+VARIANTS['tc_c5p6'] = ['-DCOPTER_POLICY_TC_CTAS_PER_SM=5', '-DCOPTER_POLICY_TC_POLY=6']
+VARIANTS['tc_c6p6'] = ['-DCOPTER_POLICY_TC_CTAS_PER_SM=6', '-DCOPTER_POLICY_TC_POLY=6']
+VARIANTS['tc_c6p8'] = ['-DCOPTER_POLICY_TC_CTAS_PER_SM=6', '-DCOPTER_POLICY_TC_POLY=8']
+VARIANTS['tc_ro5'] = ['-DCOPTER_POLICY_ROLLOUT_TC_CTAS_PER_SM=5']  # fused rollout: 5 CTAs per SM (<= 80 registers)
+VARIANTS['tc_ro5c5'] = ['-DCOPTER_POLICY_ROLLOUT_TC_CTAS_PER_SM=5', '-DCOPTER_POLICY_TC_CTAS_PER_SM=5']
+VARIANTS['tc_ro3'] = ['-DCOPTER_POLICY_ROLLOUT_TC_CTAS_PER_SM=3']
 VARIANTS['tc_s2x2'] = ['-DCOPTER_POLICY_TC_SLOTS=2', '-DCOPTER_POLICY_TC_SPLIT=2']  # 2 tiles in flight, 2 CTAs per SM, two threads per row
 VARIANTS['nofast'] = ['-DCOPTER_FAST_SUBSTEP=0']      # K-fused loop without the straight-line substep
 VARIANTS['nostreak'] = ['-DCOPTER_CALM_STREAK=0']     # K-fused loop: flags + hot test + two votes on every substep
