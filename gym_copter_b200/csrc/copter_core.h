@@ -308,18 +308,20 @@ COPTER_HD void airborne_integrate(const KParams<T>& kp, L (&s)[12], const Forces
 template <typename T, int NP, bool DIRECT>
 COPTER_HD bool dynamics_update(const KParams<T>& kp, T (&s)[12], int& st, const Forces<T>& f, const T (&p)[NP], T& na, T& nc) {
     na = (T)0; nc = (T)0;
-    T sph, cph, sth, cth, sps, cps;
-    sincos3_t(s[6], s[8], s[10], sph, cph, sth, cth, sps, cps);
-
-    if (DIRECT && st == ST_LANDED) {                               // :147-149
-        const T netz = fma_(f.bz, cph * cth, kp.G);                // :143
-        if (netz < (T)0) st = ST_AIRBORNE;
-    }
-
     const bool touch = s[4] > (T)0 && s[5] > (T)0;                 // :162 (pre-step state)
-    if (st == ST_AIRBORNE && !touch) {                             // :159, :180-187
-        airborne_integrate<T, T, NP, true>(kp, s, f, p, sph, cph, sth, cth, sps, cps, na, nc);
-        return true;
+    // (the sines / cosines are needed only by the take-off test and the airborne step: a vehicle on the ground,
+    // touching it, levelling or crashed goes straight to the status machine)
+    if ((DIRECT && st == ST_LANDED) || (st == ST_AIRBORNE && !touch)) {
+        T sph, cph, sth, cth, sps, cps;
+        sincos3_t(s[6], s[8], s[10], sph, cph, sth, cth, sps, cps);
+        if (DIRECT && st == ST_LANDED) {                           // :147-149
+            const T netz = fma_(f.bz, cph * cth, kp.G);            // :143
+            if (netz < (T)0) st = ST_AIRBORNE;
+        }
+        if (st == ST_AIRBORNE && !touch) {                         // :159, :180-187
+            airborne_integrate<T, T, NP, true>(kp, s, f, p, sph, cph, sth, cth, sps, cps, na, nc);
+            return true;
+        }
     }
     if (st == ST_LEVELING) {                                       // :152-156
         s[6] = (T)0; s[8] = (T)0; st = ST_LANDED;

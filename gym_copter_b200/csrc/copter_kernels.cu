@@ -238,6 +238,20 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
             // machine, no perturbation, one predicated region.  Anything else takes the general step.
             const bool hot = airborne_hot<T>(s, st, steps);
             const bool fast = COPTER_FAST_SUBSTEP && __all_sync(0xffffffffu, (int)!live | (int)hot);
+            // Substep 0 of a launch on a batch whose episodes are spread over all phases: some lane of almost every
+            // warp starts a fresh episode (it reset inside the previous launch) and owes the reset perturbation, which
+            // used to send the whole warp through the general step.  The straight-line step with the perturbation
+            // terms (exactly dynamics_update's airborne case, zeros for the lanes that are not fresh) covers it.
+            bool fresh = false;
+            if (COPTER_FAST_SUBSTEP && COPTER_FRESH_FAST && !fast && k == 0)
+                fresh = __all_sync(0xffffffffu, (int)!live | (int)airborne_hot_fresh<T>(s, st));
+            // A crash takes three steps (touch-down, CRASHED, done; dynamics/__init__.py:162-177, task.py:121), a landing
+            // more: while such a lane is the only thing between the warp and the straight-line step, the airborne
+            // lanes take it anyway and the lane on the ground runs the status machine beside them (divergent, but
+            // its step has no arithmetic), instead of everybody going through the general step.
+            bool mixed = false;
+            if (COPTER_FAST_SUBSTEP && COPTER_GROUND_SPLIT && !Variant<VARIANT>::direct && !fast)
+                mixed = __all_sync(0xffffffffu, (int)!live | (int)hot | (int)on_ground<T>(s, st));
             bool dn = false;
             if (COPTER_CALM_STREAK && fast) {                           // warp-uniform
                 // Streak of straight-line substeps: as long as every live lane stays calm (airborne_calm:
@@ -271,9 +285,10 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
                 }
             } else if (live) {
                 dz_prev = s[5];
-                if (fast) {
+                if (fast || fresh || (mixed && hot)) {
                     const bool tmo = steps == kp.max_steps;
-                    airborne_arith<T, T>(kp, s, forces, na, nc);
+                    if (fresh) { airborne_arith_pert<T, T>(kp, s, forces, pert, na, nc); pert[0] = (T)0; pert[1] = (T)0; pert[2] = (T)0; }
+                    else airborne_arith<T, T>(kp, s, forces, na, nc);
                     steps = min(steps + 1, kp.steps_cap);
                     const int end = airborne_flags<T, VARIANT>(kp, s[0], s[2], s[6], s[8], tmo);
                     ++run.steps;
@@ -286,11 +301,17 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
                     run_step<T>(run, na, nc, cause);
                 }
             }
-            if (dn) {                                                  // only a live lane can have ended
-                live = false;
-                ep_cause = cause;
-                total = run_reward<T, VARIANT>(kp, run, s, cause, na, nc, dz_prev);
-                if (STATS) ep_len = steps - 1;                         // `steps` is 1 right after reset (task.py:191,197)
+            // An env that ends idles for the rest of the launch, so everything its ending needs -- the run's reward, the
+            // terminal observation, the reset -- waits until after the loop, where the lanes that did not end take the
+            // same run_reward call: one converged call instead of a divergent one at every ending.
+            if (dn) { live = false; ep_cause = cause; }                // only a live lane can have ended
+        }
+        done_any = valid && !live;
+        if (valid) {
+            total = run_reward<T, VARIANT>(kp, run, s, done_any ? ep_cause : 0, na, nc, dz_prev);
+            if (STATS) { n_steps = run.steps; ret += total; }
+            if (done_any) {
+                if (STATS) { ep_len = steps - 1; ep_ret = ret; ret = (T)0; }   // `steps` is 1 right after reset (task.py:191,197)
                 if (a.final_obs) {   // terminal observation; rows of unfinished envs stay untouched
 #pragma unroll
                     for (int j = 0; j < O; ++j) a.final_obs[i * O + j] = (float)s[Variant<VARIANT>::first + j];
@@ -299,14 +320,6 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
                     reset_state<T>(kp, s, st, steps);
                     episode = (episode + 1) & kp.ep_mask;
                 }
-            }
-        }
-        done_any = valid && !live;
-        if (valid) {
-            if (!done_any) total = run_reward<T, VARIANT>(kp, run, s, 0, na, nc, dz_prev);
-            if (STATS) {
-                n_steps = run.steps; ret += total;
-                if (done_any) { ep_ret = ret; ret = (T)0; }
             }
         }
     }

@@ -40,6 +40,16 @@ namespace copter {
 #ifndef COPTER_FAST_SUBSTEP
 #define COPTER_FAST_SUBSTEP 1     // 0 (A/B knob): every substep of a K-fused launch takes the general env_advance
 #endif
+#ifndef COPTER_FRESH_FAST
+#define COPTER_FRESH_FAST 0      // 1 (A/B knob): a warp with a fresh episode in it takes a straight-line step WITH the reset perturbation
+                                 // at substep 0 instead of the general step.  Measured slower (K = 16: 1.484 vs 1.443 ms): off.
+#endif
+#ifndef COPTER_GROUND_SPLIT
+#define COPTER_GROUND_SPLIT 0    // 1 (A/B knob): while a lane on the ground is all that keeps a warp from the straight-line step, the airborne
+                                 // lanes take it and that lane runs the status machine beside them.  Measured slower (K = 16: 1.511 vs
+                                 // 1.444 ms, profiles/r2_ab_k_loop.txt): the general step is only ~35 % dearer than the straight-line one,
+                                 // two divergent passes cost more.  Off.
+#endif
 #ifndef COPTER_CALM_STREAK
 #define COPTER_CALM_STREAK 1     // 0 (A/B knob): every straight-line substep re-derives the ending flags and the hot test
 #endif
@@ -161,6 +171,17 @@ template <typename T>
 __device__ __forceinline__ bool airborne_hot(const T (&s)[12], int st, int steps) {
     return airborne_hot_c<T>(s[4], s[5], s[6], s[8], s[10], st, steps);
 }
+// A vehicle the airborne arithmetic does not apply to (on the ground, touching it, levelling, crashed): its step is
+// the status machine alone -- env_advance without sines, cosines or integration (dynamics_update skips them).
+template <typename T>
+__device__ __forceinline__ bool on_ground(const T (&s)[12], int st) {
+    return st != ST_AIRBORNE || (s[4] > (T)0 && s[5] > (T)0);
+}
+// the same without the "past the first step" condition: the precondition of airborne_arith_pert()
+template <typename T>
+__device__ __forceinline__ bool airborne_hot_fresh(const T (&s)[12], int st) {
+    return airborne_hot_c<T>(s[4], s[5], s[6], s[8], s[10], st, 0);
+}
 
 // Returns the step's ending flags: bit 0 out of bounds, bit 1 over-angle (exclusive: the reference
 // tests them with if / elif, task.py:111-118), bit 2 the env's own step limit; 0 = the episode goes
@@ -174,6 +195,15 @@ __device__ __forceinline__ void airborne_arith(const KParams<T>& kp, L (&s)[12],
     else sincos3_t(s[6], s[8], s[10], sph, cph, sth, cth, sps, cps);
     const L none[3] = {L((T)0), L((T)0), L((T)0)};
     airborne_integrate<L, T, 3, false>(kp, s, f, none, sph, cph, sth, cth, sps, cps, na, nc);
+}
+// the same with the reset perturbation `p` of a fresh episode (zeros for an env past its first step): exactly the
+// airborne case of dynamics_update, which always carries the perturbation terms
+template <typename L, typename T>
+__device__ __forceinline__ void airborne_arith_pert(const KParams<T>& kp, L (&s)[12], const Forces<L>& f, const L (&p)[3], L& na, L& nc) {
+    L sph, cph, sth, cth, sps, cps;
+    if constexpr (sizeof(T) == 4) { sincos_poly<L>(s[6], sph, cph); sincos_poly<L>(s[8], sth, cth); sincos_poly<L>(s[10], sps, cps); }
+    else sincos3_t(s[6], s[8], s[10], sph, cph, sth, cth, sps, cps);
+    airborne_integrate<L, T, 3, true>(kp, s, f, p, sph, cph, sth, cth, sps, cps, na, nc);
 }
 // task.py:111-130 with the stale status AIRBORNE, on the state after the step
 template <typename T, int VARIANT>
