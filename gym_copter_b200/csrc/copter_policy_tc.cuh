@@ -88,10 +88,35 @@ __device__ __forceinline__ void bar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void bar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(bar)) : "memory");
 }
+// Waiting warps must not eat the issue slots of the working ones: a warp's TMEM lane quarter ties it to the SM
+// sub-partition warp % 4, so the MMA warps of ALL resident CTAs (warp 4) sit on sub-partition 0, and a tight
+// try_wait loop there starves that sub-partition's epilogue warps -- whose tiles cannot finish before they do.
+// COPTER_POLICY_TC_WAIT: 0 = tight loop (try_wait's default, short suspension), 1 = try_wait with a suspend-time
+// hint (the thread sleeps in hardware until the phase completes or the hint expires), 2 = tight loop + __nanosleep.
+#ifndef COPTER_POLICY_TC_WAIT
+#define COPTER_POLICY_TC_WAIT 1
+#endif
+#ifndef COPTER_POLICY_TC_WAIT_NS
+#define COPTER_POLICY_TC_WAIT_NS 20000
+#endif
 __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+#if COPTER_POLICY_TC_WAIT == 1
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" :: "r"(smem_addr(bar)), "r"(parity), "r"((uint32_t)COPTER_POLICY_TC_WAIT_NS) : "memory");
+#elif COPTER_POLICY_TC_WAIT == 2
+    uint32_t ok = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(COPTER_POLICY_TC_WAIT_NS);
+    }
+#else
     asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
                  "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
                  "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
