@@ -1215,6 +1215,7 @@ copter_policy_rollout_tc_kernel(const __grid_constant__ KParams<float> kp, const
     if (t_id == 0) {
         tc::bar_init(&sm.done[0], 1);
         tc::bar_init(&sm.ready[0], tc::kTile);
+        tc::bar_init(&sm.clc_bar[0], 1); tc::bar_init(&sm.clc_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) tc::tmem_alloc(sm);
@@ -1228,25 +1229,29 @@ copter_policy_rollout_tc_kernel(const __grid_constant__ KParams<float> kp, const
     const int64_t n_tiles = (a.n + tc::kTile - 1) / tc::kTile;
 
     if (warp == kMmaWarp) {
-        // ===== MMA issuer: 3 layers per env-step, n_steps env-steps per tile =====
-        if (lane == 0) {
-            uint32_t phase = 0;
-            for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x)
-                for (int t = 0; t < a.n_steps; ++t)
+        // ===== MMA issuer: 3 layers per env-step, n_steps env-steps per tile.  Warp-uniform, the issuing lane elected per
+        // layer (tc::issue_layer_uniform); tiles by cluster launch control, one request in flight (tc::next_tile) =====
+        const tc::LayerDescs d = tc::make_layer_descs(sm, 0, tmem_base);
+        uint32_t phase = 0, clc_phase = 0, tile_id = blockIdx.x;
+        tc::request_tile(sm, 0);
+        for (int k = 0; tile_id != tc::kNoTile; ++k) {
+            for (int t = 0; t < a.n_steps; ++t)
 #pragma unroll
-                    for (int layer = 1; layer <= 3; ++layer) {
-                        tc::bar_wait(&sm.ready[0], phase); phase ^= 1u;
-                        tc::issue_layer(sm, 0, layer, tmem_base);
-                    }
+                for (int layer = 1; layer <= 3; ++layer) {
+                    tc::bar_wait(&sm.ready[0], phase); phase ^= 1u;
+                    tc::issue_layer_uniform(d, layer, &sm.done[0]);
+                }
+            tile_id = tc::next_tile(sm, k, tile_id, clc_phase, n_tiles);
+            if (tile_id != tc::kNoTile) tc::request_tile(sm, k + 1);      // clc_resp[(k + 1) & 1] was last read at the end of tile k - 1
         }
     } else {
         // ===== epilogue warps: thread <-> env row <-> TMEM lane =====
         const int row = t_id;                                                        // 0..127
         const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);        // this warp's quarter of the TMEM lanes
         tc::SlotSmem& ss = sm.slot[0];
-        uint32_t phase = 0;
-        for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
-            const int64_t row0 = tile_id * tc::kTile + warp * 32, i = row0 + lane;
+        uint32_t phase = 0, clc_phase = 0, tile_id = blockIdx.x;
+        for (int k = 0; tile_id != tc::kNoTile; tile_id = tc::next_tile(sm, k, tile_id, clc_phase, n_tiles), ++k) {
+            const int64_t row0 = (int64_t)tile_id * tc::kTile + warp * 32, i = row0 + lane;
             const bool valid = i < a.n;
             const int64_t left = a.n - row0;
             const int rows = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
@@ -1716,7 +1721,8 @@ int launch_policy_v(const PolicyArgs& a, cudaStream_t s) {
         }
         const int64_t tiles = (a.n + tc::kTile - 1) / tc::kTile, pairs = (tiles + tc::kSlots - 1) / tc::kSlots;
         const int64_t cap = (int64_t)sm_count() * COPTER_POLICY_TC_CTAS_PER_SM;
-        kernel<<<(int)(pairs < cap ? pairs : cap), tc::kThreads, smem, s>>>(t);
+        // cluster launch control: one CTA per tile in the grid, the resident CTAs take the pending ones over
+        kernel<<<(int)(tc::kClc ? tiles : (pairs < cap ? pairs : cap)), tc::kThreads, smem, s>>>(t);
         return (int)cudaGetLastError();
     }
     copter_mlp_policy_kernel<V::first, V::O, V::A><<<persistent_grid_for<copter_mlp_policy_kernel<V::first, V::O, V::A>>(a.n), 128, 0, s>>>(a);
@@ -1735,7 +1741,7 @@ int launch_policy_rollout_tc(const KParams<float>& kp, const PolicyRolloutArgs& 
         configured[dev] = true;
     }
     const int64_t tiles = (a.n + tc::kTile - 1) / tc::kTile, cap = (int64_t)sm_count() * COPTER_POLICY_ROLLOUT_TC_CTAS_PER_SM;
-    kernel<<<(int)(tiles < cap ? tiles : cap), tc::kTile + 32, smem, s>>>(kp, a);
+    kernel<<<(int)(tc::kClc ? tiles : (tiles < cap ? tiles : cap)), tc::kTile + 32, smem, s>>>(kp, a);
     return (int)cudaGetLastError();
 }
 #endif

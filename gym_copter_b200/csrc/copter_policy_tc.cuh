@@ -33,6 +33,12 @@ constexpr int kTile = 128, kH = 64, kK1 = 16, kN3 = 16;
 #define COPTER_POLICY_TC_SLOTS 1             // tiles in flight per CTA
 #endif
 constexpr int kSlots = COPTER_POLICY_TC_SLOTS;
+#ifndef COPTER_POLICY_TC_ONES_ROWS
+#define COPTER_POLICY_TC_ONES_ROWS 8
+#endif
+constexpr int kOnesRows = COPTER_POLICY_TC_ONES_ROWS;
+static_assert(kOnesRows == 8 || kOnesRows == 128, "the ones tile: one 8-row group read 16 times, or all 128 rows");
+constexpr uint32_t kOnesSBO = kOnesRows == 8 ? 0u : 256u;       // = (kK1 / 8) * 128 for the full tile
 static_assert(kSlots >= 1 && kSlots <= 4, "TMEM budget: 64 columns per slot, <= 256 columns per CTA");
 // TMEM columns of a CTA: 64 per slot.  The 16 output accumulator columns of layer 3 REUSE the first columns of the
 // slot's hidden accumulator: layer 3 is issued only after every epilogue thread has pulled its layer-2 row out of
@@ -58,10 +64,15 @@ struct alignas(128) Smem {
     __nv_bfloat16 b2[kH * kK1];          // layer 2 bias step [64 x 16] (column 0 = hi, 1 = lo)
     __nv_bfloat16 w3[kN3 * kH];          // layer 3 weights  [16 x 64]  (rows ACT.. are zero)
     __nv_bfloat16 b3[kN3 * kK1];         // layer 3 bias step [16 x 16]
-    __nv_bfloat16 ones[kTile * kK1];     // A tile of the bias steps: columns 0, 1 = 1
+    // A tile of the bias steps: columns 0, 1 = 1.  All 128 rows are the same, so (COPTER_POLICY_TC_ONES_ROWS = 8) only ONE
+    // 8-row group is stored and the descriptor's stride between row groups is 0: 256 B instead of 4 KB, which is what
+    // lets a seventh CTA fit into an SM's shared memory.
+    __nv_bfloat16 ones[kOnesRows * kK1];
     SlotSmem slot[kSlots];               // kSlots tiles in flight per CTA (see the kernel)
     uint64_t done[kSlots];               // MMA warp -> epilogue warps: the slot's accumulator is complete (tcgen05.commit)
     uint64_t ready[kSlots];              // epilogue threads -> MMA warp: the slot's next A tile is in shared memory (128 arrivals)
+    uint64_t clc_bar[2];                 // cluster launch control: response k has landed in clc_resp[k & 1] (see next_tile)
+    alignas(16) uint4 clc_resp[2];
     uint32_t tmem_base;
 };
 
@@ -121,6 +132,33 @@ __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem()  { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one lane of a converged warp (the MMA warp runs its loop warp-uniformly and elects the issuing lane per instruction
+// group: the descriptors then live in uniform registers instead of being moved there, R2UR, before every MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// Cluster launch control (sm_100): the grid holds one CTA per tile; a running CTA cancels a CTA that has not been
+// launched yet and takes over its block index.  The 16-byte response lands in shared memory through an mbarrier.
+__device__ __forceinline__ void clc_try_cancel(void* resp16, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 16;" :: "r"(smem_addr(bar)) : "memory");
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+                 :: "r"(smem_addr(resp16)), "r"(smem_addr(bar)) : "memory");
+}
+constexpr uint32_t kNoTile = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t clc_response(const void* resp16) {      // the cancelled CTA's blockIdx.x, or kNoTile
+    uint32_t ok, x;
+    asm volatile("{\n\t.reg .b128 r;\n\t.reg .pred p;\n\t.reg .b64 lo, hi;\n\t.reg .b32 y, z, w;\n\t"
+                 "ld.shared.v2.b64 {lo, hi}, [%2];\n\t"
+                 "mov.b128 r, {lo, hi};\n\t"
+                 "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p, r;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t"
+                 "mov.u32 %1, 0;\n\t"
+                 "@p clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%1, y, z, w}, r;\n\t}"
+                 : "=r"(ok), "=r"(x) : "r"(smem_addr(resp16)) : "memory");
+    return ok ? x : kNoTile;
+}
 
 // 16 consecutive fp32 columns of this thread's TMEM lane (asynchronous: tmem_wait() before the values are used)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -138,6 +176,27 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j]);
 }
+
+// Developer timeline (tools/microbench/policy_tc_trace.cu): clock64 stamps of a few CTAs' steady-state tiles --
+// who = epilogue warp 0..3 (lane 0) or 4 = the MMA thread; event = 3 * layer + {0: woke up, 1: work done, 2: arrived / committed};
+// 12 + 8 * (layer - 1) + 2 q + {0: chunk q of the hidden accumulator has landed, 1: its tanh / packs / stores are issued}.
+#ifdef COPTER_POLICY_TC_TRACE
+constexpr int kTraceCtas = 4, kTraceTiles = 8, kTraceFirstTile = 30, kTraceCtaStep = 211;
+__device__ long long g_trace[kTraceCtas][kTraceTiles][5][32];
+__device__ __forceinline__ void trace(int who, int round, int event) {
+    const int c = blockIdx.x / kTraceCtaStep, r = round - kTraceFirstTile;
+    if (blockIdx.x % kTraceCtaStep == 0 && c < kTraceCtas && r >= 0 && r < kTraceTiles) g_trace[c][r][who][event] = clock64();
+}
+__device__ long long g_trace_cta[kTraceCtas][4];          // kernel entry, set-up done (weights in shared memory, TMEM allocated), last tile done, exit
+__device__ __forceinline__ void trace_cta(int event) {
+    if (threadIdx.x == 0 && blockIdx.x % kTraceCtaStep == 0 && blockIdx.x / kTraceCtaStep < kTraceCtas) g_trace_cta[blockIdx.x / kTraceCtaStep][event] = clock64();
+}
+#define TC_TRACE(cond, who, round, event) do { if (cond) trace(who, round, event); } while (0)
+#define TC_TRACE_CTA(event) trace_cta(event)
+#else
+#define TC_TRACE_CTA(event) do { } while (0)
+#define TC_TRACE(cond, who, round, event) do { } while (0)
+#endif
 
 __device__ __forceinline__ float tanh_mufu(float x) {
     float y;
@@ -174,12 +233,13 @@ __device__ __forceinline__ float tanh_fma(float x) {
 // PIPELINED: the load of chunk q + 1 is in flight under the tanh of chunk q (two 16-register buffers); without it
 // one buffer, each load awaited before use (16 registers fewer: the fused rollout kernel, which also holds an env).
 template <int NCHUNK, bool PIPELINED = true>      // NCHUNK chunks of 16 columns starting at column col0 (the row's 64 columns may be split between two threads)
-__device__ __forceinline__ void hidden_epilogue(uint32_t taddr_row, __nv_bfloat16* a_tile, int row, int col0) {
+__device__ __forceinline__ void hidden_epilogue(uint32_t taddr_row, __nv_bfloat16* a_tile, int row, int col0, int trace_round = 0, int trace_event = 0) {
     uint32_t r[PIPELINED ? 2 : 1][16];
     tmem_ld16(taddr_row + col0, r[0]);
 #pragma unroll
     for (int q = 0; q < NCHUNK; ++q) {
         tmem_wait();                                               // chunk q has landed
+        TC_TRACE((threadIdx.x & 31) == 0, (threadIdx.x >> 5) & 3, trace_round, trace_event + 2 * q);
         constexpr int kMask = PIPELINED ? 1 : 0;
         if (PIPELINED && q + 1 < NCHUNK) tmem_ld16(taddr_row + col0 + 16 * (q + 1), r[(q + 1) & kMask]);
         float y[16];
@@ -196,34 +256,59 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr_row, __nv_bfloat1
         for (int j = 0; j < 8; ++j) w[j] = pack2(y[2 * j], y[2 * j + 1]);
         *reinterpret_cast<uint4*>(a_tile + canon(row, col0 + 16 * q, kH / 8)) = make_uint4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<uint4*>(a_tile + canon(row, col0 + 16 * q + 8, kH / 8)) = make_uint4(w[4], w[5], w[6], w[7]);
+        TC_TRACE((threadIdx.x & 31) == 0, (threadIdx.x >> 5) & 3, trace_round, trace_event + 2 * q + 1);
     }
 }
 
 // Weights -> shared memory in the canonical layout, biases split into bf16 hi + lo.  Whole CTA; sync after.
+// The global loads are issued in batches of kWBatch per thread before anything is stored: one load per loop trip
+// (the first version) made the set-up 23 000 cycles per CTA -- 4 % of a 2^23-env launch -- of exposed L2 latency.
 template <int OBS, int ACT>
 __device__ __forceinline__ void load_weights(Smem& sm, const float* w1, const float* b1, const float* w2, const float* b2,
                                              const float* w3, const float* b3) {
     const __nv_bfloat16 zero = __float2bfloat16(0.0f), one = __float2bfloat16(1.0f);
     auto hi = [](float b) { return __float2bfloat16(b); };
     auto lo = [](float b) { return __float2bfloat16(b - __bfloat162float(__float2bfloat16(b))); };
-    for (int e = threadIdx.x; e < kH * kK1; e += blockDim.x) {
-        const int n = e / kK1, k = e % kK1;
-        sm.w1[canon(n, k, kK1 / 8)] = k < OBS ? __float2bfloat16(w1[n * OBS + k]) : (k == 14 ? hi(b1[n]) : (k == 15 ? lo(b1[n]) : zero));
-        sm.b2[canon(n, k, kK1 / 8)] = k == 0 ? hi(b2[n]) : (k == 1 ? lo(b2[n]) : zero);
+    constexpr int kWBatch = 8;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int base = 0; base < kH * kH; base += kWBatch * nt) {
+        float v[kWBatch];
+#pragma unroll
+        for (int u = 0; u < kWBatch; ++u) { const int e = base + u * nt + tid; v[u] = e < kH * kH ? __ldg(w2 + e) : 0.0f; }
+#pragma unroll
+        for (int u = 0; u < kWBatch; ++u) { const int e = base + u * nt + tid; if (e < kH * kH) sm.w2[canon(e / kH, e % kH, kH / 8)] = __float2bfloat16(v[u]); }
     }
-    for (int e = threadIdx.x; e < kH * kH; e += blockDim.x) {
-        const int n = e / kH, k = e % kH;
-        sm.w2[canon(n, k, kH / 8)] = __float2bfloat16(w2[n * kH + k]);
+    float vb1 = 0.0f, vb2 = 0.0f, vb3 = 0.0f;                    // the biases: rows tid of the bias columns / bias tiles
+    if (tid < kH) { vb1 = __ldg(b1 + tid); vb2 = __ldg(b2 + tid); }
+    if (tid < ACT) vb3 = __ldg(b3 + tid);
+    for (int base = 0; base < kH * kK1; base += kWBatch * nt) {
+        float v[kWBatch];
+#pragma unroll
+        for (int u = 0; u < kWBatch; ++u) { const int e = base + u * nt + tid, n = e / kK1, k = e % kK1; v[u] = (e < kH * kK1 && k < OBS) ? __ldg(w1 + n * OBS + k) : 0.0f; }
+#pragma unroll
+        for (int u = 0; u < kWBatch; ++u) {
+            const int e = base + u * nt + tid, n = e / kK1, k = e % kK1;
+            if (e < kH * kK1 && k < 14) sm.w1[canon(n, k, kK1 / 8)] = __float2bfloat16(v[u]);          // columns 14, 15: the bias, below
+        }
     }
-    for (int e = threadIdx.x; e < kN3 * kH; e += blockDim.x) {
-        const int n = e / kH, k = e % kH;
-        sm.w3[canon(n, k, kH / 8)] = n < ACT ? __float2bfloat16(w3[n * kH + k]) : zero;
+    {
+        float v[kWBatch];
+        static_assert(kN3 * kH <= kWBatch * 128, "one batch covers layer 3");
+#pragma unroll
+        for (int u = 0; u < kWBatch; ++u) { const int e = u * nt + tid, n = e / kH; v[u] = (e < kN3 * kH && n < ACT) ? __ldg(w3 + e) : 0.0f; }
+#pragma unroll
+        for (int u = 0; u < kWBatch; ++u) { const int e = u * nt + tid; if (e < kN3 * kH) sm.w3[canon(e / kH, e % kH, kH / 8)] = __float2bfloat16(v[u]); }
     }
-    for (int e = threadIdx.x; e < kN3 * kK1; e += blockDim.x) {
-        const int n = e / kK1, k = e % kK1;
-        sm.b3[canon(n, k, kK1 / 8)] = (n < ACT && k == 0) ? hi(b3[n]) : ((n < ACT && k == 1) ? lo(b3[n]) : zero);
+    if (tid < kH) {
+        sm.w1[canon(tid, 14, kK1 / 8)] = hi(vb1); sm.w1[canon(tid, 15, kK1 / 8)] = lo(vb1);
+#pragma unroll
+        for (int k = 0; k < kK1; ++k) sm.b2[canon(tid, k, kK1 / 8)] = k == 0 ? hi(vb2) : (k == 1 ? lo(vb2) : zero);
     }
-    for (int e = threadIdx.x; e < kTile * kK1; e += blockDim.x) {
+    if (tid < kN3) {
+#pragma unroll
+        for (int k = 0; k < kK1; ++k) sm.b3[canon(tid, k, kK1 / 8)] = (tid < ACT && k == 0) ? hi(vb3) : ((tid < ACT && k == 1) ? lo(vb3) : zero);
+    }
+    for (int e = tid; e < kOnesRows * kK1; e += nt) {
         const int r = e / kK1, k = e % kK1;
         sm.ones[canon(r, k, kK1 / 8)] = k < 2 ? one : zero;
     }
@@ -249,15 +334,59 @@ __device__ __forceinline__ void issue_layer(Smem& sm, int slot, int layer, uint3
         for (int j = 0; j < kH / 16; ++j)
             mma_bf16(tmem_base + col_hidden(slot), make_desc(reinterpret_cast<const char*>(ss.a) + j * kStep, kLBO, kSBO64),
                      make_desc(reinterpret_cast<const char*>(sm.w2) + j * kStep, kLBO, kSBO64), idesc64, j > 0 ? 1u : 0u);
-        mma_bf16(tmem_base + col_hidden(slot), make_desc(sm.ones, kLBO, kSBO16), make_desc(sm.b2, kLBO, kSBO16), idesc64, 1u);
+        mma_bf16(tmem_base + col_hidden(slot), make_desc(sm.ones, kLBO, kOnesSBO), make_desc(sm.b2, kLBO, kSBO16), idesc64, 1u);
     } else {                     // D[128 x 16] = A[128 x 64] W3^T + ones b3^T
 #pragma unroll
         for (int j = 0; j < kH / 16; ++j)
             mma_bf16(tmem_base + col_out(slot), make_desc(reinterpret_cast<const char*>(ss.a) + j * kStep, kLBO, kSBO64),
                      make_desc(reinterpret_cast<const char*>(sm.w3) + j * kStep, kLBO, kSBO64), idesc16, j > 0 ? 1u : 0u);
-        mma_bf16(tmem_base + col_out(slot), make_desc(sm.ones, kLBO, kSBO16), make_desc(sm.b3, kLBO, kSBO16), idesc16, 1u);
+        mma_bf16(tmem_base + col_out(slot), make_desc(sm.ones, kLBO, kOnesSBO), make_desc(sm.b3, kLBO, kSBO16), idesc16, 1u);
     }
     mma_commit(&sm.done[slot]);
+}
+
+// The same for a warp-uniform MMA warp: every descriptor of a slot is built once, outside the elected branch, so the
+// compiler keeps them in uniform registers; the elected lane then issues a layer's MMAs and the commit back to back.
+// (Issued from inside an `if (lane == 0)` branch, each MMA was preceded by R2UR moves and descriptor arithmetic: the
+// timeline of tools/microbench/policy_tc_trace.cu showed 250 / 570 / 600 cycles to ISSUE layers 1 / 2 / 3 -- 28 % of
+// a tile's 5100-cycle chain.)
+struct LayerDescs {
+    uint64_t a1, w1, a[kH / 16], w2[kH / 16], ones, b2, w3[kH / 16], b3;
+    uint32_t d_hidden, d_out;
+};
+__device__ __forceinline__ LayerDescs make_layer_descs(Smem& sm, int slot, uint32_t tmem_base) {
+    constexpr uint32_t kLBO = 128, kSBO16 = (kK1 / 8) * 128, kSBO64 = (kH / 8) * 128, kStep = 256;
+    LayerDescs d;
+    SlotSmem& ss = sm.slot[slot];
+    d.a1 = make_desc(ss.a1(), kLBO, kSBO16); d.w1 = make_desc(sm.w1, kLBO, kSBO16);
+#pragma unroll
+    for (int j = 0; j < kH / 16; ++j) {
+        d.a[j] = make_desc(reinterpret_cast<const char*>(ss.a) + j * kStep, kLBO, kSBO64);
+        d.w2[j] = make_desc(reinterpret_cast<const char*>(sm.w2) + j * kStep, kLBO, kSBO64);
+        d.w3[j] = make_desc(reinterpret_cast<const char*>(sm.w3) + j * kStep, kLBO, kSBO64);
+    }
+    d.ones = make_desc(sm.ones, kLBO, kOnesSBO); d.b2 = make_desc(sm.b2, kLBO, kSBO16); d.b3 = make_desc(sm.b3, kLBO, kSBO16);
+    d.d_hidden = tmem_base + col_hidden(slot); d.d_out = tmem_base + col_out(slot);
+    return d;
+}
+__device__ __forceinline__ void issue_layer_uniform(const LayerDescs& d, int layer, uint64_t* done) {     // whole warp, converged
+    constexpr uint32_t idesc64 = make_idesc(kH), idesc16 = make_idesc(kN3);
+    fence_after_sync();
+    if (elect_one()) {
+        if (layer == 1) {
+            mma_bf16(d.d_hidden, d.a1, d.w1, idesc64, 0u);
+        } else if (layer == 2) {
+#pragma unroll
+            for (int j = 0; j < kH / 16; ++j) mma_bf16(d.d_hidden, d.a[j], d.w2[j], idesc64, j > 0 ? 1u : 0u);
+            mma_bf16(d.d_hidden, d.ones, d.b2, idesc64, 1u);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kH / 16; ++j) mma_bf16(d.d_out, d.a[j], d.w3[j], idesc16, j > 0 ? 1u : 0u);
+            mma_bf16(d.d_out, d.ones, d.b3, idesc16, 1u);
+        }
+        mma_commit(done);
+    }
+    __syncwarp();
 }
 
 // this thread's observation -> its row of the slot's layer-1 A tile (16 bf16: OBS values, zeros, 1, 1)
@@ -290,9 +419,35 @@ __device__ __forceinline__ void tmem_free(uint32_t base) {     // warp 0, conver
 #define COPTER_POLICY_TC_SPLIT 1             // epilogue threads per env row: 1, or 2 (each takes 32 of the 64 hidden columns)
 #endif
 #ifndef COPTER_POLICY_TC_CTAS_PER_SM
-#define COPTER_POLICY_TC_CTAS_PER_SM (COPTER_POLICY_TC_SLOTS == 1 ? (COPTER_POLICY_TC_SPLIT == 1 ? 5 : 3) : 2)   // x kTmemCols <= the SM's 512 TMEM columns
+#define COPTER_POLICY_TC_CTAS_PER_SM (COPTER_POLICY_TC_SLOTS == 1 ? (COPTER_POLICY_TC_SPLIT == 1 ? 7 : 3) : 2)   // x kTmemCols <= the SM's 512 TMEM columns
+#endif
+// Tile scheduling of the one-tile-in-flight shape: 1 = cluster launch control (grid = one CTA per tile; a resident CTA
+// cancels a pending one and takes over its tile), 0 = static grid stride.  The warp scheduler favours the warps of the
+// CTA that arrived first on an SM: with a static split the first CTA of an SM finished its 88 tiles after 469 000 cycles
+// and the fifth after 611 000 (the launch's duration) -- with stolen tiles every CTA works until the tiles run out.
+#ifndef COPTER_POLICY_TC_CLC
+#define COPTER_POLICY_TC_CLC 1
 #endif
 constexpr int kSplit = COPTER_POLICY_TC_SPLIT;
+constexpr bool kSimple = COPTER_POLICY_TC_SLOTS == 1 && COPTER_POLICY_TC_SPLIT == 1;      // the shipped shape: its own, leaner loop
+constexpr bool kClc = kSimple && COPTER_POLICY_TC_CLC != 0;
+// Tile k + 1 of a CTA (tile 0 is blockIdx.x): the answer to try_cancel k, read by every thread of both roles from
+// clc_resp[k & 1] once clc_bar[k & 1] has completed -- or, without cluster launch control, a grid stride.
+__device__ __forceinline__ uint32_t next_tile(Smem& sm, int k, uint32_t cur, uint32_t& clc_phase, int64_t n_tiles) {
+    if constexpr (kClc) {
+        bar_wait(&sm.clc_bar[k & 1], (clc_phase >> (k & 1)) & 1u); clc_phase ^= 1u << (k & 1);
+        return clc_response(&sm.clc_resp[k & 1]);
+    } else {
+        return (int64_t)cur + gridDim.x < n_tiles ? cur + gridDim.x : kNoTile;
+    }
+}
+// the MMA warp (converged): ask for the tile after next -- answer k + 1 -- unless answer k was "nothing left"
+__device__ __forceinline__ void request_tile(Smem& sm, int k_next) {
+    if constexpr (kClc) {
+        if (elect_one()) { fence_async_smem(); clc_try_cancel(&sm.clc_resp[k_next & 1], &sm.clc_bar[k_next & 1]); }
+        __syncwarp();
+    }
+}
 constexpr int kEpilogueThreads = kTile * kSplit;
 constexpr int kThreads = kEpilogueThreads + 32;      // the epilogue warps + the MMA warp
 
@@ -328,8 +483,10 @@ copter_mlp_policy_tc_kernel(const __grid_constant__ Args a) {
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int t = threadIdx.x, warp = t >> 5;
     constexpr int kMmaWarp = kEpilogueThreads / 32;
+    TC_TRACE_CTA(0);
     if (t == 0) {
         for (int q = 0; q < kSlots; ++q) { bar_init(&sm.done[q], 1); bar_init(&sm.ready[q], kEpilogueThreads); }
+        bar_init(&sm.clc_bar[0], 1); bar_init(&sm.clc_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) tmem_alloc(sm);
@@ -338,16 +495,103 @@ copter_mlp_policy_tc_kernel(const __grid_constant__ Args a) {
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    TC_TRACE_CTA(1);
     const uint32_t tmem_base = sm.tmem_base;
     const int64_t n_tiles = (a.n + kTile - 1) / kTile;
     // slot s works through tiles blockIdx.x + (kSlots r + s) gridDim.x, r = 0, 1, ...: both roles walk the same sequence
     const int64_t stride = kSlots * (int64_t)gridDim.x;
     auto any = [](const int (&l)[kSlots]) { int v = 0; for (int q = 0; q < kSlots; ++q) v |= l[q]; return v != 0; };
 
+    if constexpr (kSimple) {
+        // ===== one tile in flight per CTA, one epilogue thread per env row =====
+        // Tile k of this CTA: k = 0 is blockIdx.x; tile k + 1 is the answer to try_cancel k (CLC) or tile k + gridDim.x.
+        // The MMA warp keeps one try_cancel in flight; both roles read answer k from clc_resp[k & 1] after clc_bar[k & 1]
+        // -- the epilogue threads after they have handed layer 2 its A tile, i.e. while they would only wait -- and
+        // clc_resp[k & 1] is re-armed (try_cancel k + 2) only after every epilogue thread has arrived for layer 1 of tile
+        // k + 1, which it does after that read.
+        if (warp == kMmaWarp) {
+            const LayerDescs d = make_layer_descs(sm, 0, tmem_base);
+            uint32_t tile = blockIdx.x, phase = 0, clc_phase = 0;
+            request_tile(sm, 0);
+            for (int k = 0; tile != kNoTile; ++k) {
+                bar_wait(&sm.ready[0], phase); phase ^= 1u;
+                TC_TRACE((t & 31) == 0, 4, k, 0);
+                issue_layer_uniform(d, 1, &sm.done[0]);
+                TC_TRACE((t & 31) == 0, 4, k, 2);
+                const uint32_t nxt = next_tile(sm, k, tile, clc_phase, n_tiles);
+                if (nxt != kNoTile) request_tile(sm, k + 1);          // (a failed try_cancel is the last one)
+#pragma unroll
+                for (int layer = 2; layer <= 3; ++layer) {
+                    bar_wait(&sm.ready[0], phase); phase ^= 1u;
+                    TC_TRACE((t & 31) == 0, 4, k, 3 * (layer - 1));
+                    issue_layer_uniform(d, layer, &sm.done[0]);
+                    TC_TRACE((t & 31) == 0, 4, k, 3 * (layer - 1) + 2);
+                }
+                tile = nxt;
+            }
+        } else {
+            const int row = t;
+            const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);       // this warp's quarter of the 128 TMEM lanes
+            const float4* planes = reinterpret_cast<const float4*>(a.state);
+            auto fetch = [&](uint32_t tl, float4 (&p)[3]) {
+                const int64_t i = (int64_t)tl * kTile + row;
+                if (tl != kNoTile && i < a.n) { p[0] = planes[i]; p[1] = planes[a.stride + i]; p[2] = planes[2 * a.stride + i]; }
+                else p[0] = p[1] = p[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            uint32_t tile = blockIdx.x, phase = 0, clc_phase = 0;
+            float4 nxt[3];
+            fetch(tile, nxt);
+            write_obs_row<FIRST, OBS>(sm.slot[0], row, nxt);
+            fence_before_sync();
+            bar_arrive(&sm.ready[0]);
+            for (int k = 0; tile != kNoTile; ++k) {
+                uint32_t nxt_tile = kNoTile;
+#pragma unroll
+                for (int layer = 1; layer <= 2; ++layer) {
+                    bar_wait(&sm.done[0], phase); phase ^= 1u;
+                    fence_after_sync();
+                    TC_TRACE((t & 31) == 0, warp, k, 3 * (layer - 1));
+                    hidden_epilogue<4>(lane_base + col_hidden(0), sm.slot[0].a, row, 0, k, 12 + 8 * (layer - 1));      // (layer 2 overwrites the tile its finished MMAs read)
+                    TC_TRACE((t & 31) == 0, warp, k, 3 * (layer - 1) + 1);
+                    fence_async_smem();
+                    fence_before_sync();
+                    bar_arrive(&sm.ready[0]);
+                    TC_TRACE((t & 31) == 0, warp, k, 3 * (layer - 1) + 2);
+                    if (layer == 1) {                                    // under layer 2's MMAs: which tile is next, and its state on the way
+                        nxt_tile = next_tile(sm, k, tile, clc_phase, n_tiles);
+                        fetch(nxt_tile, nxt);
+                    }
+                }
+                bar_wait(&sm.done[0], phase); phase ^= 1u;
+                fence_after_sync();
+                TC_TRACE((t & 31) == 0, warp, k, 6);
+                float pre[4];
+                tmem_ld4(lane_base + col_out(0), pre);
+                TC_TRACE((t & 31) == 0, warp, k, 7);
+                if (nxt_tile != kNoTile) {                               // the next tile's observation row first: the MMA warp is waiting for it
+                    write_obs_row<FIRST, OBS>(sm.slot[0], row, nxt);
+                    fence_before_sync();
+                    bar_arrive(&sm.ready[0]);
+                    TC_TRACE((t & 31) == 0, warp, k, 8);
+                }
+                const int64_t i = (int64_t)tile * kTile + row;
+                if (i < a.n) {
+                    float act[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) act[j] = fmaf(a.out_scale, tanh_mufu(pre[j]), a.out_offset);
+                    if constexpr (ACT == 4) reinterpret_cast<float4*>(a.action)[i] = make_float4(act[0], act[1], act[2], act[3]);
+                    else if constexpr (ACT == 2) reinterpret_cast<float2*>(a.action)[i] = make_float2(act[0], act[1]);
+                    else a.action[i] = act[0];
+                }
+                tile = nxt_tile;
+            }
+        }
+    } else
     if (warp == kMmaWarp) {
         // ===== MMA issuer =====
         if ((t & 31) == 0) {
             int64_t tile[kSlots];
+            int rnd[kSlots] = {};                                                         // tiles done by the slot (trace builds)
             int layer[kSlots];                                                            // the layer to issue next
             uint32_t phase[kSlots];
 #pragma unroll
@@ -357,9 +601,11 @@ copter_mlp_policy_tc_kernel(const __grid_constant__ Args a) {
                 for (int s = 0; s < kSlots; ++s) {
                     if (layer[s] == 0) continue;
                     bar_wait(&sm.ready[s], phase[s]); phase[s] ^= 1u;
+                    TC_TRACE(true, 4, rnd[s], 3 * (layer[s] - 1));
                     issue_layer(sm, s, layer[s], tmem_base);
+                    TC_TRACE(true, 4, rnd[s], 3 * (layer[s] - 1) + 2);
                     if (layer[s] < 3) ++layer[s];
-                    else { tile[s] += stride; layer[s] = tile[s] < n_tiles ? 1 : 0; }
+                    else { tile[s] += stride; ++rnd[s]; layer[s] = tile[s] < n_tiles ? 1 : 0; }
                 }
             }
         }
@@ -375,6 +621,7 @@ copter_mlp_policy_tc_kernel(const __grid_constant__ Args a) {
             else p[0] = p[1] = p[2] = make_float4(0.f, 0.f, 0.f, 0.f);
         };
         int64_t tile[kSlots];
+        int rnd[kSlots] = {};                   // tiles done by the slot (trace builds)
         int layer[kSlots];                      // the layer whose result this thread reads next (0: the slot has run out of tiles)
         uint32_t phase[kSlots];
         float4 nxt[kSlots][3];
@@ -396,22 +643,27 @@ copter_mlp_policy_tc_kernel(const __grid_constant__ Args a) {
                 if (layer[s] == 0) continue;
                 bar_wait(&sm.done[s], phase[s]); phase[s] ^= 1u;
                 fence_after_sync();
+                TC_TRACE((t & 31) == 0, warp & 3, rnd[s], 3 * (layer[s] - 1));
                 if (layer[s] < 3) {
                     // (layer 2 overwrites the tile its finished MMAs read)
-                    hidden_epilogue<4 / kSplit>(lane_base + col_hidden(s), sm.slot[s].a, row, half * (kH / kSplit));
+                    hidden_epilogue<4 / kSplit>(lane_base + col_hidden(s), sm.slot[s].a, row, half * (kH / kSplit), rnd[s], 12 + 8 * (layer[s] - 1));
+                    TC_TRACE((t & 31) == 0, warp & 3, rnd[s], 3 * (layer[s] - 1) + 1);
                     fence_async_smem();
                     fence_before_sync();
                     bar_arrive(&sm.ready[s]);
+                    TC_TRACE((t & 31) == 0, warp & 3, rnd[s], 3 * (layer[s] - 1) + 2);
                     ++layer[s];
                 } else {
                     float pre[4] = {0.f, 0.f, 0.f, 0.f};
                     if (owner) tmem_ld4(lane_base + col_out(s), pre);
                     const int64_t i = tile[s] * kTile + row;
-                    tile[s] += stride;
+                    TC_TRACE((t & 31) == 0, warp & 3, rnd[s], 7);
+                    tile[s] += stride; ++rnd[s];
                     if (tile[s] < n_tiles) {                                       // the next tile's observation row first: the MMA warp is waiting for it
                         if (owner) write_obs_row<FIRST, OBS>(sm.slot[s], row, nxt[s]);
                         fence_before_sync();
                         bar_arrive(&sm.ready[s]);
+                        TC_TRACE((t & 31) == 0, warp & 3, rnd[s] - 1, 8);
                         layer[s] = 1;
                         fetch(tile[s] + stride, nxt[s]);
                     } else {
@@ -429,9 +681,11 @@ copter_mlp_policy_tc_kernel(const __grid_constant__ Args a) {
             }
         }
     }
+    TC_TRACE_CTA(2);
     fence_before_sync();
     __syncthreads();
     if (warp == kMmaWarp) tmem_free(tmem_base);
+    TC_TRACE_CTA(3);
 }
 
 }  // namespace tc
