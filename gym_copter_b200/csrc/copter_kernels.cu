@@ -1173,22 +1173,25 @@ copter_policy_rollout_kernel(const __grid_constant__ KParams<float> kp, const __
 //   MMA warp          layer 3 (N = 16) ...              epilogue: tcgen05.ld 4 columns, action = offset +
 //                     scale tanh(.), exploration noise, Eq. 6, one reference step, reward / done row t
 // State, flight status and the running shaping never leave the registers between the steps of the
-// horizon; a CTA walks its tiles persistently, 4 CTAs (16 epilogue warps) share an SM and fill one
-// another's MMA round trips.  The per-env arithmetic is that of the tcgen05 policy kernel followed by
+// horizon; the grid holds one CTA per tile and the resident CTAs take the pending tiles over (cluster launch
+// control, tc::next_tile), 6 CTAs (24 epilogue warps) share an SM and fill one another's MMA round trips.
+// The per-env arithmetic is that of the tcgen05 policy kernel followed by
 // copter_step_f32 (k = 1): bit-identical to that two-kernel path
-// (tests/test_gpu_rollout.py::test_fused_policy_rollout_tc_equals_policy_tc_kernel_plus_step).
+// (tests/test_gpu_rollout.py::test_fused_policy_rollout_equals_policy_kernel_plus_step[*-1]).
 // ------------------------------------------------------------------------------------------
-// Measured, 2^23 envs, horizon 16 (profiles/r2_sweep_policy_tc_ctas.txt, r2_sweep_policy_tc_rollout.txt), ms per env-step:
+// Measured, 2^23 envs, horizon 16, ms per env-step.  First version (static grid stride over the tiles, MMAs issued from
+// inside an `if (lane == 0)` branch; profiles/r2_sweep_policy_tc_ctas.txt, r2_sweep_policy_tc_rollout.txt):
 //   3 CTAs/SM 0.501, 4 CTAs/SM (94 registers) 0.444 / 0.441 (TMEM read-back double- / single-buffered in registers),
-//   5 CTAs/SM (72 registers, 16 B of spills) 0.424 / 0.424, 6 CTAs/SM (64 registers) 0.524; __maxnreg__(80): 0.54.
-//   The warp-MMA kernel above: 0.404 -- its 20 warps per SM are independent chains, here four warps share every
-//   tile barrier and every layer costs an mbarrier round trip through the MMA warp, and one env-step of a tile is a
-//   strictly serial chain (observation -> 3 layers -> action -> step -> observation): only other tiles fill the gaps
-//   and registers allow five.  So the fused rollout DEFAULTS to the warp-MMA kernel; COPTER_B200_POLICY_ROLLOUT_TC=1
-//   (or -DCOPTER_POLICY_ROLLOUT_TC=1) selects this one.  The standalone policy kernel, whose threads hold no env,
-//   is faster on tcgen05 (0.321 vs 0.359 ms) and defaults to it.
+//   5 CTAs/SM (72 registers) 0.424, 6 CTAs/SM (64 registers) 0.524 -- behind the warp-MMA kernel above (0.404).
+// The clock64 timeline of the standalone kernel (tools/microbench/policy_tc_trace.cu) showed why: the warp scheduler
+// favours the oldest CTA of an SM, so a static split leaves the youngest CTA 30 % behind and the SM idling at the end;
+// and a layer took 250-600 cycles to ISSUE.  With stolen tiles, warp-uniform issue from prebuilt descriptors and the
+// observation staging folded into the A tile (profiles/r2_sweep_policy_tc_rollout2.txt):
+//   4 CTAs/SM 0.376, 5 CTAs/SM 0.373, 6 CTAs/SM (64 registers, no spills) 0.342, 7 CTAs/SM (56 registers) 0.348
+// -- 2.45e10 env-steps/s, 15 % faster than the warp-MMA kernel, so this kernel is the default of the fused rollout
+// (COPTER_B200_POLICY_ROLLOUT_TC=0 or -DCOPTER_POLICY_ROLLOUT_TC=0 selects the warp-MMA kernel).
 #ifndef COPTER_POLICY_ROLLOUT_TC_CTAS_PER_SM
-#define COPTER_POLICY_ROLLOUT_TC_CTAS_PER_SM 5      // x 64 TMEM columns <= the SM's 512
+#define COPTER_POLICY_ROLLOUT_TC_CTAS_PER_SM 6      // x 64 TMEM columns <= the SM's 512; 64 registers, 31.7 KB of shared memory (4: 0.376, 5: 0.373, 6: 0.342, 7: 0.348 ms per env-step)
 #endif
 #ifndef COPTER_POLICY_ROLLOUT_TC_PIPELINED
 #define COPTER_POLICY_ROLLOUT_TC_PIPELINED 0        // TMEM read-back double-buffered in registers (16 more registers; no gain)
@@ -1198,9 +1201,13 @@ copter_policy_rollout_kernel(const __grid_constant__ KParams<float> kp, const __
 #if COPTER_POLICY_ROLLOUT_TC_AVAILABLE
 
 struct RolloutTcSmem {
-    tc::Smem mlp;                                   // weights, the slot's A tiles, the two mbarriers
-    float tiles[4][32 * 12];                        // per-warp observation staging (write_obs_rows)
+    tc::Smem mlp;                                   // weights, the slot's A tiles, the mbarriers
+    // The per-warp observation staging of write_obs_rows (4 x 1.5 KB) lives INSIDE the slot's hidden A tile, past the
+    // 4 KB its layer-1 alias occupies: observations are recorded at the start of an env-step and after the last one,
+    // when no MMA reads that tile and no thread writes it before layer 1 has completed (6 KB less per CTA).
+    __device__ __forceinline__ float* stage(int warp) { return reinterpret_cast<float*>(reinterpret_cast<char*>(mlp.slot[0].a) + 4096) + warp * (32 * 12); }
 };
+static_assert(4096 + 4 * 32 * 12 * sizeof(float) <= sizeof(tc::SlotSmem), "observation staging fits behind the layer-1 alias");
 
 template <int VARIANT, bool STATS>
 __global__ void __launch_bounds__(tc::kTile + 32, COPTER_POLICY_ROLLOUT_TC_CTAS_PER_SM)
@@ -1269,7 +1276,7 @@ copter_policy_rollout_tc_kernel(const __grid_constant__ KParams<float> kp, const
             Shaping<T> pre_sh = lander_shaping<T>(kp, s);
             for (int t = 0; t < a.n_steps; ++t) {
                 // the observation the policy acts on at step t
-                if (a.obs_tn && rows > 0) write_obs_rows<VARIANT, T>(a.obs_tn + (int64_t)t * a.n * O, rs.tiles[warp], lane, row0, rows, s);
+                if (a.obs_tn && rows > 0) write_obs_rows<VARIANT, T>(a.obs_tn + (int64_t)t * a.n * O, rs.stage(warp), lane, row0, rows, s);
                 tc::write_obs_row<FIRST, O>(ss, row, s);
                 tc::fence_before_sync();
                 tc::bar_arrive(&sm.ready[0]);
@@ -1339,7 +1346,7 @@ copter_policy_rollout_tc_kernel(const __grid_constant__ KParams<float> kp, const
                 if (a.done_any) a.done_any[i] = done_any ? 1 : 0;
                 if (STATS && a.ep_return) a.ep_return[i] = ret;
             }
-            if (a.obs && rows > 0) write_obs_rows<VARIANT, T>(a.obs, rs.tiles[warp], lane, row0, rows, s);
+            if (a.obs && rows > 0) write_obs_rows<VARIANT, T>(a.obs, rs.stage(warp), lane, row0, rows, s);
         }
     }
     tc::fence_before_sync();
@@ -1693,10 +1700,11 @@ int policy_tc_setting() {
     const char* e = getenv("COPTER_B200_POLICY_TC");        // read on every call: tests and A/B runs flip it inside one process
     return e ? (atoi(e) != 0) : COPTER_POLICY_TC;
 }
-// The same choice for the fused policy + step rollout (copter_policy_rollout_f32): measured, the warp-MMA kernel wins
-// there (the comment on copter_policy_rollout_tc_kernel), so it is the default.
+// The same choice for the fused policy + step rollout (copter_policy_rollout_f32).  Until the tcgen05 kernel took its
+// tiles by cluster launch control and issued its MMAs warp-uniformly the warp-MMA kernel won (0.404 vs 0.424 ms per
+// env-step at 2^23 envs); since then the tcgen05 kernel does (0.342 ms, 6 CTAs per SM), so it is the default.
 #ifndef COPTER_POLICY_ROLLOUT_TC
-#define COPTER_POLICY_ROLLOUT_TC 0
+#define COPTER_POLICY_ROLLOUT_TC 1
 #endif
 int policy_rollout_tc_setting() {
     const char* e = getenv("COPTER_B200_POLICY_ROLLOUT_TC");

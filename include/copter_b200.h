@@ -263,7 +263,7 @@ int copter_reset_force_f64(const CopterParams* p, double* out, const uint32_t* e
  * A/B runs; the defaults are the measured-faster ones): COPTER_B200_POLICY_TC=1 (default) evaluates it with
  * tcgen05.mma and accumulators in tensor memory, =0 with warp-level mma.sync; they differ in rounding
  * (bias carried as bf16 hi + lo, a quarter of the hidden tanh as FMA-pipe polynomials in the former), both
- * within 2e-2 of the fp32 network.  COPTER_B200_POLICY_ROLLOUT_TC=0 (default) / 1 makes the same choice
+ * within 2e-2 of the fp32 network.  COPTER_B200_POLICY_ROLLOUT_TC=1 (default) / 0 makes the same choice
  * for copter_policy_rollout_f32 below; each fused kernel is bit-identical to the standalone kernel of
  * its own kind followed by copter_step_f32.
  */

@@ -338,8 +338,8 @@ def test_planar_heuristics_rollout_vs_oracle(pkg, variant, source, scale, offset
 @pytest.fixture
 def policy_kernel_choice():
     """COPTER_B200_POLICY_TC selects the standalone policy kernel per call -- '1' tcgen05 / TMEM (its default),
-    '0' warp-level mma.sync -- and COPTER_B200_POLICY_ROLLOUT_TC the fused policy + step rollout kernel ('0' is its
-    default).  choose(v) sets both to the same kind."""
+    '0' warp-level mma.sync -- and COPTER_B200_POLICY_ROLLOUT_TC the fused policy + step rollout kernel (the same
+    values and default).  choose(v) sets both to the same kind."""
     import os
     names = ('COPTER_B200_POLICY_TC', 'COPTER_B200_POLICY_ROLLOUT_TC')
     old = {k: os.environ.get(k) for k in names}

@@ -1,4 +1,10 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_rollout.py tests/test_gpu_host_exact.py -m gpu -q -x -k "polic" 2>&1 | tail -5
-echo "== default"; timeout 300 python tools/policy_tc_check.py 2>&1 | head -6
-echo "== rollout tc=1"; COPTER_B200_POLICY_ROLLOUT_TC=1 timeout 300 python tools/policy_tc_check.py 2>&1 | sed -n 3p
+COPTER_HYP_EXAMPLES=600 COPTER_HYP_RANDOM=1 timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k test_random_shapes_vs_oracle 2>&1 | tail -40 > gpurun_out/hyp_many.log; tail -5 gpurun_out/hyp_many.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k test_random_shapes_vs_oracle 2>&1 | tail -3
+python - <<'PY'
+import json
+rows=[json.loads(l) for l in open('gpurun_out/r2_tracker_flips.jsonl')]
+rows=[r for r in rows if not r['fp64']]
+rows.sort(key=lambda r:-r['flips'])
+print(len(rows),'fp32 examples; top flips:',[(r['flips'],r['episodes']) for r in rows[:12]])
+PY
