@@ -239,7 +239,7 @@ COPTER_HD void reset_force(const KParams<T>& kp, uint64_t seed, uint64_t env, ui
 // ------------------------------------------------------------------------------------------
 // dynamics
 // ------------------------------------------------------------------------------------------
-template <typename L> struct Forces { L bz, u2, u3, u4, om; };   // -U1/M, U2/Ix, U3/Iy, U4/Iz, Omega
+template <typename L> struct Forces { L bz, u2, u3, u4, jxom, jyom; };   // -U1/M, U2/Ix, U3/Iy, U4/Iz, Jr/Ix Omega, Jr/Iy Omega
 
 // dynamics/__init__.py:120-132.  Always evaluated in fp64 (see header comment).
 template <typename T>
@@ -253,7 +253,10 @@ COPTER_HD Forces<T> motor_forces(const KParams<T>& kp, T m0, T m1, T m2, T m3) {
     f.u3 = (T)(kp.kP * ((q1 + q3) - (q0 + q2)));      // pitch forward (:237-241)
     f.u4 = (T)(kp.kY * (s01 - s23));                  // yaw cw (:243-247)
     // Omega: zero in the live model (:135); u4 of the UNSQUARED speeds in attic/mars (:143)
-    f.om = (T)(kp.kOm * (((double)m0 + (double)m1) - ((double)m2 + (double)m3)));
+    // the rotor-gyroscopic terms of Eq. 12 as two per-launch products (Omega is fixed while the action is): the step
+    // multiplies them by one body rate each instead of forming (Jr/I rate) Omega every substep.  Zero in the live model (:135).
+    const T om = (T)(kp.kOm * (((double)m0 + (double)m1) - ((double)m2 + (double)m3)));
+    f.jxom = kp.jx * om; f.jyom = kp.jy * om;
     return f;
 }
 
@@ -274,31 +277,31 @@ COPTER_HD void airborne_integrate(const KParams<T>& kp, L (&s)[12], const Forces
     L d1 = f.bz * ux, d3 = f.bz * uy;
     L d5 = fma_(f.bz, cph * cth, L(kp.G));                        // netz (:143)
     const L dphi = s[7], dthe = s[9], dpsi = s[11];
-    // Eq. 12 (:257-290); Omega = f.om is zero in the live model (:135)
-    L d7 = fma_(dpsi * dthe, L(kp.gphi), fma_(-(L(kp.jx) * dthe), f.om, f.u2));
-    L d9 = -fma_(dpsi * dphi, L(kp.gthe), fma_(L(kp.jy) * dphi, f.om, f.u3));
+    // Eq. 12 (:257-290); the Omega terms are zero in the live model (:135)
+    L d7 = fma_(dpsi * dthe, L(kp.gphi), fma_(-dthe, f.jxom, f.u2));
+    L d9 = -fma_(dpsi * dphi, L(kp.gthe), fma_(dphi, f.jyom, f.u3));
     L d11 = fma_(dthe * dphi, L(kp.gpsi), f.u4);
     if constexpr (PERT) {                                         // added twice (:263-287, :183); 2 p is exact
         d1 = fma_(L((T)2), p[0], d1); d3 = fma_(L((T)2), p[1], d3); d5 = fma_(L((T)2), p[2], d5);
         if constexpr (NP == 6) { d7 = fma_(L((T)2), p[3], d7); d9 = fma_(L((T)2), p[4], d9); d11 = fma_(L((T)2), p[5], d11); }
     }
-    // forward Euler, every derivative from the old state (:187)
-    const L dt = L(kp.dt), two = L((T)2);
-    const L i0 = dt * s[1], i1 = dt * d1, i2 = dt * s[3], i3 = dt * d3, i4 = dt * s[5], i5 = dt * d5;
-    const L i10 = dt * dpsi, i11 = dt * d11;
-    L a = i0 * fma_(two, s[0], i0);
-    a = fma_(i1, fma_(two, s[1], i1), a);
-    a = fma_(i2, fma_(two, s[2], i2), a);
-    a = fma_(i3, fma_(two, s[3], i3), a);
-    a = fma_(i4, fma_(two, s[4], i4), a);
-    na = fma_(i5, fma_(two, s[5], i5), a);
-    nc = fma_(i11, fma_(two, s[11], i11), i10 * fma_(two, s[10], i10));
-    s[0] = fma_(dt, s[1], s[0]);   s[1] = fma_(dt, d1, s[1]);
-    s[2] = fma_(dt, s[3], s[2]);   s[3] = fma_(dt, d3, s[3]);
-    s[4] = fma_(dt, s[5], s[4]);   s[5] = fma_(dt, d5, s[5]);
+    // forward Euler, every derivative from the old state (:187), interleaved with the step's shaping numerators per
+    // unit of dt:  a(new) - a(old) = sum_j inc_j (2 old_j + inc_j) with the Euler increment inc_j = dt ds_j taken BEFORE it
+    // is rounded into the state (shaping_delta), and 2 old_j + inc_j = old_j + new_j up to that rounding (2^-25 of the
+    // term), so each component adds ds_j old_j before and ds_j new_j after its in-place update -- two FMAs, no
+    // temporaries; the factor dt is applied once by the consumer (shaping_delta, run_reward).  A position is updated
+    // before its velocity, whose old value is its derivative.
+    const L dt = L(kp.dt);
+    L a = s[1] * s[0];  s[0] = fma_(dt, s[1], s[0]);  a = fma_(s[1], s[0], a);
+    a = fma_(d1, s[1], a);  s[1] = fma_(dt, d1, s[1]);  a = fma_(d1, s[1], a);
+    a = fma_(s[3], s[2], a);  s[2] = fma_(dt, s[3], s[2]);  a = fma_(s[3], s[2], a);
+    a = fma_(d3, s[3], a);  s[3] = fma_(dt, d3, s[3]);  a = fma_(d3, s[3], a);
+    a = fma_(s[5], s[4], a);  s[4] = fma_(dt, s[5], s[4]);  a = fma_(s[5], s[4], a);
+    a = fma_(d5, s[5], a);  s[5] = fma_(dt, d5, s[5]);  na = fma_(d5, s[5], a);
     s[6] = fma_(dt, dphi, s[6]);   s[7] = fma_(dt, d7, s[7]);
     s[8] = fma_(dt, dthe, s[8]);   s[9] = fma_(dt, d9, s[9]);
-    s[10] = fma_(dt, dpsi, s[10]); s[11] = fma_(dt, d11, s[11]);
+    L c = dpsi * s[10];  s[10] = fma_(dt, dpsi, s[10]);  c = fma_(dpsi, s[10], c);
+    c = fma_(d11, s[11], c);  s[11] = fma_(dt, d11, s[11]);  nc = fma_(d11, s[11], c);
 }
 
 // dynamics/__init__.py:139-197 for one env.  DIRECT enables the LANDED -> AIRBORNE take-off
@@ -378,8 +381,8 @@ COPTER_HD Shaping<T> lander_shaping(const KParams<T>& kp, const T (&s)[12]) {
 
 // reward = shaping(post) - shaping(pre) (envs/lander.py:58-62), evaluated without the
 // cancellation of two O(250..1e4) numbers:  sqrt(a1) - sqrt(a0) = (a1 - a0) / (sqrt(a1) + sqrt(a0))
-// with a1 - a0 = sum_j inc_j (2 pre_j + inc_j) (`na`, `nc` from airborne_integrate), where
-// inc_j = dt*ds_j is the Euler increment BEFORE it is rounded into the stored state.  In fp32
+// with a1 - a0 = sum_j inc_j (2 pre_j + inc_j) = dt sum_j ds_j (pre_j + post_j) (`na`, `nc` from airborne_integrate,
+// per unit of dt), where inc_j = dt*ds_j is the Euler increment BEFORE it is rounded into the stored state.  In fp32
 // this keeps the reward error proportional to |reward| (1e-5 measured) instead of
 // |shaping| * 2^-24 (literal subtraction, up to 1e-3) or ulp(state)/increment (differences of
 // stored states, 3e-4 at |v| ~ 270 m/s); in fp64 it agrees with the reference's literal
@@ -387,8 +390,8 @@ COPTER_HD Shaping<T> lander_shaping(const KParams<T>& kp, const T (&s)[12]) {
 template <typename T>
 COPTER_HD T shaping_delta(const KParams<T>& kp, const Shaping<T>& pre, T na, T nc, const Shaping<T>& post) {
     const T da = post.ra + pre.ra, dc = post.rc + pre.rc;
-    const T ga = da > (T)0 ? reward_div(na, da) : (T)0;
-    const T gc = dc > (T)0 ? reward_div(nc, dc) : (T)0;
+    const T ga = da > (T)0 ? reward_div(kp.dt * na, da) : (T)0;      // (na, nc: numerators per unit of dt, airborne_integrate)
+    const T gc = dc > (T)0 ? reward_div(kp.dt * nc, dc) : (T)0;
     return -(kp.xyz_pf * ga + kp.yaw_pf * gc) - (post.pen - pre.pen);
 }
 
@@ -500,8 +503,8 @@ COPTER_HD T run_reward(const KParams<T>& kp, const RewardRun<T>& run, const T (&
     if constexpr (Variant<VARIANT>::reward == REWARD_LANDER) {
         Shaping<T> end = lander_shaping<T>(kp, s);
         if (replaced) {
-            end.ra = reward_sqrt(max_t(end.ra * end.ra - na, (T)0));
-            end.rc = reward_sqrt(max_t(end.rc * end.rc - nc, (T)0));
+            end.ra = reward_sqrt(max_t(end.ra * end.ra - kp.dt * na, (T)0));
+            end.rc = reward_sqrt(max_t(end.rc * end.rc - kp.dt * nc, (T)0));
             end.pen = abs_t(dz_prev) > kp.dz_max ? kp.dz_penalty : (T)0;
         }
         const T total = shaping_delta<T>(kp, run.start, run.na, run.nc, end);

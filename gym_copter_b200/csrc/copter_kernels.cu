@@ -459,7 +459,7 @@ copter_step_pair_kernel(const __grid_constant__ KParams<float> kp, const __grid_
     }
     Forces<F2> F;
     F.bz = F2(fe[0].bz, fe[1].bz); F.u2 = F2(fe[0].u2, fe[1].u2); F.u3 = F2(fe[0].u3, fe[1].u3);
-    F.u4 = F2(fe[0].u4, fe[1].u4); F.om = F2(fe[0].om, fe[1].om);
+    F.u4 = F2(fe[0].u4, fe[1].u4); F.jxom = F2(fe[0].jxom, fe[1].jxom); F.jyom = F2(fe[0].jyom, fe[1].jyom);
 
     F2 RNA(0.0f), RNC(0.0f), NA(0.0f), NC(0.0f), DZP = S[5];
     for (int k = 0; k < a.k; ++k) {
