@@ -229,7 +229,8 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
         run_begin<T, VARIANT>(kp, run, s);
         T na = (T)0, nc = (T)0, dz_prev = s[5]; int cause = 0;
         constexpr int kUnroll = COPTER_K_UNROLL;
-        bool live = valid;                                             // has an env that has not finished in this launch
+        bool live = valid;                                             // has an env that still takes substeps in this launch
+        bool ended = false;                                            // its episode ended in this launch
 #pragma unroll kUnroll
         for (int k = 0; k < a.k; ++k) {
             if (__all_sync(0xffffffffu, !live)) break;                 // whole warp finished: idle
@@ -301,12 +302,27 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
                     run_step<T>(run, na, nc, cause);
                 }
             }
+            // A vehicle that has reached the ground finishes there: touch-down, CRASHED or LEVELING -> LANDED, done
+            // (dynamics/__init__.py:152-177, task.py:121, lander.py:64-72) -- steps of the status machine alone, no
+            // arithmetic, the state does not move.  Left to the loop, every one of them sent the WHOLE warp through the
+            // general step (5.7 of a K = 16 launch's substeps on a desynchronised batch, profiles/r2_step_kernel_k16_*).
+            // COPTER_GROUND_FF (A/B knob, off: measured slower, see copter_physics.cuh): the lane takes them here instead,
+            // alone, at once, as far as the launch's substeps reach, and is out of the loop afterwards -- finished, or
+            // parked in its ground status for the next launch.
+            if (COPTER_GROUND_FF && !Variant<VARIANT>::direct && live && !dn && on_ground<T>(s, st)) {
+                for (int kk = k + 1; kk < a.k && !dn; ++kk) {
+                    dz_prev = s[5];
+                    env_advance<T, VARIANT>(kp, s, st, steps, forces, pert, na, nc, dn, cause);
+                    run_step<T>(run, na, nc, cause);
+                }
+                live = false;
+            }
             // An env that ends idles for the rest of the launch, so everything its ending needs -- the run's reward, the
             // terminal observation, the reset -- waits until after the loop, where the lanes that did not end take the
             // same run_reward call: one converged call instead of a divergent one at every ending.
-            if (dn) { live = false; ep_cause = cause; }                // only a live lane can have ended
+            if (dn) { live = false; ended = true; ep_cause = cause; }
         }
-        done_any = valid && !live;
+        done_any = ended;
         if (valid) {
             total = run_reward<T, VARIANT>(kp, run, s, done_any ? ep_cause : 0, na, nc, dz_prev);
             if (STATS) { n_steps = run.steps; ret += total; }

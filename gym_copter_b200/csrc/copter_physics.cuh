@@ -50,6 +50,13 @@ namespace copter {
                                  // 1.444 ms, profiles/r2_ab_k_loop.txt): the general step is only ~35 % dearer than the straight-line one,
                                  // two divergent passes cost more.  Off.
 #endif
+#ifndef COPTER_GROUND_FF
+#define COPTER_GROUND_FF 0       // 1 (A/B knob): a lane that has reached the ground takes its remaining status-machine steps at once, alone, and
+                                 // leaves the loop, instead of one per substep with the whole warp in the general step (5.7 of the 16
+                                 // substeps of a K = 16 launch on a desynchronised batch).  Bit-identical, measured SLOWER (K = 16: 1.533 vs
+                                 // 1.391 ms, K = 2: 0.485 vs 0.453, profiles/r2_ab_k_loop2.txt): a lone lane's env_advance costs the
+                                 // warp almost what a general step of all 32 lanes does.  Off.
+#endif
 #ifndef COPTER_CALM_STREAK
 #define COPTER_CALM_STREAK 1     // 0 (A/B knob): every straight-line substep re-derives the ending flags and the hot test
 #endif

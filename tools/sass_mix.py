@@ -46,6 +46,20 @@ def main(path, launch=0, per=1.0):
     print('%-14s %14s %10s %8s %8s' % ('opcode', 'executed', 'per unit', 'exec %', 'stall %'))
     for op, n in ex.most_common(40):
         print('%-14s %14d %10.2f %8.2f %8.2f' % (op, n, n / per, 100.0 * n / tot, 100.0 * st[op] / max(tots, 1)))
+    # where in the kernel the instructions are executed: runs of consecutive SASS lines with the same execution count
+    # (= basic blocks executed together), largest first -- "rows a..b  xN executions  instructions  per unit  first opcodes"
+    runs, cur = [], None
+    for k, r in enumerate(b['rows']):
+        n = int(r[ce] or 0)
+        if cur is not None and cur[2] == n:
+            cur[1] = k
+        else:
+            cur = [k, k, n]
+            runs.append(cur)
+    print('# hottest straight-line regions (SASS rows, executions of the region, warp-instructions, per unit)')
+    for a0, a1, n in sorted(runs, key=lambda c: -(c[1] - c[0] + 1) * c[2])[:24]:
+        ops = ' '.join(re.sub(r'\s+', ' ', b['rows'][k][ci]).strip().split(' ')[0] for k in range(a0, min(a1 + 1, a0 + 6)))
+        print('%5d..%-5d x%-11d %13d %8.2f   %s' % (a0, a1, n, (a1 - a0 + 1) * n, (a1 - a0 + 1) * n / per, ops))
 
 
 if __name__ == '__main__':
