@@ -485,8 +485,8 @@ def main():
             pms = max_over_ranks(p0.elapsed_time(p1))
             policy_rollout = {'value': world * pn * pT * reps / (pms * 1e-3), 'unit': UNIT, 'ms_per_env_step': pms / (reps * pT),
                               'workload': 'Lander3D f32, %d envs/GPU, tanh MLP 10-64-64-4 policy + env step fused in '
-                                          'copter_policy_rollout_kernel, horizon %d per launch, reward/done rows written' % (pn, pT),
-                              'bound': 'MUFU (XU) pipe: 132 tanh per env-step'}
+                                          'copter_policy_rollout_tc_kernel (tcgen05 / TMEM; COPTER_B200_POLICY_ROLLOUT_TC=0 selects the warp-MMA kernel), horizon %d per launch, reward/done rows written' % (pn, pT),
+                              'bound': 'MUFU (XU) pipe + issue slots: 104 MUFU tanh and 32 FMA-pipe polynomial tanh per env-step'}
             del pro, penv, pol
         except Exception as e:
             policy_rollout = {'unavailable': repr(e)[:200]}
