@@ -5,9 +5,9 @@
 //   the MMA warp's elected lane issues the layer's MMAs (A = the tile's activations in shared memory,
 //   B = the layer's weights in shared memory, D = 128 x 64 fp32 in TMEM)  ->  tcgen05.commit on an mbarrier
 //   ->  every epilogue thread pulls ITS OWN row of D out of TMEM (tcgen05.ld 32x32b), applies tanh, rounds
-//   to bf16 and writes the row back to shared memory as the next layer's A operand  ->  mbarrier arrive.
+//   to 16 bits (fp16, COPTER_POLICY_TC_F16) and writes the row back to shared memory as the next layer's A operand  ->  mbarrier arrive.
 // The epilogue warps issue no MMA, no fragment loads and no bias adds (the biases ride along as one extra
-// K-step: a constant A tile of ones times a B tile holding each bias split into two bf16 halves, hi + lo,
+// K-step: a constant A tile of ones times a B tile holding each bias split into two 16-bit halves, hi + lo,
 // so the bias keeps ~16 bits).  What is left per env is 132 tanh + 66 packs + the TMEM loads; the floor is
 // the MUFU pipe, and because three quarters of the issue slots and the whole FMA pipe are free here, a
 // quarter of the hidden tanh are evaluated as a polynomial on the FMA pipe instead (COPTER_POLICY_TC_POLY).
@@ -23,6 +23,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace copter {
@@ -82,8 +83,21 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 __device__ __forceinline__ uint64_t make_desc(const void* tile, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((smem_addr(tile) >> 4) & 0x3FFFu) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
-// instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 128
-__host__ __device__ constexpr uint32_t make_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24); }
+// instruction descriptor: D = fp32, A and B of one 16-bit format, both K-major, M = 128
+// COPTER_POLICY_TC_F16 != 0: the HIDDEN activations (the A operand of layers 2 and 3) are fp16 instead of bf16 -- three
+// more significand bits for values in [-1, 1]: the error against the fp64 network halves (max 0.0046 / mean 0.0007
+// instead of 0.0092 / 0.0016 on the microbenchmark's network).  1: tanh as before (two tanh.approx.f32 or two
+// polynomials, then one cvt.rn.f16x2.f32).  2: the MUFU share as `cvt.rn.f16x2.f32` + `tanh.approx.f16x2`, two issue
+// slots per pair instead of three -- measured SLOWER (0.275 vs 0.267 ms, profiles/r2_sweep_policy_tc_f16.txt: the packed
+// tanh costs the XU pipe its two slots and then some), kept as a knob.  The observation rows (layer 1's A operand, unbounded
+// magnitudes) and layer 1's weights stay bf16; the weights and bias tiles of layers 2 and 3 are fp16 as well (an MMA
+// whose descriptor mixes an fp16 A with a bf16 B raises "illegal instruction" on sm_100a: measured).
+#ifndef COPTER_POLICY_TC_F16
+#define COPTER_POLICY_TC_F16 1
+#endif
+constexpr bool kF16 = COPTER_POLICY_TC_F16 != 0, kPackedTanh = COPTER_POLICY_TC_F16 == 2;
+// ab_bf16: format of the A and B operands (bits 7-9 and 10-12: 0 = fp16, 1 = bf16)
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool ab_bf16 = true) { return (1u << 4) | ((ab_bf16 ? 1u : 0u) << 7) | ((ab_bf16 ? 1u : 0u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24); }
 
 __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -203,12 +217,24 @@ __device__ __forceinline__ float tanh_mufu(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// two hidden activations as one fp16 pair: rounded to fp16 first, one packed MUFU instruction
+__device__ __forceinline__ uint32_t tanh_pair_f16(float lo, float hi) {
+    uint32_t h, y;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack2_f16(float lo, float hi) {
+    uint32_t h;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+    return h;
+}
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&v);
 }
 
-// this thread's hidden accumulator row (64 columns of TMEM) -> tanh -> bf16 -> its row of the A tile.
+// this thread's hidden accumulator row (64 columns of TMEM) -> tanh -> fp16 (bf16 without COPTER_POLICY_TC_F16) -> its row of the A tile.
 // TMEM is read at 64 B per clock per SM (B300_MICROARCH.md): the 32 KB of a tile's hidden accumulator
 // take as long to read (512 cycles) as its 8192 tanh take on the four MUFU pipes, so the two must
 // overlap: the load of chunk q + 1 is in flight while the tanh of chunk q issue (tcgen05.wait::ld waits
@@ -242,18 +268,30 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr_row, __nv_bfloat1
         TC_TRACE((threadIdx.x & 31) == 0, (threadIdx.x >> 5) & 3, trace_round, trace_event + 2 * q);
         constexpr int kMask = PIPELINED ? 1 : 0;
         if (PIPELINED && q + 1 < NCHUNK) tmem_ld16(taddr_row + col0 + 16 * (q + 1), r[(q + 1) & kMask]);
-        float y[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const float x = __uint_as_float(r[q & kMask][j]);
-            // the polynomial lanes are spread over the chunk so that the two pipes interleave
-            const bool poly = COPTER_POLICY_TC_POLY > 0 && ((j * COPTER_POLICY_TC_POLY) % 16) < COPTER_POLICY_TC_POLY;
-            y[j] = poly ? tanh_fma(x) : tanh_mufu(x);
-        }
-        if (!PIPELINED && q + 1 < NCHUNK) tmem_ld16(taddr_row + col0 + 16 * (q + 1), r[0]);      // r[0] is dead: lands under the packs and stores
         uint32_t w[8];
+        if constexpr (kPackedTanh) {
+            // pair p = columns 2p, 2p + 1; COPTER_POLICY_TC_POLY / 2 of the 8 pairs take the polynomial, spread over the chunk
 #pragma unroll
-        for (int j = 0; j < 8; ++j) w[j] = pack2(y[2 * j], y[2 * j + 1]);
+            for (int p = 0; p < 8; ++p) {
+                const float x0 = __uint_as_float(r[q & kMask][2 * p]), x1 = __uint_as_float(r[q & kMask][2 * p + 1]);
+                constexpr int kPolyPairs = COPTER_POLICY_TC_POLY / 2;
+                const bool poly = kPolyPairs > 0 && ((p * kPolyPairs) % 8) < kPolyPairs;
+                w[p] = poly ? pack2_f16(tanh_fma(x0), tanh_fma(x1)) : tanh_pair_f16(x0, x1);
+            }
+            if (!PIPELINED && q + 1 < NCHUNK) tmem_ld16(taddr_row + col0 + 16 * (q + 1), r[0]);      // r[0] is dead: lands under the stores
+        } else {
+            float y[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float x = __uint_as_float(r[q & kMask][j]);
+                // the polynomial lanes are spread over the chunk so that the two pipes interleave
+                const bool poly = COPTER_POLICY_TC_POLY > 0 && ((j * COPTER_POLICY_TC_POLY) % 16) < COPTER_POLICY_TC_POLY;
+                y[j] = poly ? tanh_fma(x) : tanh_mufu(x);
+            }
+            if (!PIPELINED && q + 1 < NCHUNK) tmem_ld16(taddr_row + col0 + 16 * (q + 1), r[0]);      // r[0] is dead: lands under the packs and stores
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = kF16 ? pack2_f16(y[2 * j], y[2 * j + 1]) : pack2(y[2 * j], y[2 * j + 1]);
+        }
         *reinterpret_cast<uint4*>(a_tile + canon(row, col0 + 16 * q, kH / 8)) = make_uint4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<uint4*>(a_tile + canon(row, col0 + 16 * q + 8, kH / 8)) = make_uint4(w[4], w[5], w[6], w[7]);
         TC_TRACE((threadIdx.x & 31) == 0, (threadIdx.x >> 5) & 3, trace_round, trace_event + 2 * q + 1);
@@ -269,6 +307,12 @@ __device__ __forceinline__ void load_weights(Smem& sm, const float* w1, const fl
     const __nv_bfloat16 zero = __float2bfloat16(0.0f), one = __float2bfloat16(1.0f);
     auto hi = [](float b) { return __float2bfloat16(b); };
     auto lo = [](float b) { return __float2bfloat16(b - __bfloat162float(__float2bfloat16(b))); };
+    // layers 2 and 3: the operand format of the hidden activations (fp16 bit patterns in the same 16-bit tiles when kF16)
+    auto hid = [](float v) { return kF16 ? __ushort_as_bfloat16(__half_as_ushort(__float2half_rn(v))) : __float2bfloat16(v); };
+    auto hid_lo = [](float b) {
+        return kF16 ? __ushort_as_bfloat16(__half_as_ushort(__float2half_rn(b - __half2float(__float2half_rn(b)))))
+                    : __float2bfloat16(b - __bfloat162float(__float2bfloat16(b)));
+    };
     constexpr int kWBatch = 8;
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int base = 0; base < kH * kH; base += kWBatch * nt) {
@@ -276,7 +320,7 @@ __device__ __forceinline__ void load_weights(Smem& sm, const float* w1, const fl
 #pragma unroll
         for (int u = 0; u < kWBatch; ++u) { const int e = base + u * nt + tid; v[u] = e < kH * kH ? __ldg(w2 + e) : 0.0f; }
 #pragma unroll
-        for (int u = 0; u < kWBatch; ++u) { const int e = base + u * nt + tid; if (e < kH * kH) sm.w2[canon(e / kH, e % kH, kH / 8)] = __float2bfloat16(v[u]); }
+        for (int u = 0; u < kWBatch; ++u) { const int e = base + u * nt + tid; if (e < kH * kH) sm.w2[canon(e / kH, e % kH, kH / 8)] = hid(v[u]); }
     }
     float vb1 = 0.0f, vb2 = 0.0f, vb3 = 0.0f;                    // the biases: rows tid of the bias columns / bias tiles
     if (tid < kH) { vb1 = __ldg(b1 + tid); vb2 = __ldg(b2 + tid); }
@@ -297,20 +341,20 @@ __device__ __forceinline__ void load_weights(Smem& sm, const float* w1, const fl
 #pragma unroll
         for (int u = 0; u < kWBatch; ++u) { const int e = u * nt + tid, n = e / kH; v[u] = (e < kN3 * kH && n < ACT) ? __ldg(w3 + e) : 0.0f; }
 #pragma unroll
-        for (int u = 0; u < kWBatch; ++u) { const int e = u * nt + tid; if (e < kN3 * kH) sm.w3[canon(e / kH, e % kH, kH / 8)] = __float2bfloat16(v[u]); }
+        for (int u = 0; u < kWBatch; ++u) { const int e = u * nt + tid; if (e < kN3 * kH) sm.w3[canon(e / kH, e % kH, kH / 8)] = hid(v[u]); }
     }
     if (tid < kH) {
         sm.w1[canon(tid, 14, kK1 / 8)] = hi(vb1); sm.w1[canon(tid, 15, kK1 / 8)] = lo(vb1);
 #pragma unroll
-        for (int k = 0; k < kK1; ++k) sm.b2[canon(tid, k, kK1 / 8)] = k == 0 ? hi(vb2) : (k == 1 ? lo(vb2) : zero);
+        for (int k = 0; k < kK1; ++k) sm.b2[canon(tid, k, kK1 / 8)] = k == 0 ? hid(vb2) : (k == 1 ? hid_lo(vb2) : zero);
     }
     if (tid < kN3) {
 #pragma unroll
-        for (int k = 0; k < kK1; ++k) sm.b3[canon(tid, k, kK1 / 8)] = (tid < ACT && k == 0) ? hi(vb3) : ((tid < ACT && k == 1) ? lo(vb3) : zero);
+        for (int k = 0; k < kK1; ++k) sm.b3[canon(tid, k, kK1 / 8)] = (tid < ACT && k == 0) ? hid(vb3) : ((tid < ACT && k == 1) ? hid_lo(vb3) : zero);
     }
     for (int e = tid; e < kOnesRows * kK1; e += nt) {
         const int r = e / kK1, k = e % kK1;
-        sm.ones[canon(r, k, kK1 / 8)] = k < 2 ? one : zero;
+        sm.ones[canon(r, k, kK1 / 8)] = k < 2 ? (kF16 ? __ushort_as_bfloat16((unsigned short)0x3C00u) : one) : zero;     // 1.0 in the hidden A format (fp16: 0x3C00)
     }
 }
 
@@ -324,11 +368,11 @@ struct Args {
 // One elected thread issues the MMAs of layer `layer` (1..3) of a slot and commits them to the slot's mbarrier.
 __device__ __forceinline__ void issue_layer(Smem& sm, int slot, int layer, uint32_t tmem_base) {
     constexpr uint32_t kLBO = 128, kSBO16 = (kK1 / 8) * 128, kSBO64 = (kH / 8) * 128, kStep = 256;   // one K = 16 step = two chunks
-    constexpr uint32_t idesc64 = make_idesc(kH), idesc16 = make_idesc(kN3);
+    constexpr uint32_t idesc1 = make_idesc(kH), idesc64 = make_idesc(kH, !kF16), idesc16 = make_idesc(kN3, !kF16);
     SlotSmem& ss = sm.slot[slot];
     fence_after_sync();
     if (layer == 1) {            // D[128 x 64] = A1[128 x 16] W1^T (bias in columns 14, 15)
-        mma_bf16(tmem_base + col_hidden(slot), make_desc(ss.a1(), kLBO, kSBO16), make_desc(sm.w1, kLBO, kSBO16), idesc64, 0u);
+        mma_bf16(tmem_base + col_hidden(slot), make_desc(ss.a1(), kLBO, kSBO16), make_desc(sm.w1, kLBO, kSBO16), idesc1, 0u);
     } else if (layer == 2) {     // D[128 x 64] = A[128 x 64] W2^T + ones b2^T
 #pragma unroll
         for (int j = 0; j < kH / 16; ++j)
@@ -370,11 +414,11 @@ __device__ __forceinline__ LayerDescs make_layer_descs(Smem& sm, int slot, uint3
     return d;
 }
 __device__ __forceinline__ void issue_layer_uniform(const LayerDescs& d, int layer, uint64_t* done) {     // whole warp, converged
-    constexpr uint32_t idesc64 = make_idesc(kH), idesc16 = make_idesc(kN3);
+    constexpr uint32_t idesc1 = make_idesc(kH), idesc64 = make_idesc(kH, !kF16), idesc16 = make_idesc(kN3, !kF16);
     fence_after_sync();
     if (elect_one()) {
         if (layer == 1) {
-            mma_bf16(d.d_hidden, d.a1, d.w1, idesc64, 0u);
+            mma_bf16(d.d_hidden, d.a1, d.w1, idesc1, 0u);
         } else if (layer == 2) {
 #pragma unroll
             for (int j = 0; j < kH / 16; ++j) mma_bf16(d.d_hidden, d.a[j], d.w2[j], idesc64, j > 0 ? 1u : 0u);

@@ -106,7 +106,8 @@ class FusedMLPPolicy:
     """
     The tanh MLP O -> 64 -> 64 -> A evaluated by ONE hand-written kernel (copter_policy_mlp_f32)
     straight from the env's fp32 state planes -- no observation tensor, no [N,64] intermediates in
-    HBM.  Two implementations, bf16 operands with fp32 accumulation in both: tcgen05.mma with the
+    HBM.  Two implementations, 16-bit operands (bf16; fp16 for the hidden layers of the tcgen05 kernel) with fp32
+    accumulation in both: tcgen05.mma with the
     accumulators in tensor memory, 128 envs per tile (the default; csrc/copter_policy_tc.cuh), and
     warp-level mma.sync with the activations in registers (csrc/copter_policy.cuh; selected by
     COPTER_B200_POLICY_TC=0 in the environment); FusedPolicyRollout has a fused kernel of each kind.  `net` is a torch.nn.Sequential(Linear, Tanh, Linear, Tanh, Linear,

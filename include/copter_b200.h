@@ -258,7 +258,9 @@ int copter_reset_force_f64(const CopterParams* p, double* out, const uint32_t* e
  * (observation = state components first..first+O-1 of the variant) and writing the action rows
  * copter_step_f32 consumes:  action = out_offset + out_scale * tanh(W3 tanh(W2 tanh(W1 obs + b1) + b2) + b3).
  * Weights use the torch.nn.Linear layouts W[out][in] (fp32, device memory); they and the
- * activations are rounded to bf16 for the tensor-core MMAs (fp32 accumulation).  hidden must be 64.
+ * activations are rounded to 16 bits for the tensor-core MMAs (fp32 accumulation): bf16 everywhere in the
+ * warp-MMA kernels; in the tcgen05 kernels bf16 for the observation and layer 1's weights, fp16 for the
+ * hidden activations (values in [-1, 1]) and the weights of layers 2 and 3.  hidden must be 64.
  * Two implementations of the same network exist, selectable per call through the environment (tests and
  * A/B runs; the defaults are the measured-faster ones): COPTER_B200_POLICY_TC=1 (default) evaluates it with
  * tcgen05.mma and accumulators in tensor memory, =0 with warp-level mma.sync; they differ in rounding

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-for v in fresh1 split1 fresh1split1 unroll2; do echo "$v $(COPTER_B200_LIB=tools/variants/lib_$v.so timeout 600 python tools/ab_k.py)" | tee -a gpurun_out/r2_ab_k_loop3.txt; done
-echo "default $(timeout 600 python tools/ab_k.py)" | tee -a gpurun_out/r2_ab_k_loop3.txt
+timeout 900 python -m pytest tests/test_gpu_rollout.py tests/test_gpu_host_exact.py -m gpu -q -k "polic" 2>&1 | tail -15
+echo "== default"; timeout 300 python tools/policy_tc_check.py 2>&1 | head -6
