@@ -365,7 +365,7 @@ def test_fused_mlp_policy_vs_torch_fp32(pkg, variant, kernel, policy_kernel_choi
     Tolerance: bf16 rounding of inputs, weights and two layers of activations (2^-9 relative
     each) plus tanh.approx (2^-11) on outputs in [-1, 1]."""
     policy_kernel_choice(kernel)
-    n = 4099 if kernel == '0' else 4099 + 128 * 700          # the tcgen05 kernel: more tiles than resident CTAs, ragged tail
+    n = 4099 if kernel == '0' else 4099 + 128 * 1500         # the tcgen05 kernel: more tiles (1533) than resident CTAs (148 x 7), so tiles are taken over by cluster launch control; ragged tail
     env = pkg.CopterVecEnv(variant, n, seed=3)
     env.reset()
     g = torch.Generator(device='cuda').manual_seed(0)
@@ -395,13 +395,14 @@ def test_fused_mlp_policy_vs_torch_fp32(pkg, variant, kernel, policy_kernel_choi
 
 @pytest.mark.parametrize('kernel', ['1', '0'])
 @pytest.mark.parametrize('variant,n', [('Lander3D', 4099), ('Lander2D', 1000), ('Hover3D', 257), ('Lander1D', 31), ('Takeoff', 129),
-                                       ('Lander3D', 128 * 148 * 4 + 77)])
+                                       ('Lander3D', 128 * 148 * 8 + 77)])
 def test_fused_policy_rollout_equals_policy_kernel_plus_step(pkg, variant, n, kernel, policy_kernel_choice):
     """copter_policy_rollout_f32 (policy + env step for T steps in one launch, state in
     registers) against the same network evaluated by copter_policy_mlp_f32 and stepped by
     copter_step_f32, launch by launch: done flags, recorded actions / observations, final state
     and counters are bit-identical, rewards agree to a few ulp (ragged n covers partly filled warps
-    and tiles; the last size gives the persistent CTAs of the tcgen05 kernel more than one tile each).
+    and tiles; the last size holds more tiles than the tcgen05 kernel has resident CTAs (148 x 6), so its CTAs take
+    further tiles over by cluster launch control).
     Both implementations of the network exist fused and standalone -- '1': tcgen05 / TMEM
     (copter_policy_rollout_tc_kernel vs copter_mlp_policy_tc_kernel), '0': warp-level MMAs -- and each
     fused kernel is pinned to the standalone kernel of its own kind (the two kinds round differently:
