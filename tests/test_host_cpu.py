@@ -289,3 +289,22 @@ def test_integration_md_stub_matches_the_binding():
     # every library call the stub makes exists with that name
     for fn in set(re.findall(r'lib\.(copter_[a-z0-9_]+)\(', code)):
         assert hasattr(binding.load(), fn), fn
+
+
+def test_profile_facts_come_from_the_committed_captures(tmp_path):
+    """bench.py folds numbers of the ncu captures into its line (roofline.traffic, roofline_k4 / k16).  They are
+    produced by tools/make_profile_facts.py from the condensed captures: re-deriving them from the committed
+    captures must give the committed facts file (so the line and profiles/ describe the same build)."""
+    import json
+    import subprocess
+    import sys
+    out = tmp_path / 'facts.json'
+    prof = os.path.join(ROOT, 'profiles')
+    subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'make_profile_facts.py'), prof, str(out)], check=True, capture_output=True)
+    mine, committed = json.load(open(out)), json.load(open(os.path.join(prof, 'r2_profile_facts.json')))
+    for key in ('k4_warp_instr_per_32_env_substeps', 'k16_warp_instr_per_32_env_substeps'):
+        assert abs(mine[key] - committed[key]) <= 1e-6 * committed[key], key
+    assert mine['k1_traffic']['dram_bytes_per_launch'] == committed['k1_traffic']['dram_bytes_per_launch']
+    # sanity of the numbers themselves: DRAM traffic within 5 % of the algorithmic 165 B per env, K = 16 cheaper per substep than K = 4
+    assert 0.95 <= mine['k1_traffic']['dram_bytes_per_launch'] / (165.0 * mine['k1_traffic']['envs']) <= 1.05
+    assert mine['k16_warp_instr_per_32_env_substeps'] < mine['k4_warp_instr_per_32_env_substeps']

@@ -1,6 +1,7 @@
 mkdir -p gpurun_out; rm -f gpurun_out/r2_tracker_flips.jsonl
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv | tail -1
 timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/pytest_gpu.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -4 gpurun_out/smoke.log
 # the captures first: bench.py folds their numbers (profiles/r2_profile_facts.json) into its line
 bash tools/_ncu_capture.sh step_kernel_k1 copter_step 2 1 524288 -- python tools/profile_k.py 1
 bash tools/_ncu_capture.sh step_kernel_k4 copter_step 2 1 2097152 -- python tools/profile_k.py 4
