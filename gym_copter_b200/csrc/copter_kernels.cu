@@ -1800,6 +1800,24 @@ struct Pipeline {
     cudaEvent_t start, done[8];
 };
 
+// A shard this small is a latency problem, not a bandwidth one (the single-env facade: BASELINE.json configs[0]).  When
+// every host array is page-locked and mapped into the device's address space (cudaHostAlloc / cudaHostRegister under
+// unified addressing -- what torch's pin_memory() gives), the step kernel reads the commands from and writes its
+// results to the HOST arrays directly: one launch and one stream synchronisation instead of an event, a copy in, a
+// launch, three to five copies out and their events.  The device-side action / obs / reward / done buffers of `dev`
+// are not touched on this path (state and counters are, of course).
+#ifndef COPTER_DIRECT_MAX_ENVS
+#define COPTER_DIRECT_MAX_ENVS 256
+#endif
+// device address of a page-locked, mapped host array, or nullptr (asked on every call: an address seen before may
+// belong to a different, pageable allocation by now)
+static void* mapped_device_pointer(const void* host) {
+    if (!host) return nullptr;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
+}
+
 template <typename T>
 int step_host(Pipeline* pl, const CopterParams* p, const CopterBuffers* dev, const void* h_action, float* h_obs,
               void* h_reward, uint8_t* h_done, uint8_t* h_cause, float* h_final_obs, int64_t n, int64_t env_offset, uint64_t seed, int k, int variant,
@@ -1812,6 +1830,27 @@ int step_host(Pipeline* pl, const CopterParams* p, const CopterBuffers* dev, con
     chunk = (chunk + 255) / 256 * 256;                    // keeps every sub-shard 16-byte aligned
     const int64_t stride = dev->state_stride > 0 ? dev->state_stride : n;
     cudaError_t ce;
+    if (n > 0 && n <= COPTER_DIRECT_MAX_ENVS) {           // the direct path: see mapped_device_pointer
+        const bool want_obs = h_obs && dev->obs, want_cause = h_cause && dev->cause, want_final = h_final_obs && dev->final_obs;
+        void* d_action = mapped_device_pointer(h_action);
+        void* d_reward = mapped_device_pointer(h_reward);
+        void* d_done = mapped_device_pointer(h_done);
+        void* d_obs = want_obs ? mapped_device_pointer(h_obs) : nullptr;
+        void* d_cause = want_cause ? mapped_device_pointer(h_cause) : nullptr;
+        void* d_final = want_final ? mapped_device_pointer(h_final_obs) : nullptr;
+        if (d_action && d_reward && d_done && (!want_obs || d_obs) && (!want_cause || d_cause) && (!want_final || d_final) &&
+            aligned16(d_action) && (!d_obs || aligned16(d_obs))) {
+            CopterBuffers b = *dev;
+            b.state_stride = stride;
+            b.action = d_action; b.reward = d_reward; b.done = (uint8_t*)d_done;
+            b.obs = want_obs ? (float*)d_obs : (dev->obs ? dev->obs : nullptr);
+            b.cause = want_cause ? (uint8_t*)d_cause : dev->cause;
+            b.final_obs = want_final ? (float*)d_final : dev->final_obs;
+            const int e = launch_step<T>(p, &b, n, env_offset, seed, k, variant, flags, (cudaStream_t)caller_stream);
+            if (e) return e;
+            return (int)cudaStreamSynchronize((cudaStream_t)caller_stream);
+        }
+    }
     if ((ce = cudaEventRecord(pl->start, (cudaStream_t)caller_stream)) != cudaSuccess) return (int)ce;
     for (int s = 0; s < pl->n_streams; ++s)
         if ((ce = cudaStreamWaitEvent(pl->streams[s], pl->start, 0)) != cudaSuccess) return (int)ce;

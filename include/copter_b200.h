@@ -315,6 +315,11 @@ int copter_policy_rollout_f32(const CopterParams* p, const CopterBuffers* b, con
  * page-locked for the copies to be asynchronous.  Work is ordered after `stream`; the call
  * returns when all chunks have landed in the host arrays.  h_cause / h_final_obs (nullable)
  * receive dev->cause / dev->final_obs when those device buffers are given.
+ * Shards of at most 256 envs (the single-env facade) whose host arrays are all page-locked and mapped
+ * (cudaHostAlloc / cudaHostRegister under unified addressing) take a direct path: ONE launch whose kernel
+ * reads the commands from and writes obs / reward / done / cause / final_obs to the host arrays themselves,
+ * then one stream synchronisation; the device-side action / obs / reward / done buffers of `dev` are not
+ * touched on that path.
  */
 int copter_pipeline_create(int n_streams, void** out_pipeline);      /* 1..8 streams */
 int copter_pipeline_destroy(void* pipeline);

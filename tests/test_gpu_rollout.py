@@ -148,6 +148,35 @@ def test_step_host_matches_device_step(pkg):
     e1.close()
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+@pytest.mark.parametrize('n', [1, 37, 256])
+def test_step_host_direct_path_matches_device_step(pkg, n, dtype):
+    """Shards of at most 256 envs with page-locked host arrays: the step kernel reads the commands from and writes
+    observation / reward / done / cause / terminal observation to the HOST arrays themselves (one launch, one
+    synchronisation: the single-env facade's path).  Same numbers as the device-tensor step, K = 1 and K = 3."""
+    rng = np.random.default_rng(n)
+    for k in (1, 3):
+        kw = dict(seed=6, dtype=dtype, k_substeps=k, report_cause=True, keep_final_obs=True, max_steps=40)
+        e1, e2 = pkg.CopterVecEnv('Lander3D', n, **kw), pkg.CopterVecEnv('Lander3D', n, **kw)
+        e1.reset(); e2.reset()
+        npdt = np.float32 if dtype == torch.float32 else np.float64
+        ended = 0
+        for t in range(60):
+            a = (1.625e-2 * (1 + 0.5 * rng.standard_normal((n, 4)))).astype(npdt)
+            if t % 5 == 4:
+                a[::2] = rng.uniform(-1, 1, (len(a[::2]), 4)).astype(npdt)
+            obs, r, term, trunc, info = e1.step_host(a)
+            o2, r2, t2, tr2, i2 = e2.step(torch.as_tensor(a))
+            assert np.array_equal(obs, o2.cpu().numpy()) and np.array_equal(r, r2.cpu().numpy())
+            assert np.array_equal(term | trunc, (t2 | tr2).cpu().numpy()) and np.array_equal(trunc, tr2.cpu().numpy())
+            assert np.array_equal(info['cause'], i2['cause'].cpu().numpy())
+            done = term | trunc
+            assert np.array_equal(info['final_obs'][done], i2['final_obs'].cpu().numpy()[done])
+            ended += int(done.sum())
+        assert ended > 0 and torch.equal(e1.state, e2.state) and torch.equal(e1.steps, e2.steps)
+        e1.close()
+
+
 def test_csv_export_matches_lander_py_format(pkg, tmp_path):
     env = pkg.make('gym_copter:Lander-v0')
     obs, _ = env.reset(force=[1.0, 2.0, 3.0])
