@@ -1800,14 +1800,17 @@ struct Pipeline {
     cudaEvent_t start, done[8];
 };
 
-// A shard this small is a latency problem, not a bandwidth one (the single-env facade: BASELINE.json configs[0]).  When
+// A small shard is a latency problem, not a bandwidth one (the single-env facade: BASELINE.json configs[0]).  When
 // every host array is page-locked and mapped into the device's address space (cudaHostAlloc / cudaHostRegister under
 // unified addressing -- what torch's pin_memory() gives), the step kernel reads the commands from and writes its
 // results to the HOST arrays directly: one launch and one stream synchronisation instead of an event, a copy in, a
 // launch, three to five copies out and their events.  The device-side action / obs / reward / done buffers of `dev`
-// are not touched on this path (state and counters are, of course).
+// are not touched on this path (state and counters are, of course).  Measured (profiles/r2_direct_path_sweep.txt, us per
+// step_host call, copy pipeline -> direct): 1 env 37 -> 21, 4096 envs 50 -> 27, 65 536 envs 168 -> 128, 2^20 envs 2201 ->
+// 1999, 2^22 level, 2^24 33.2 -> 33.9 ms (the chunked pipeline wins once the transfers dominate).  The limit is
+// COPTER_DIRECT_MAX_ENVS, or COPTER_B200_DIRECT_MAX_ENVS in the environment (read once; 0 switches the path off).
 #ifndef COPTER_DIRECT_MAX_ENVS
-#define COPTER_DIRECT_MAX_ENVS 256
+#define COPTER_DIRECT_MAX_ENVS 65536
 #endif
 // device address of a page-locked, mapped host array, or nullptr (asked on every call: an address seen before may
 // belong to a different, pageable allocation by now)
@@ -1830,7 +1833,8 @@ int step_host(Pipeline* pl, const CopterParams* p, const CopterBuffers* dev, con
     chunk = (chunk + 255) / 256 * 256;                    // keeps every sub-shard 16-byte aligned
     const int64_t stride = dev->state_stride > 0 ? dev->state_stride : n;
     cudaError_t ce;
-    if (n > 0 && n <= COPTER_DIRECT_MAX_ENVS) {           // the direct path: see mapped_device_pointer
+    static const int64_t direct_max = [] { const char* e = getenv("COPTER_B200_DIRECT_MAX_ENVS"); return e ? (int64_t)atoll(e) : (int64_t)COPTER_DIRECT_MAX_ENVS; }();
+    if (n > 0 && n <= direct_max) {                       // the direct path: see mapped_device_pointer
         const bool want_obs = h_obs && dev->obs, want_cause = h_cause && dev->cause, want_final = h_final_obs && dev->final_obs;
         void* d_action = mapped_device_pointer(h_action);
         void* d_reward = mapped_device_pointer(h_reward);

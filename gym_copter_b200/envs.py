@@ -353,7 +353,10 @@ class CopterVecEnv:
         copy); returns numpy (obs, reward, terminated, truncated, info) -- views of the
         page-locked buffers, valid until the next call.  The host->device copy of the actions,
         the step kernel and the device->host copies of obs/reward/done are chunked and
-        pipelined over `n_streams` CUDA streams inside copter_step_host_*.
+        pipelined over `n_streams` CUDA streams inside copter_step_host_*.  Shards of at most 65 536 envs take a
+        direct path instead: one launch whose kernel reads the commands from and writes its results to the
+        page-locked host buffers themselves (the env's device-side obs / reward / done tensors are then not
+        refreshed by this call; state and counters are).
         """
         if not self._is_reset:
             raise CopterError('step() called before reset()')

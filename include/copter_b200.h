@@ -315,7 +315,8 @@ int copter_policy_rollout_f32(const CopterParams* p, const CopterBuffers* b, con
  * page-locked for the copies to be asynchronous.  Work is ordered after `stream`; the call
  * returns when all chunks have landed in the host arrays.  h_cause / h_final_obs (nullable)
  * receive dev->cause / dev->final_obs when those device buffers are given.
- * Shards of at most 256 envs (the single-env facade) whose host arrays are all page-locked and mapped
+ * Shards of at most 65 536 envs (COPTER_B200_DIRECT_MAX_ENVS in the environment overrides the limit, 0 switches
+ * the path off) whose host arrays are all page-locked and mapped
  * (cudaHostAlloc / cudaHostRegister under unified addressing) take a direct path: ONE launch whose kernel
  * reads the commands from and writes obs / reward / done / cause / final_obs to the host arrays themselves,
  * then one stream synchronisation; the device-side action / obs / reward / done buffers of `dev` are not

@@ -130,7 +130,7 @@ def test_policy_rollout_graph_equals_eager(pkg):
 
 
 def test_step_host_matches_device_step(pkg):
-    n = 70000
+    n = 70000            # above the direct path's limit: the chunked copy pipeline
     rng = np.random.default_rng(0)
     e1 = pkg.CopterVecEnv('Lander3D', n, seed=4, track_stats=True)
     e2 = pkg.CopterVecEnv('Lander3D', n, seed=4, track_stats=True)
@@ -149,9 +149,9 @@ def test_step_host_matches_device_step(pkg):
 
 
 @pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
-@pytest.mark.parametrize('n', [1, 37, 256])
+@pytest.mark.parametrize('n', [1, 37, 256, 5000])
 def test_step_host_direct_path_matches_device_step(pkg, n, dtype):
-    """Shards of at most 256 envs with page-locked host arrays: the step kernel reads the commands from and writes
+    """Shards of at most 65 536 envs with page-locked host arrays: the step kernel reads the commands from and writes
     observation / reward / done / cause / terminal observation to the HOST arrays themselves (one launch, one
     synchronisation: the single-env facade's path).  Same numbers as the device-tensor step, K = 1 and K = 3."""
     rng = np.random.default_rng(n)
