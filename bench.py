@@ -492,6 +492,31 @@ def main():
             policy_rollout = {'unavailable': repr(e)[:200]}
         torch.cuda.empty_cache()
 
+    # ---- configs[0] side measurement: the reference's own call shape, ONE env, host arrays in and out ---
+    single_env = None
+    if not args.no_extras and k == 1 and rank == 0:
+        try:
+            import numpy as np
+            senv = g.make('gym_copter:Lander-v0')
+            senv.reset()
+            sa, s_steps, s_eps = 0.0166 * np.ones(4), 0, 0
+            for _ in range(200):
+                if senv.step(sa)[2]:
+                    senv.reset()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            while s_steps < 3000:
+                s_steps += 1
+                if senv.step(sa)[2]:
+                    senv.reset(); s_eps += 1
+            el = time.perf_counter() - t0
+            single_env = {'us_per_step': el / s_steps * 1e6, 'steps_per_s': s_steps / el, 'episodes': s_eps,
+                          'workload': "make('gym_copter:Lander-v0'): one fp64 env, lander.py's constant command, reset() on done, wall clock "
+                                      'around env.step() (numpy in, numpy out: copter_step_host_f64, direct path)'}
+            senv.close()
+        except Exception as e:
+            single_env = {'unavailable': repr(e)[:200]}
+
     # ---- end to end through the host-array API -------------------------------------------
     env = g.CopterVecEnv(args.variant, n, dtype=dtype, seed=2026, env_offset=rank * n, k_substeps=k, auto_reset=True)
     actions = make_actions(torch, args.stream, n, A, 1, dtype, dev, 1234 + rank)
@@ -609,6 +634,7 @@ def main():
             'streams': streams,
             'fused_substeps': extras,
             'policy_rollout': policy_rollout,
+            'single_env': single_env,
         }
         line.update(roof_k)
         json_out.write(json.dumps(line) + '\n')
