@@ -649,25 +649,10 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_global
 
 // Cluster launch control (sm_100): a running CTA cancels a CTA of the grid that has not been launched
 // yet and takes over its block index -- dynamic tile scheduling done by the hardware, no counter in
-// memory.  The 16-byte response lands in shared memory through an mbarrier like a TMA copy.
-__device__ __forceinline__ void clc_try_cancel(void* resp16, uint64_t* bar) {
-    mbar_expect_tx(bar, 16);
-    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
-                 :: "r"(smem_u32(resp16)), "r"(smem_u32(bar)) : "memory");
-}
-// returns the cancelled CTA's blockIdx.x, or 0xFFFFFFFF when nothing was left to cancel
-__device__ __forceinline__ uint32_t clc_response(const void* resp16) {
-    uint32_t ok, x;
-    asm volatile("{\n\t.reg .b128 r;\n\t.reg .pred p;\n\t.reg .b64 lo, hi;\n\t.reg .b32 y, z, w;\n\t"
-                 "ld.shared.v2.b64 {lo, hi}, [%2];\n\t"
-                 "mov.b128 r, {lo, hi};\n\t"
-                 "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p, r;\n\t"
-                 "selp.u32 %0, 1, 0, p;\n\t"
-                 "mov.u32 %1, 0;\n\t"
-                 "@p clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%1, y, z, w}, r;\n\t}"
-                 : "=r"(ok), "=r"(x) : "r"(smem_u32(resp16)) : "memory");
-    return ok ? x : 0xFFFFFFFFu;
-}
+// memory.  The 16-byte response lands in shared memory through an mbarrier like a TMA copy.  (One definition,
+// shared with the tcgen05 policy kernels: copter_policy_tc.cuh.)
+using tc::clc_try_cancel;       // arrive.expect_tx(16) on the barrier + clusterlaunchcontrol.try_cancel into resp16
+using tc::clc_response;         // the cancelled CTA's blockIdx.x, or 0xFFFFFFFF when nothing was left to cancel
 
 #ifndef COPTER_TMA_CLC
 #define COPTER_TMA_CLC 1          // 1: one CTA per tile in the grid, running CTAs steal the pending ones (cluster launch
