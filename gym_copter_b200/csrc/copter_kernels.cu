@@ -310,9 +310,11 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
             // alone, at once, as far as the launch's substeps reach, and is out of the loop afterwards -- finished, or
             // parked in its ground status for the next launch.
             if (COPTER_GROUND_FF && !Variant<VARIANT>::direct && live && !dn && on_ground<T>(s, st)) {
+                if (COPTER_GROUND_FF == 2) { na = (T)0; nc = (T)0; }        // (what env_advance reports for a step that moves nothing)
                 for (int kk = k + 1; kk < a.k && !dn; ++kk) {
                     dz_prev = s[5];
-                    env_advance<T, VARIANT>(kp, s, st, steps, forces, pert, na, nc, dn, cause);
+                    if (COPTER_GROUND_FF == 2) ground_advance<T, VARIANT>(kp, s, st, steps, dn, cause);
+                    else env_advance<T, VARIANT>(kp, s, st, steps, forces, pert, na, nc, dn, cause);
                     run_step<T>(run, na, nc, cause);
                 }
                 live = false;

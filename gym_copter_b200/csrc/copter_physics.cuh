@@ -55,7 +55,10 @@ namespace copter {
                                  // leaves the loop, instead of one per substep with the whole warp in the general step (5.7 of the 16
                                  // substeps of a K = 16 launch on a desynchronised batch).  Bit-identical, measured SLOWER (K = 16: 1.533 vs
                                  // 1.391 ms, K = 2: 0.485 vs 0.453, profiles/r2_ab_k_loop2.txt): a lone lane's env_advance costs the
-                                 // warp almost what a general step of all 32 lanes does.  Off.
+                                 // warp almost what a general step of all 32 lanes does.  2: the same with the status machine written
+                                 // out for a grounded vehicle (ground_advance, ~25 instructions per step): 1.462 vs 1.392 ms, K = 2 0.479
+                                 // vs 0.466 (profiles/r2_ab_k_loop4.txt) -- still slower, and already at K = 2 where hardly any vehicle
+                                 // lands: the extra block costs the loop more than the general steps it saves.  Off.
 #endif
 #ifndef COPTER_CALM_STREAK
 #define COPTER_CALM_STREAK 1     // 0 (A/B knob): every straight-line substep re-derives the ending flags and the hot test
@@ -183,6 +186,35 @@ __device__ __forceinline__ bool airborne_hot(const T (&s)[12], int st, int steps
 template <typename T>
 __device__ __forceinline__ bool on_ground(const T (&s)[12], int st) {
     return st != ST_AIRBORNE || (s[4] > (T)0 && s[5] > (T)0);
+}
+// env_advance for such a vehicle, written out: dynamics_update (dynamics/__init__.py:147-177) is then the status
+// machine alone and _Task.step's tests (task.py:111-130, lander.py:64-72) follow unchanged.  Not for the `direct`
+// variants (a LANDED vehicle can take off there).  COPTER_GROUND_FF = 2 steps a grounded lane with this instead of
+// the general env_advance.
+template <typename T, int VARIANT>
+__device__ __forceinline__ void ground_advance(const KParams<T>& kp, T (&s)[12], int& st, int& steps, bool& done, int& cause) {
+    using V = Variant<VARIANT>;
+    const int st0 = st;                                            // task.py:81 stale status
+    if (st0 == ST_LEVELING) { s[6] = (T)0; s[8] = (T)0; st = ST_LANDED; }                                  // :152-156
+    else if (st0 == ST_AIRBORNE)                                   // touching the ground: :162-177 (early return, nothing moves)
+        st = (s[5] > kp.lvy || abs_t(s[3]) > kp.lvx || abs_t(s[6]) > kp.lang) ? ST_CRASHED : ST_LEVELING;
+    cause = 0;
+    done = false;
+    if (V::lander && st0 == ST_LANDED) {                           // lander.py:64-72
+        done = true; cause |= CAUSE_LANDED;
+        if (sqrt_t(s[0] * s[0] + s[2] * s[2]) < kp.target_radius) cause |= CAUSE_BONUS;
+    }
+    if (abs_t(s[0]) >= kp.bounds || abs_t(s[2]) >= kp.bounds) {    // task.py:111
+        done = true; cause |= CAUSE_OOB;
+    } else if (abs_t(s[6]) >= kp.max_angle || abs_t(s[8]) >= kp.max_angle) {   // :116
+        done = true; cause |= CAUSE_ANGLE;
+    } else if (st0 == ST_CRASHED) {                                // :121
+        done = true;
+    }
+    if (st0 == ST_CRASHED) cause |= CAUSE_CRASHED;
+    if (steps == kp.max_steps) { done = true; cause |= CAUSE_TIMEOUT; }          // :128
+    steps = steps < kp.steps_cap ? steps + 1 : kp.steps_cap;       // :130
+    if (!done) cause = 0;
 }
 // the same without the "past the first step" condition: the precondition of airborne_arith_pert()
 template <typename T>

@@ -31,6 +31,7 @@ COMBOS = [
     ['-DCOPTER_POLICY_TC_POLY=8', '-DCOPTER_POLICY_ROLLOUT_TC_CTAS_PER_SM=3', '-DCOPTER_POLICY_TC=0'],
     ['-DCOPTER_POLICY_TC_CLC=0', '-DCOPTER_POLICY_TC_ONES_ROWS=128', '-DCOPTER_POLICY_TC_CTAS_PER_SM=5', '-DCOPTER_POLICY_ROLLOUT_TC=0'],
     ['-DCOPTER_GROUND_FF=1', '-DCOPTER_GROUND_SPLIT=1', '-DCOPTER_FRESH_FAST=1', '-DCOPTER_POLICY_TC_WAIT=2'],
+    ['-DCOPTER_GROUND_FF=2', '-DCOPTER_POLICY_TC_F16=2', '-DCOPTER_POLICY_TC_POLY=6'],
 ]
 
 
