@@ -177,6 +177,32 @@ def test_step_host_direct_path_matches_device_step(pkg, n, dtype):
         e1.close()
 
 
+def test_step_host_with_pageable_arrays_takes_the_copy_pipeline(pkg):
+    """A caller of the C ABI whose host arrays are NOT page-locked (plain numpy): the direct path must not be taken
+    (the kernel cannot address pageable memory) -- the call falls back to the copy pipeline and gives the same numbers."""
+    import ctypes as C
+    from gym_copter_b200 import _lib
+    n = 64
+    e1, e2 = pkg.CopterVecEnv('Lander3D', n, seed=9), pkg.CopterVecEnv('Lander3D', n, seed=9)
+    e1.reset(); e2.reset()
+    e1.host_buffers()                                   # creates the pipeline-side state lazily, as step_host would
+    pipe = C.c_void_p()
+    _lib.check(e1._lib.copter_pipeline_create(2, C.byref(pipe)), 'copter_pipeline_create')
+    rng = np.random.default_rng(3)
+    obs, rew, done = np.zeros((n, 10), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8)     # pageable
+    for t in range(20):
+        a = (1.625e-2 * (1 + 0.3 * rng.standard_normal((n, 4)))).astype(np.float32)
+        b = e1._buffers(e1._action, e1._force)
+        rc = e1._lib.copter_step_host_f32(pipe, C.byref(e1.params), C.byref(b), a.ctypes.data, obs.ctypes.data, rew.ctypes.data,
+                                          done.ctypes.data, None, None, n, 0, e1.seed_value, 1, 0, _lib.F_AUTO_RESET, 1 << 20,
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, rc
+        o2, r2, t2, _, _ = e2.step(torch.as_tensor(a))
+        assert np.array_equal(obs, o2.cpu().numpy()) and np.array_equal(rew, r2.cpu().numpy()) and np.array_equal(done.astype(bool), t2.cpu().numpy())
+    assert torch.equal(e1.state, e2.state)
+    e1._lib.copter_pipeline_destroy(pipe)
+
+
 def test_csv_export_matches_lander_py_format(pkg, tmp_path):
     env = pkg.make('gym_copter:Lander-v0')
     obs, _ = env.reset(force=[1.0, 2.0, 3.0])
