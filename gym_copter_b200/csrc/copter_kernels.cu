@@ -358,7 +358,7 @@ __device__ __forceinline__ void step_tile(const KParams<T>& kp, const StepArgs<T
 }
 
 template <typename T, int VARIANT, bool STATS>
-__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? COPTER_F32_CTAS_PER_SM : 2)
+__global__ void __launch_bounds__(kBlock, sizeof(T) == 4 ? COPTER_STEP_CTAS_PER_SM : 2)
 copter_step_kernel(const __grid_constant__ KParams<T> kp, const __grid_constant__ StepArgs<T> a) {
     constexpr int O = Variant<VARIANT>::O, A = Variant<VARIANT>::A;
     __shared__ __align__(16) float tiles[kWarpsPerBlock][32 * O];

@@ -19,7 +19,14 @@
 namespace copter {
 
 #ifndef COPTER_F32_CTAS_PER_SM
-#define COPTER_F32_CTAS_PER_SM 8  // x 128 threads: 1024 resident envs per SM at <= 64 registers
+#define COPTER_F32_CTAS_PER_SM 8  // x 128 threads: 1024 resident envs per SM at <= 64 registers (the drawn-command rollout kernels)
+#endif
+// The step kernel itself: 10 CTAs per SM (<= 48 registers, which the fp32 step kernels reach without spills since the
+// two-FMA shaping numerators; at 8 the compiler took 56 and the hardware placed 9).  HBM-bound launches do not care
+// (K = 1: 0.4135 vs 0.4134 ms); the issue-bound ones gain a little from the extra warps (K = 8 0.834 -> 0.818, K = 16
+// 1.390 -> 1.359 ms, profiles/r2_ab_k_loop5.txt; 9: 1.373, 7: 1.404; 11+ spill).
+#ifndef COPTER_STEP_CTAS_PER_SM
+#define COPTER_STEP_CTAS_PER_SM 10
 #endif
 
 #ifndef COPTER_BLOCK
